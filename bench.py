@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on its configuration, B200 path vs the reference path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3]
+
+Workload at N=1 (and per rank at N>1, weak scaling): BASELINE.json configs[1] --
+Fisher-vector encode, GMM K=256 (diag) on SIFT-PCA-64 (bundled
+gmm_k256_sift_pca + pca_k256_sift_f2), 8,189 synthetic images x 2,000 SIFT-like 128-D fp32
+descriptors.  One step = one pass of the encode path over that batch.
+
+value  : images/s, whole job, descriptors already resident in HBM, timed with CUDA events
+         on the launching stream, max over ranks.  Inputs (8.4 GB) >> L2 (126 MB), so no
+         explicit flush is needed between steps.
+e2e    : the same through the public API with HOST buffers (pinned): every step copies the
+         descriptors H2D and the encodings D2H inside the timed region.
+roofline / cpu_baseline: see DESIGN.md "Measurement".
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "python-visual-similarity_b200"))
+
+METRIC = "fv_encode_images_per_s_k256"
+UNIT = "images/s"
+WORKLOADS = {
+    # name: (n_images, T, d_in, description)
+    "c2": (8189, 2000, 128, "FV encode, GMM K=256 diag, SIFT-128 -> PCA-64, 8189 images x 2000 descriptors"),
+    "c3": (100000, 196, 514, "VLAD encode, K=256, VGG16 conv 514-D, 196 descriptors/image, 100k images"),
+}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def sift_like_host(rng, rows, d=128):
+    return np.floor(np.clip(np.abs(rng.normal(0, 40, (rows, d))), 0, 255)).astype(np.float32)
+
+
+# --------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference's CPU path
+# --------------------------------------------------------------------------------------
+def oracle_fv_rate(descs, seconds_hint=None):
+    """images/s of the NumPy/fp64 restatement of FisherVectorEncoder.encode on this host."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pvs_oracle as O
+    wdir = os.path.join(ROOT, "python-visual-similarity_b200", "pyvisim_b200", "res", "model_files")
+    g = np.load(os.path.join(wdir, "gmm_k256_sift_pca.npz"))
+    p = np.load(os.path.join(wdir, "pca_k256_sift_f2.npz"))
+    t0 = time.perf_counter()
+    out = O.fv_encode(descs, g["weights"], g["means"], g["covariances"], g["precisions_cholesky"],
+                      pca=(p["components"], p["mean"]))
+    dt = time.perf_counter() - t0
+    return len(descs) / dt, dt, out
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_img, T, d_in, desc = WORKLOADS["c2"]
+    sample = 32
+    rng = np.random.default_rng(0)
+    descs = [sift_like_host(rng, T, d_in) for _ in range(sample)]
+    for _ in range(args.warmup):
+        oracle_fv_rate(descs[:4])
+    times = []
+    for _ in range(args.steps):
+        _, dt, _ = oracle_fv_rate(descs)
+        times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = sample / (ms / 1e3)
+    cores = os.cpu_count()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "sample": f"{sample} images x {T} descriptors per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} of {n_img} images per step, NumPy/OpenBLAS default threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------
+# clocks sampler (pynvml), runs during the timed region
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.ok, self._stop = [], set(), False, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.max = None
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def __enter__(self):
+        if self.ok:
+            self.t = threading.Thread(target=self._loop, daemon=True)
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self.ok:
+            self.t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max, "reasons": sorted(self.reasons)}
+
+
+# --------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from pyvisim_b200 import _native as N
+    from pyvisim_b200.encoders import FisherVectorEncoder, GMMWeights
+    from pyvisim_b200.features import Descriptors
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n_img, T, d_in, desc = WORKLOADS["c2"]
+    if args.images:
+        n_img = args.images
+    rows = n_img * T
+    enc = FisherVectorEncoder(feature_extractor=Descriptors(d_in), weights=GMMWeights.OXFORD102_K256_SIFT_PCA,
+                              output_dtype=np.float32)
+    K, D = enc.clustering_model.means_.shape
+    out_dim = 2 * K * D + K
+
+    # synthetic SIFT-like descriptors, generated on the device (seeded per rank)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x = torch.empty((rows, d_in), dtype=torch.float32, device=dev)
+    step_rows = 1 << 20
+    for r in range(0, rows, step_rows):
+        blk = x[r:r + step_rows]
+        blk.normal_(0, 40, generator=gen)
+        blk.abs_().clamp_(0, 255).floor_()
+    offsets = torch.arange(n_img + 1, dtype=torch.int64) * T
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        return enc.encode_descriptors(x, offsets, images_per_call=args.images_per_call)
+
+    for _ in range(args.warmup):
+        out = step()
+    barrier()
+    N.lib().pvs_launch_count_reset()
+    N.profile_enable(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            out = step()
+        ev1.record()
+        barrier()
+    total_ms = ev0.elapsed_time(ev1)
+    launches = int(N.lib().pvs_launch_count())
+    stages = N.profile_read()
+    N.profile_enable(False)
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * n_img / (ms_per_step / 1e3)
+    checksum = float(out.double().sum().item())
+
+    # ---- e2e: host (pinned) in, host (pinned) out, through encode_descriptors ------------
+    e2e_images = n_img if args.e2e_images <= 0 else min(n_img, args.e2e_images)
+    e_rows = e2e_images * T
+    x_host = torch.empty((e_rows, d_in), dtype=torch.float32, pin_memory=True)
+    x_host.copy_(x[:e_rows])
+    out_host = torch.empty((e2e_images, out_dim), dtype=torch.float32, pin_memory=True)
+    x_np, out_np = x_host.numpy(), out_host.numpy()
+    offs_np = (np.arange(e2e_images + 1, dtype=np.int64) * T)
+    e2e_steps = max(1, min(args.steps, 3))
+    enc.encode_descriptors(x_np, offs_np, out=out_np)                      # warm-up (arena allocation)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        enc.encode_descriptors(x_np, offs_np, out=out_np)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * e2e_images / e2e_s
+    e2e_ok = bool(np.allclose(out_np[:4], out[:4].cpu().numpy(), atol=1e-6))
+
+    # ---- roofline of the dominant kernel (live CUDA-event stage times) -------------------
+    pk = peaks()
+    dominant = max(stages.items(), key=lambda kv: kv[1][0]) if stages else (None, (0.0, 0))
+    flops_per_image = {"pca_project": 2 * T * d_in * D, "gmm_logits": 2 * T * K * 2 * D,
+                       "fv_stats": 2 * T * K * 2 * D, "tc_fv_posterior": 2 * T * K * 2 * D,
+                       "tc_fv_stats": 2 * T * K * 2 * D}
+    bytes_per_image = {"gmm_softmax": 2 * T * K * 4, "fv_finalize": K * (2 * D + 1) * 4 + out_dim * 4 * 3}
+    roofline = None
+    if dominant[0]:
+        name, (ms, n) = dominant
+        per_launch_ms = ms / n
+        imgs_per_launch = n_img * args.steps / n
+        if name in flops_per_image:
+            ach = flops_per_image[name] * imgs_per_launch / (per_launch_ms / 1e3) / 1e12
+            peak = pk["bf16_tflops_sustained"]
+            roofline = {"bound": "tensor", "kernel": name, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                        "frac": ach / peak, "traffic": None,
+                        "peak_source": f"bf16 dense sustained, {pk['source']} (kernel runs inside a long step)"}
+        else:
+            ach = bytes_per_image.get(name, 0) * imgs_per_launch / (per_launch_ms / 1e3) / 1e9
+            roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                        "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": f"hbm copy, {pk['source']}"}
+        roofline["kernel_ms_per_launch"] = per_launch_ms
+        roofline["kernel_share_of_step"] = ms / total_ms
+    # whole-path HBM roofline (algorithmic bytes per image: descriptors in + encoding out)
+    alg_bytes = T * d_in * 4 + out_dim * 4
+    path_gbs = alg_bytes * n_img / (ms_per_step / 1e3) / 1e9
+
+    # ---- CPU baseline: oracle port on a bounded sample (rank 0, N=1 only) ------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sample = args.cpu_sample
+        descs = [x[i * T:(i + 1) * T].cpu().numpy() for i in range(sample)]
+        rate, dt, ref_out = oracle_fv_rate(descs)
+        err = float(np.linalg.norm(out[:sample].cpu().numpy().astype(np.float64) - ref_out) / np.linalg.norm(ref_out))
+        cpu = {"value": rate, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+               "sample": f"first {sample} of {n_img} images, {dt:.1f} s, NumPy/OpenBLAS default threads",
+               "parity_rel_l2_vs_gpu": err}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "images_per_gpu": n_img, "descriptors_per_image": T, "d_in": d_in,
+                       "k": K, "d": D, "weights": "bundled gmm_k256_sift_pca + pca_k256_sift_f2",
+                       "l2": "inputs (8.4 GB/GPU) larger than L2, no flush", "parallelism": f"dp{world} (images sharded, no collective)",
+                       "images_per_call": args.images_per_call},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(e_rows * d_in * 4 + (e2e_images + 1) * 8),
+                    "d2h_bytes_per_step": int(e2e_images * out_dim * 4), "images": e2e_images,
+                    "matches_device_path": e2e_ok},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "path_hbm": {"algorithmic_bytes_per_image": alg_bytes, "achieved_gbs": path_gbs,
+                         "frac_of_hbm_peak": path_gbs / pk["hbm_gbs"]},
+            "stages_ms": {k: round(v[0] / args.steps, 4) for k, v in stages.items()},
+            "cpu_baseline": cpu,
+            "clocks": clocks.summary(),
+            "checksum": checksum,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--images", type=int, default=0, help="override images per GPU (debug)")
+    ap.add_argument("--images-per-call", type=int, default=512)
+    ap.add_argument("--e2e-images", type=int, default=0, help="images in the host-buffer leg (0 = all)")
+    ap.add_argument("--cpu-sample", type=int, default=128)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

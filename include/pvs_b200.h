@@ -1,0 +1,179 @@
+/*
+ * pvs_b200.h  --  C ABI of the B200-native encode-and-compare path for pyvisim.
+ *
+ * The reference (MechaCritter/Python-Visual-Similarity, pyvisim 0.1.3) is pure Python and
+ * has no FFI layer: its operator boundary is the Python class API
+ * (VLADEncoder / FisherVectorEncoder / Pipeline  .encode() / .similarity_score()).  Every
+ * export below replaces the *body* of one reference routine -- the scikit-learn / NumPy
+ * calls under that API -- and is what a ctypes stub inside the reference would bind
+ * (INTEGRATION.md shows that stub).  The reference routine each export replaces is cited
+ * as path:line relative to the reference root.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++ / torch types.  Every call returns 0 on success or
+ *     a negative pvs_status; pvs_last_error() gives the thread-local message.
+ *     Nothing throws or exits across this boundary.
+ *   - *_dev pointers are device pointers on the current CUDA device; the caller owns every
+ *     buffer.  Calls are asynchronous and ordered on `stream` (a cudaStream_t passed as
+ *     void*; NULL = legacy default stream).  The only hidden device memory is the
+ *     per-model constant block owned by a pvs_model handle; scratch comes from the
+ *     caller through an explicit workspace whose size pvs_*_workspace_bytes() reports.
+ *   - *_host entry points take host pointers, do their own staged H2D / D2H copies and
+ *     synchronise before returning (they are what encode() on NumPy arrays calls).
+ *   - descriptors are packed row-major fp32 [total_rows, d_in]; image i owns rows
+ *     offsets[i] .. offsets[i+1]  (int64, n_images + 1 entries, offsets[0] == 0) -- the
+ *     CSR form of the reference's Python loop over images (encoders/vlad.py:87,
+ *     encoders/fisher_vector.py:89).
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with
+ *     PVS_ERR_CUDA.
+ */
+#ifndef PVS_B200_H
+#define PVS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PVS_VERSION 100 /* 0.1.0 */
+
+typedef enum pvs_status {
+    PVS_OK = 0,
+    PVS_ERR_BAD_ARG = -1,     /* NULL pointer, negative size, unknown enum            */
+    PVS_ERR_BAD_SHAPE = -2,   /* dimension mismatch between model / pca / descriptors  */
+    PVS_ERR_CUDA = -3,        /* CUDA runtime error (message has the cudaError string) */
+    PVS_ERR_WORKSPACE = -4,   /* workspace too small                                   */
+    PVS_ERR_UNSUPPORTED = -5  /* e.g. norm_order <= 0                                  */
+} pvs_status;
+
+typedef enum pvs_model_kind { PVS_MODEL_KMEANS = 1, PVS_MODEL_GMM_DIAG = 2, PVS_MODEL_PCA = 3 } pvs_model_kind;
+typedef enum pvs_dtype { PVS_F32 = 0, PVS_BF16 = 1 } pvs_dtype;
+
+/* compute path selector for the contractions (see DESIGN.md "kernels") */
+typedef enum pvs_path {
+    PVS_PATH_AUTO = 0,   /* tcgen05 tensor-core kernels when the shape allows, else SIMT */
+    PVS_PATH_SIMT = 1,   /* fp32 CUDA-core kernels (any K, D)                            */
+    PVS_PATH_TENSOR = 2  /* force the tcgen05 kernels; PVS_ERR_UNSUPPORTED if shape can't */
+} pvs_path;
+
+typedef struct pvs_model pvs_model; /* opaque; device-resident, immutable after create */
+
+/* ---- library ------------------------------------------------------------------------ */
+int pvs_version(void);
+const char* pvs_last_error(void);
+/* sm count / compute capability of the current device; PVS_ERR_CUDA when there is none */
+int pvs_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
+/* number of kernel launches issued by this library on this thread since the last reset
+ * (bench.py reports it as gpu_launches) */
+int64_t pvs_launch_count(void);
+void pvs_launch_count_reset(void);
+int pvs_set_path(int path); /* pvs_path; process-wide default PVS_PATH_AUTO */
+/* Optional per-stage device timing: while enabled every kernel stage is bracketed by CUDA
+ * events on the stream it is launched on; pvs_profile_read() folds the finished records
+ * and returns the accumulated milliseconds / launch count of one stage. */
+int pvs_profile_enable(int on);
+int pvs_profile_stage_count(void);
+const char* pvs_profile_stage_name(int stage);
+int pvs_profile_read(int stage, double* total_ms, int64_t* launches);
+
+/* ---- model handles (weights uploaded once) ------------------------------------------ */
+/* K-Means centres, fp32 [k, d].  Replaces the state read by KMeans.predict at
+ * encoders/vlad.py:95-96 (cluster_centers_). */
+int pvs_kmeans_create(const float* centers_host, int k, int d, pvs_model** out);
+/* Diagonal GMM, fp64 [k], [k,d], [k,d], [k,d] exactly as scikit-learn stores them
+ * (weights_, means_, covariances_, precisions_cholesky_), read at
+ * encoders/fisher_vector.py:95-99.  Derived constants are folded in fp64 on the host. */
+int pvs_gmm_create(const double* weights_host, const double* means_host,
+                   const double* covariances_host, const double* precisions_cholesky_host,
+                   int k, int d, pvs_model** out);
+/* PCA (whiten=False): components fp32 [d_out, d_in], mean fp32 [d_in]
+ * (encoders/vlad.py:89-90, encoders/fisher_vector.py:91-92). */
+int pvs_pca_create(const float* components_host, const float* mean_host, int d_out, int d_in,
+                   pvs_model** out);
+int pvs_model_destroy(pvs_model* m);
+int pvs_model_dims(const pvs_model* m, int* kind, int* k, int* d, int* d_in);
+
+/* ---- a1: PCA projection  (sklearn PCA.transform called at vlad.py:90, fisher_vector.py:92)
+ * y[rows, d_out] = x @ C^T - mean @ C^T, fp32 */
+int pvs_pca_project(const pvs_model* pca, const float* x_dev, int64_t rows, float* y_dev, void* stream);
+
+/* ---- a2-a4: VLAD  (VLADEncoder.encode body, encoders/vlad.py:88-111) ------------------
+ * out_dev: fp32 [n_images, k * d]  (cluster-major; flatten=False is a host-side reshape)
+ * labels_out_dev: optional int32 [total_rows] hard assignments (NULL to skip)
+ * pca may be NULL.  power = power_norm_weight, norm_order = ord of the per-cluster norm
+ * (>0, or INFINITY), eps = epsilon.  Images with zero descriptors produce zero rows here;
+ * quirk Q1 (the reference aborts the batch, vlad.py:92-93) is reproduced by the host
+ * wrapper, which knows the iteration order. */
+size_t pvs_vlad_workspace_bytes(const pvs_model* kmeans, const pvs_model* pca, int64_t total_rows, int64_t n_images);
+int pvs_vlad_encode(const pvs_model* kmeans, const pvs_model* pca, const float* desc_dev,
+                    const int64_t* offsets_dev, int64_t n_images, int64_t total_rows, float power,
+                    float norm_order, float eps, float* out_dev, int32_t* labels_out_dev,
+                    void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ---- a5-a8: Fisher vector  (FisherVectorEncoder.encode body, fisher_vector.py:90-133) ---
+ * out_dev: fp32 [n_images, 2*k*d + k] = [d_pi | d_mu | d_sigma] per image, power- and
+ * globally ord-normalised.  argmax_out_dev: optional int32 [total_rows], arg-max posterior. */
+size_t pvs_fv_workspace_bytes(const pvs_model* gmm, const pvs_model* pca, int64_t total_rows, int64_t n_images);
+int pvs_fv_encode(const pvs_model* gmm, const pvs_model* pca, const float* desc_dev,
+                  const int64_t* offsets_dev, int64_t n_images, int64_t total_rows, float power,
+                  float norm_order, float eps, float* out_dev, int32_t* argmax_out_dev,
+                  void* workspace_dev, size_t workspace_bytes, void* stream);
+/* posterior only: q fp32 [rows, k] (GaussianMixture.predict_proba, fisher_vector.py:99);
+ * y_dev is already PCA-projected [rows, d] */
+int pvs_gmm_posterior(const pvs_model* gmm, const float* y_dev, int64_t rows, float* q_dev, void* stream);
+/* hard assignment only: labels int32 [rows] (KMeans.predict, vlad.py:95) */
+int pvs_kmeans_assign(const pvs_model* kmeans, const float* y_dev, int64_t rows, int32_t* labels_dev, void* stream);
+
+/* ---- a10: cosine similarity  (_utils.py:312-330 -> sklearn cosine_similarity) --------- */
+/* row L2-normalise fp32 [n, d] -> fp32 or bf16 [n, d]; zero rows stay zero */
+int pvs_l2_normalize_rows(const float* x_dev, int64_t n, int64_t d, void* out_dev, int out_dtype, void* stream);
+/* full matrix, fp32: s[n, m] = normalise(x) @ normalise(y)^T.  x/y are RAW (un-normalised)
+ * fp32; workspace holds the two normalised copies. */
+size_t pvs_cosine_matrix_workspace_bytes(int64_t n, int64_t m, int64_t d);
+int pvs_cosine_matrix(const float* x_dev, int64_t n, const float* y_dev, int64_t m, int64_t d,
+                      float* s_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ---- a10 + a11: similarity with fused top-k  (eval.py:37-43, 76-80, 131-132) ----------
+ * q_dev [n_q, d], db_dev [n_db, d]: ALREADY row-normalised, dtype fp32 or bf16.
+ * For every query row the k best database rows by score, ties broken by lowest index
+ * (the reference's np.argsort order on exact ties is unspecified).  Scores descending.
+ * idx_out = local database row + db_index_offset (global ids for a sharded database).
+ * k <= PVS_TOPK_MAX. */
+#define PVS_TOPK_MAX 1024
+size_t pvs_cosine_topk_workspace_bytes(int64_t n_q, int64_t n_db, int64_t d, int k, int dtype);
+int pvs_cosine_topk(const void* q_dev, const void* db_dev, int dtype, int64_t n_q, int64_t n_db,
+                    int64_t d, int k, int64_t db_index_offset, float* scores_out_dev,
+                    int64_t* idx_out_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+/* merge `parts` top-k lists per row (scores/idx laid out [parts, n_q, k]) into one
+ * [n_q, k] list with the same ordering rule -- used when the DATABASE is sharded. */
+int pvs_topk_merge(const float* scores_dev, const int64_t* idx_dev, int parts, int64_t n_q, int k,
+                   float* scores_out_dev, int64_t* idx_out_dev, void* stream);
+
+/* ---- f1: label logic on top-k lists  (eval.py:82-98, 126-145) ------------------------- */
+/* hits_out[q] = any(db_labels[idx[q, :k]] == query_labels[q]);  ap_out[q] = average precision
+ * with the reference's quirk Q6 (R counted inside the truncated list). Either may be NULL. */
+int pvs_topk_label_metrics(const int64_t* idx_dev, const int32_t* db_labels_dev,
+                           const int32_t* query_labels_dev, int64_t n_q, int k,
+                           int32_t* hits_out_dev, float* ap_out_dev, void* stream);
+
+/* ---- host-buffer entry points (what encode()/similarity_func call with NumPy arrays) --
+ * Pinned or pageable host pointers; inputs are staged in image chunks of at most
+ * chunk_rows descriptor rows (0 = library default) on two streams so H2D, compute and
+ * D2H overlap.  They return after the last D2H has completed. */
+int pvs_vlad_encode_host(const pvs_model* kmeans, const pvs_model* pca, const float* desc_host,
+                         const int64_t* offsets_host, int64_t n_images, float power, float norm_order,
+                         float eps, float* out_host, int32_t* labels_out_host, int64_t chunk_rows);
+int pvs_fv_encode_host(const pvs_model* gmm, const pvs_model* pca, const float* desc_host,
+                       const int64_t* offsets_host, int64_t n_images, float power, float norm_order,
+                       float eps, float* out_host, int64_t chunk_rows);
+int pvs_cosine_matrix_host(const float* x_host, int64_t n, const float* y_host, int64_t m, int64_t d,
+                           float* s_host);
+int pvs_cosine_topk_host(const float* q_host, int64_t n_q, const float* db_host, int64_t n_db, int64_t d,
+                         int k, int use_bf16, float* scores_out_host, int64_t* idx_out_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PVS_B200_H */

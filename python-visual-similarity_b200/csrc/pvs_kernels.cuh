@@ -1,0 +1,47 @@
+// pvs_kernels.cuh -- launcher prototypes shared between the C-ABI layer and the kernel TUs.
+#pragma once
+#include "pvs_common.cuh"
+
+namespace pvs {
+
+// ---- generic fp32 CUDA-core contraction (any shape) -----------------------------------
+// C[m,n] = alpha * sum_k A'[m,k] * B[n,k] + bias[n]
+//   square_cat == 0 : A' = A                      (kdim = a_cols)
+//   square_cat == 1 : A' = [A*A | A] per row      (kdim = 2*a_cols; B is [n, 2*a_cols])
+int launch_gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                   int64_t M, int N, int a_cols, int square_cat, float alpha, const float* bias,
+                   cudaStream_t st);
+
+// in-place softmax over each row of L [rows, k]; optional arg-max per row
+int launch_row_softmax(float* L, int64_t rows, int k, int32_t* argmax_out, cudaStream_t st);
+// labels[r] = argmin_j S[r, j], lowest index on ties
+int launch_row_argmin(const float* S, int64_t rows, int k, int32_t* labels, cudaStream_t st);
+
+// ---- VLAD aggregation + normalisation ---------------------------------------------------
+int launch_vlad_aggregate(const float* y, int d, const int32_t* labels, const int64_t* offsets,
+                          int64_t n_images, const float* centers, int k, float power, float norm_order,
+                          float eps, float* out, cudaStream_t st);
+
+// ---- Fisher vector statistics + gradients ------------------------------------------------
+// S [n_images, k, 2d+1] = per image ( q^T [y | y*y] , sum_t q ) / T
+int launch_fv_stats(const float* q, const float* y, int d, int k, const int64_t* offsets,
+                    int64_t n_images, float* S, cudaStream_t st);
+int launch_fv_finalize(const float* S, const pvs_model* gmm, int64_t n_images, float power,
+                       float norm_order, float eps, float* out, cudaStream_t st);
+
+// ---- similarity / top-k --------------------------------------------------------------------
+int launch_l2_normalize(const float* x, int64_t n, int64_t d, void* out, int out_dtype, cudaStream_t st);
+int launch_bf16_to_f32(const void* x, int64_t n, float* out, cudaStream_t st);
+// per-row top-k of a dense score block S [rows, n_db] (row stride lds)
+int launch_topk_rows(const float* S, int64_t lds, int64_t rows, int64_t n_db, int k, int64_t idx_offset,
+                     float* scores_out, int64_t* idx_out, cudaStream_t st);
+int launch_topk_merge(const float* scores, const int64_t* idx, int parts, int64_t n_q, int k,
+                      float* scores_out, int64_t* idx_out, cudaStream_t st);
+int launch_label_metrics(const int64_t* idx, const int32_t* db_labels, const int32_t* q_labels,
+                         int64_t n_q, int k, int32_t* hits, float* ap, cudaStream_t st);
+
+// ---- tcgen05 tensor-core paths (pvs_tc_*.cu); return PVS_ERR_UNSUPPORTED when the shape
+//      is outside what the kernel handles so the caller can take the SIMT path -------------
+bool tc_available();
+
+}  // namespace pvs

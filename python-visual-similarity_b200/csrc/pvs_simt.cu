@@ -1,0 +1,651 @@
+// pvs_simt.cu -- fp32 CUDA-core kernels for the encode-and-compare path (any K, any D).
+//
+// These are the shape-generic kernels: every stage of the path exists here in plain fp32
+// so that odd shapes (k=32 vocabularies, D=514 descriptors, ragged images) always have a
+// GPU path.  The tcgen05 tensor-core kernels in pvs_tc_*.cu take over the contractions
+// when the shape allows; the aggregation / normalisation / top-k kernels below are
+// HBM- or latency-bound by nature and stay on CUDA cores.
+//
+// Reference routines restated (see include/pvs_b200.h for the per-export mapping):
+//   gemm_nt           sklearn PCA.transform / KMeans scores / GMM log-prob contractions
+//   row_softmax       sklearn mixture/_base.py:552-582 (logsumexp + exp)
+//   row_argmin        sklearn _k_means_lloyd.pyx:_update_chunk_dense arg-min scan
+//   vlad_aggregate    pyvisim/encoders/vlad.py:98-111
+//   fv_stats/finalize pyvisim/encoders/fisher_vector.py:102-133
+//   l2_normalize      sklearn preprocessing.normalize as used by cosine_similarity
+//   topk_rows         pyvisim/eval.py:40-43 (np.argsort(-scores)[:k])
+#include "pvs_kernels.cuh"
+
+namespace pvs {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// =====================================================================================
+// generic NT contraction
+// =====================================================================================
+namespace {
+constexpr int G_BM = 128, G_BN = 64, G_BK = 16;
+
+__global__ void __launch_bounds__(256)
+gemm_nt_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb,
+               float* __restrict__ C, int64_t ldc, int64_t M, int N, int a_cols, int sq, float alpha,
+               const float* __restrict__ bias)
+{
+    __shared__ __align__(16) float As[G_BK][G_BM + 4];
+    __shared__ __align__(16) float Bs[G_BK][G_BN + 4];
+    const int tid = threadIdx.x;
+    const int64_t m0 = (int64_t)blockIdx.x * G_BM;
+    const int n0 = blockIdx.y * G_BN;
+    const int kdim = sq ? 2 * a_cols : a_cols;
+    const int ty = tid >> 4, tx = tid & 15;
+    const int lc = tid & 15, lr = tid >> 4;
+
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < kdim; k0 += G_BK) {
+        const int kk = k0 + lc;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = lr + 16 * i;
+            const int64_t m = m0 + r;
+            float v = 0.f;
+            if (m < M && kk < kdim) {
+                if (sq) {
+                    if (kk < a_cols) { const float a = A[m * lda + kk]; v = a * a; }
+                    else v = A[m * lda + (kk - a_cols)];
+                } else {
+                    v = A[m * lda + kk];
+                }
+            }
+            As[lc][r] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = lr + 16 * i;
+            const int n = n0 + r;
+            Bs[lc][r] = (n < N && kk < kdim) ? B[(int64_t)n * ldb + kk] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < G_BK; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t m = m0 + ty * 8 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n < N) C[m * ldc + n] = alpha * acc[i][j] + (bias ? bias[n] : 0.f);
+        }
+    }
+}
+}  // namespace
+
+int launch_gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                   int64_t M, int N, int a_cols, int square_cat, float alpha, const float* bias,
+                   cudaStream_t st)
+{
+    if (M <= 0 || N <= 0) return PVS_OK;
+    dim3 grid((unsigned)ceil_div(M, G_BM), (unsigned)ceil_div(N, G_BN));
+    PVS_LAUNCH(gemm_nt_kernel, grid, 256, 0, st, A, lda, B, ldb, C, ldc, M, N, a_cols, square_cat, alpha, bias);
+    return PVS_OK;
+}
+
+// =====================================================================================
+// row softmax / arg-min (one warp per row)
+// =====================================================================================
+namespace {
+__global__ void __launch_bounds__(256)
+row_softmax_kernel(float* __restrict__ L, int64_t rows, int k, int32_t* __restrict__ argmax_out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    float* p = L + row * k;
+    float mx = -INFINITY;
+    int mi = 0x7fffffff;
+    for (int j = lane; j < k; j += 32) {
+        const float v = p[j];
+        if (v > mx) { mx = v; mi = j; }      // increasing j per lane: first max kept
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(FULL, mx, o);
+        const int oi = __shfl_xor_sync(FULL, mi, o);
+        if (ov > mx || (ov == mx && oi < mi)) { mx = ov; mi = oi; }
+    }
+    const float base = isfinite(mx) ? mx : 0.f;
+    float s = 0.f;
+    for (int j = lane; j < k; j += 32) s += expf(p[j] - base);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+    const float lse = logf(s) + base;
+    for (int j = lane; j < k; j += 32) p[j] = expf(p[j] - lse);
+    if (argmax_out && lane == 0) argmax_out[row] = mi;
+}
+
+__global__ void __launch_bounds__(256)
+row_argmin_kernel(const float* __restrict__ S, int64_t rows, int k, int32_t* __restrict__ labels)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* p = S + row * k;
+    float mn = INFINITY;
+    int mi = 0x7fffffff;
+    for (int j = lane; j < k; j += 32) {
+        const float v = p[j];
+        if (v < mn) { mn = v; mi = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(FULL, mn, o);
+        const int oi = __shfl_xor_sync(FULL, mi, o);
+        if (ov < mn || (ov == mn && oi < mi)) { mn = ov; mi = oi; }
+    }
+    if (lane == 0) labels[row] = (mi == 0x7fffffff) ? 0 : mi;
+}
+}  // namespace
+
+int launch_row_softmax(float* L, int64_t rows, int k, int32_t* argmax_out, cudaStream_t st)
+{
+    if (rows <= 0) return PVS_OK;
+    PVS_LAUNCH(row_softmax_kernel, (unsigned)ceil_div(rows, 8), 256, 0, st, L, rows, k, argmax_out);
+    return PVS_OK;
+}
+
+int launch_row_argmin(const float* S, int64_t rows, int k, int32_t* labels, cudaStream_t st)
+{
+    if (rows <= 0) return PVS_OK;
+    PVS_LAUNCH(row_argmin_kernel, (unsigned)ceil_div(rows, 8), 256, 0, st, S, rows, k, labels);
+    return PVS_OK;
+}
+
+// =====================================================================================
+// shared normalisation helpers
+// =====================================================================================
+__device__ __forceinline__ float signed_pow(float v, float p)
+{
+    if (p == 1.f) return v;
+    const float a = fabsf(v);
+    const float r = (p == 0.5f) ? sqrtf(a) : powf(a, p);
+    return v > 0.f ? r : (v < 0.f ? -r : (isnan(v) ? v : 0.f));   // np.sign(0) * x = 0
+}
+// contribution of one element to an ord-norm accumulator
+__device__ __forceinline__ float norm_term(float v, float ord)
+{
+    const float a = fabsf(v);
+    if (ord == 2.f) return a * a;
+    if (ord == 1.f) return a;
+    if (isinf(ord)) return a;          // combined with max
+    return powf(a, ord);
+}
+__device__ __forceinline__ float norm_combine(float x, float y, float ord) { return isinf(ord) ? fmaxf(x, y) : x + y; }
+__device__ __forceinline__ float norm_finish(float acc, float ord)
+{
+    if (ord == 2.f) return sqrtf(acc);
+    if (ord == 1.f || isinf(ord)) return acc;
+    return powf(acc, 1.f / ord);
+}
+
+// =====================================================================================
+// VLAD aggregation: one warp per (image, cluster); members visited in descriptor order,
+// so the fp32 accumulation order is exactly the reference's sequential loop
+// (vlad.py:102-104).  Each descriptor row is read once, each output row written once.
+// =====================================================================================
+namespace {
+template <int NACC>
+__global__ void __launch_bounds__(256)
+vlad_aggregate_kernel(const float* __restrict__ y, int d, const int32_t* __restrict__ labels,
+                      const int64_t* __restrict__ offsets, const float* __restrict__ centers, int k,
+                      int k_per_cta, float power, float ord, float eps, float* __restrict__ out)
+{
+    const int64_t img = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int64_t r0 = offsets[img];
+    const int T = (int)(offsets[img + 1] - r0);
+    const int kbeg = blockIdx.y * k_per_cta;
+    const int kend = min(k, kbeg + k_per_cta);
+    const int32_t* lab = labels + r0;
+
+    for (int c = kbeg + warp; c < kend; c += nw) {
+        float acc[NACC], cv[NACC];
+#pragma unroll
+        for (int j = 0; j < NACC; ++j) {
+            const int dd = lane + 32 * j;
+            acc[j] = 0.f;
+            cv[j] = dd < d ? centers[(int64_t)c * d + dd] : 0.f;
+        }
+        for (int t0 = 0; t0 < T; t0 += 32) {
+            const int l = (t0 + lane < T) ? lab[t0 + lane] : -1;
+            unsigned m = __ballot_sync(FULL, l == c);
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                const float* row = y + (r0 + t0 + b) * (int64_t)d;
+#pragma unroll
+                for (int j = 0; j < NACC; ++j) {
+                    const int dd = lane + 32 * j;
+                    if (dd < d) acc[j] += row[dd] - cv[j];
+                }
+            }
+        }
+        float nrm = 0.f;
+#pragma unroll
+        for (int j = 0; j < NACC; ++j) {
+            acc[j] = signed_pow(acc[j], power);
+            if (lane + 32 * j < d) nrm = norm_combine(nrm, norm_term(acc[j], ord), ord);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nrm = norm_combine(nrm, __shfl_xor_sync(FULL, nrm, o), ord);
+        const float den = norm_finish(nrm, ord) + eps;
+        float* orow = out + (img * k + c) * (int64_t)d;
+#pragma unroll
+        for (int j = 0; j < NACC; ++j) {
+            const int dd = lane + 32 * j;
+            if (dd < d) orow[dd] = acc[j] / den;
+        }
+    }
+}
+}  // namespace
+
+int launch_vlad_aggregate(const float* y, int d, const int32_t* labels, const int64_t* offsets,
+                          int64_t n_images, const float* centers, int k, float power, float norm_order,
+                          float eps, float* out, cudaStream_t st)
+{
+    if (n_images <= 0) return PVS_OK;
+    PVS_CHECK(d <= 2048, PVS_ERR_UNSUPPORTED, "VLAD aggregation supports d <= 2048 (got %d)", d);
+    // enough CTAs to fill the machine when there are few images (README quick start: 2)
+    int groups = 1;
+    while (groups < 32 && n_images * groups < 2 * 148 && (k / (groups * 2)) >= 8) groups *= 2;
+    const int k_per_cta = (int)ceil_div(k, groups);
+    dim3 grid((unsigned)n_images, (unsigned)ceil_div(k, k_per_cta));
+#define VA(N) PVS_LAUNCH(vlad_aggregate_kernel<N>, grid, 256, 0, st, y, d, labels, offsets, centers, k, k_per_cta, power, norm_order, eps, out)
+    if (d <= 64) VA(2);
+    else if (d <= 128) VA(4);
+    else if (d <= 256) VA(8);
+    else if (d <= 544) VA(17);
+    else if (d <= 1024) VA(32);
+    else VA(64);
+#undef VA
+    return PVS_OK;
+}
+
+// =====================================================================================
+// Fisher-vector statistics: per image S = q^T [y | y*y] / T  and  s0 = sum_t q / T
+// =====================================================================================
+namespace {
+constexpr int S_BM = 64, S_BN = 64, S_BK = 16;
+
+__global__ void __launch_bounds__(256)
+fv_stats_kernel(const float* __restrict__ q, const float* __restrict__ y, int d, int k,
+                const int64_t* __restrict__ offsets, float* __restrict__ S)
+{
+    __shared__ __align__(16) float As[S_BK][S_BM + 4];
+    __shared__ __align__(16) float Bs[S_BK][S_BN + 4];
+    const int64_t img = blockIdx.z;
+    const int64_t r0 = offsets[img];
+    const int T = (int)(offsets[img + 1] - r0);
+    const int j0 = blockIdx.y * S_BM, n0 = blockIdx.x * S_BN;
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int lc = tid & 63, lr = tid >> 6;            // loader: column, row (0..3)
+    const int nd = 2 * d;
+
+    float acc[4][4];
+    float s0[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int t0 = 0; t0 < T; t0 += S_BK) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int kk = lr + 4 * i;
+            const int t = t0 + kk;
+            const int j = j0 + lc, n = n0 + lc;
+            float a = 0.f, b = 0.f;
+            if (t < T) {
+                if (j < k) a = q[(r0 + t) * (int64_t)k + j];
+                if (n < d) b = y[(r0 + t) * (int64_t)d + n];
+                else if (n < nd) { const float v = y[(r0 + t) * (int64_t)d + (n - d)]; b = v * v; }
+            }
+            As[kk][lc] = a;
+            Bs[kk][lc] = b;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < S_BK; ++kk) {
+            const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+            const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                s0[i] += a[i];
+            }
+        }
+        __syncthreads();
+    }
+    const float inv_t = 1.f / (float)T;          // T == 0 -> inf -> NaN, as the reference
+    const int ld = nd + 1;
+    float* Simg = S + img * (int64_t)k * ld;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int j = j0 + ty * 4 + i;
+        if (j >= k) continue;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const int n = n0 + tx * 4 + jj;
+            if (n < nd) Simg[(int64_t)j * ld + n] = acc[i][jj] * inv_t;
+        }
+        if (blockIdx.x == 0 && tx == 0) Simg[(int64_t)j * ld + nd] = s0[i] * inv_t;
+    }
+}
+
+// gradients wrt (pi, mu, sigma), analytic normalisation, signed power, global ord-norm
+__global__ void __launch_bounds__(256)
+fv_finalize_kernel(const float* __restrict__ S, int k, int d, const float* __restrict__ mu,
+                   const float* __restrict__ var, const float* __restrict__ pi,
+                   const float* __restrict__ g_pi, const float* __restrict__ g_mu,
+                   const float* __restrict__ g_sig, float power, float ord, float eps,
+                   float* __restrict__ out)
+{
+    __shared__ float red[8];
+    __shared__ float s_den;
+    const int64_t img = blockIdx.x;
+    const int ld = 2 * d + 1;
+    const int kd = k * d;
+    const float* Simg = S + img * (int64_t)k * ld;
+    float* o = out + img * (int64_t)(2 * kd + k);
+    float part = 0.f;
+    for (int e = threadIdx.x; e < kd; e += blockDim.x) {
+        const int j = e / d, dd = e - j * d;
+        const float s0 = Simg[(int64_t)j * ld + 2 * d];
+        const float s1 = Simg[(int64_t)j * ld + dd];
+        const float s2 = Simg[(int64_t)j * ld + d + dd];
+        const float m = mu[e], v = var[e];
+        float dm = (s1 - s0 * m) * g_mu[e];
+        float ds = (-s2 - s0 * m * m + s0 * v + 2.f * s1 * m) * g_sig[e];
+        dm = signed_pow(dm, power);
+        ds = signed_pow(ds, power);
+        o[k + e] = dm;
+        o[k + kd + e] = ds;
+        part = norm_combine(part, norm_term(dm, ord), ord);
+        part = norm_combine(part, norm_term(ds, ord), ord);
+    }
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        const float s0 = Simg[(int64_t)j * ld + 2 * d];
+        const float dp = signed_pow((s0 - pi[j]) * g_pi[j], power);
+        o[j] = dp;
+        part = norm_combine(part, norm_term(dp, ord), ord);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) part = norm_combine(part, __shfl_xor_sync(FULL, part, off), ord);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = red[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) t = norm_combine(t, red[w], ord);
+        s_den = norm_finish(t, ord) + eps;
+    }
+    __syncthreads();
+    const float den = s_den;
+    // every thread rescales exactly the elements it wrote above (no cross-thread hazard)
+    for (int e = threadIdx.x; e < kd; e += blockDim.x) {
+        o[k + e] = o[k + e] / den;
+        o[k + kd + e] = o[k + kd + e] / den;
+    }
+    for (int j = threadIdx.x; j < k; j += blockDim.x) o[j] = o[j] / den;
+}
+}  // namespace
+
+int launch_fv_stats(const float* q, const float* y, int d, int k, const int64_t* offsets,
+                    int64_t n_images, float* S, cudaStream_t st)
+{
+    if (n_images <= 0) return PVS_OK;
+    for (int64_t i0 = 0; i0 < n_images; i0 += 65535) {       // gridDim.z limit
+        const int64_t n = n_images - i0 < 65535 ? n_images - i0 : 65535;
+        dim3 grid((unsigned)ceil_div(2 * d, S_BN), (unsigned)ceil_div(k, S_BM), (unsigned)n);
+        PVS_LAUNCH(fv_stats_kernel, grid, 256, 0, st, q, y, d, k, offsets + i0, S + i0 * (int64_t)k * (2 * d + 1));
+    }
+    return PVS_OK;
+}
+
+int launch_fv_finalize(const float* S, const pvs_model* g, int64_t n_images, float power, float norm_order,
+                       float eps, float* out, cudaStream_t st)
+{
+    if (n_images <= 0) return PVS_OK;
+    PVS_LAUNCH(fv_finalize_kernel, (unsigned)n_images, 256, 0, st, S, g->k, g->d, g->mu, g->var, g->pi,
+               g->g_pi, g->g_mu, g->g_sig, power, norm_order, eps, out);
+    return PVS_OK;
+}
+
+// =====================================================================================
+// row L2 normalisation (fp32 -> fp32 / bf16), zero rows stay zero
+// =====================================================================================
+namespace {
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+l2_normalize_kernel(const float* __restrict__ x, int64_t d, OutT* __restrict__ out)
+{
+    __shared__ float red[8];
+    __shared__ float s_inv;
+    const float* p = x + (int64_t)blockIdx.x * d;
+    OutT* o = out + (int64_t)blockIdx.x * d;
+    float s = 0.f;
+    for (int64_t j = threadIdx.x; j < d; j += blockDim.x) { const float v = p[j]; s = fmaf(v, v, s); }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(FULL, s, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        const float n = sqrtf(t);
+        s_inv = n == 0.f ? 1.f : n;
+    }
+    __syncthreads();
+    const float n = s_inv;
+    for (int64_t j = threadIdx.x; j < d; j += blockDim.x) {
+        const float v = p[j] / n;
+        if constexpr (sizeof(OutT) == 2) o[j] = __float2bfloat16_rn(v);
+        else o[j] = v;
+    }
+}
+
+__global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ x, int64_t n, float* __restrict__ out)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = __bfloat162float(x[i]);
+}
+}  // namespace
+
+int launch_l2_normalize(const float* x, int64_t n, int64_t d, void* out, int out_dtype, cudaStream_t st)
+{
+    if (n <= 0) return PVS_OK;
+    PVS_CHECK(n < 2147483647LL, PVS_ERR_BAD_SHAPE, "too many rows");
+    if (out_dtype == PVS_F32) PVS_LAUNCH(l2_normalize_kernel<float>, (unsigned)n, 256, 0, st, x, d, (float*)out);
+    else if (out_dtype == PVS_BF16) PVS_LAUNCH(l2_normalize_kernel<__nv_bfloat16>, (unsigned)n, 256, 0, st, x, d, (__nv_bfloat16*)out);
+    else return fail(PVS_ERR_BAD_ARG, "unknown dtype %d", out_dtype);
+    return PVS_OK;
+}
+
+int launch_bf16_to_f32(const void* x, int64_t n, float* out, cudaStream_t st)
+{
+    if (n <= 0) return PVS_OK;
+    PVS_LAUNCH(bf16_to_f32_kernel, 148 * 8, 256, 0, st, (const __nv_bfloat16*)x, n, out);
+    return PVS_OK;
+}
+
+// =====================================================================================
+// top-k
+//   key = (orderable(score) << 32) | (0xffffffff - index): a plain descending sort of the
+//   64-bit keys gives "score descending, lowest index first on ties".
+// =====================================================================================
+__device__ __forceinline__ unsigned long long topk_key(float s, unsigned idx)
+{
+    unsigned u = __float_as_uint(s);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - idx);
+}
+__device__ __forceinline__ float key_score(unsigned long long key)
+{
+    unsigned u = (unsigned)(key >> 32);
+    u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ unsigned key_index(unsigned long long key) { return 0xffffffffu - (unsigned)(key & 0xffffffffu); }
+
+// in-place descending bitonic sort of n (power of two) keys in shared memory
+__device__ void bitonic_desc(unsigned long long* buf, int n)
+{
+    for (int size = 2; size <= n; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const int l = i ^ stride;
+                if (l > i) {
+                    const unsigned long long a = buf[i], b = buf[l];
+                    const bool desc = (i & size) == 0;
+                    if (desc ? (a < b) : (a > b)) { buf[i] = b; buf[l] = a; }
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+namespace {
+constexpr int TK_CAP = 2048;
+
+__global__ void __launch_bounds__(256)
+topk_rows_kernel(const float* __restrict__ S, int64_t lds, int64_t n_db, int k, int64_t idx_offset,
+                 float* __restrict__ scores_out, int64_t* __restrict__ idx_out)
+{
+    __shared__ unsigned long long buf[TK_CAP];
+    __shared__ int count;
+    __shared__ unsigned long long tau;
+    const float* row = S + (int64_t)blockIdx.x * lds;
+    for (int i = threadIdx.x; i < TK_CAP; i += blockDim.x) buf[i] = 0ull;
+    if (threadIdx.x == 0) { count = 0; tau = 0ull; }
+    __syncthreads();
+    for (int64_t base = 0; base < n_db; base += blockDim.x) {
+        if (count + (int)blockDim.x > TK_CAP) {              // uniform: count read after a barrier
+            bitonic_desc(buf, TK_CAP);
+            if (threadIdx.x == 0) { tau = buf[k - 1]; count = k; }
+            __syncthreads();
+            for (int i = k + threadIdx.x; i < TK_CAP; i += blockDim.x) buf[i] = 0ull;
+            __syncthreads();
+        }
+        const int64_t i = base + threadIdx.x;
+        if (i < n_db) {
+            const unsigned long long key = topk_key(row[i], (unsigned)i);
+            if (key > tau) buf[atomicAdd(&count, 1)] = key;
+        }
+        __syncthreads();
+    }
+    bitonic_desc(buf, TK_CAP);
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        const unsigned long long key = buf[j];
+        const bool valid = key != 0ull;
+        scores_out[(int64_t)blockIdx.x * k + j] = valid ? key_score(key) : -INFINITY;
+        idx_out[(int64_t)blockIdx.x * k + j] = valid ? (int64_t)key_index(key) + idx_offset : -1;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+topk_merge_kernel(const float* __restrict__ scores, const int64_t* __restrict__ idx, int parts, int64_t n_q,
+                  int k, int n_pow2, float* __restrict__ scores_out, int64_t* __restrict__ idx_out)
+{
+    extern __shared__ unsigned long long mbuf[];
+    const int64_t q = blockIdx.x;
+    const int total = parts * k;
+    for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+        unsigned long long key = 0ull;
+        if (i < total) {
+            const int p = i / k, j = i - p * k;
+            const int64_t id = idx[((int64_t)p * n_q + q) * k + j];
+            if (id >= 0) key = topk_key(scores[((int64_t)p * n_q + q) * k + j], (unsigned)id);
+        }
+        mbuf[i] = key;
+    }
+    bitonic_desc(mbuf, n_pow2);
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        const unsigned long long key = mbuf[j];
+        const bool valid = key != 0ull;
+        scores_out[q * k + j] = valid ? key_score(key) : -INFINITY;
+        idx_out[q * k + j] = valid ? (int64_t)key_index(key) : -1;
+    }
+}
+
+__global__ void label_metrics_kernel(const int64_t* __restrict__ idx, const int32_t* __restrict__ db_labels,
+                                     const int32_t* __restrict__ q_labels, int64_t n_q, int k,
+                                     int32_t* __restrict__ hits, float* __restrict__ ap)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_q) return;
+    const int32_t lbl = q_labels[q];
+    int rel = 0;
+    float psum = 0.f;
+    for (int j = 0; j < k; ++j) {
+        const int64_t id = idx[q * k + j];
+        if (id >= 0 && db_labels[id] == lbl) { ++rel; psum += (float)rel / (float)(j + 1); }
+    }
+    if (hits) hits[q] = rel > 0;
+    if (ap) ap[q] = rel > 0 ? psum / (float)rel : 0.f;      // quirk Q6: R counted inside the list
+}
+}  // namespace
+
+int launch_topk_rows(const float* S, int64_t lds, int64_t rows, int64_t n_db, int k, int64_t idx_offset,
+                     float* scores_out, int64_t* idx_out, cudaStream_t st)
+{
+    if (rows <= 0) return PVS_OK;
+    PVS_CHECK(k >= 1 && k <= PVS_TOPK_MAX, PVS_ERR_BAD_ARG, "k must be in [1, %d] (got %d)", PVS_TOPK_MAX, k);
+    PVS_CHECK(n_db < 4294967295LL, PVS_ERR_BAD_SHAPE, "database shard must have < 2^32 rows");
+    PVS_LAUNCH(topk_rows_kernel, (unsigned)rows, 256, 0, st, S, lds, n_db, k, idx_offset, scores_out, idx_out);
+    return PVS_OK;
+}
+
+int launch_topk_merge(const float* scores, const int64_t* idx, int parts, int64_t n_q, int k,
+                      float* scores_out, int64_t* idx_out, cudaStream_t st)
+{
+    if (n_q <= 0) return PVS_OK;
+    PVS_CHECK(k >= 1 && k <= PVS_TOPK_MAX && parts >= 1, PVS_ERR_BAD_ARG, "bad k/parts");
+    int n_pow2 = 1;
+    while (n_pow2 < parts * k) n_pow2 <<= 1;
+    const size_t smem = (size_t)n_pow2 * sizeof(unsigned long long);
+    PVS_CHECK(smem <= 200 * 1024, PVS_ERR_UNSUPPORTED, "parts*k = %d too large to merge in one pass", parts * k);
+    if (smem > 48 * 1024)
+        PVS_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PVS_LAUNCH(topk_merge_kernel, (unsigned)n_q, 256, smem, st, scores, idx, parts, n_q, k, n_pow2, scores_out, idx_out);
+    return PVS_OK;
+}
+
+int launch_label_metrics(const int64_t* idx, const int32_t* db_labels, const int32_t* q_labels,
+                         int64_t n_q, int k, int32_t* hits, float* ap, cudaStream_t st)
+{
+    if (n_q <= 0) return PVS_OK;
+    PVS_LAUNCH(label_metrics_kernel, (unsigned)ceil_div(n_q, 256), 256, 0, st, idx, db_labels, q_labels, n_q, k, hits, ap);
+    return PVS_OK;
+}
+
+}  // namespace pvs

@@ -1,0 +1,80 @@
+"""Shared device/host dispatch for the two encoders' ``encode_descriptors``."""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import numpy as np
+
+from .. import _native as N
+from ._base_encoder import pack_descriptors
+
+
+def _is_torch(x) -> bool:
+    try:
+        import torch
+        return isinstance(x, torch.Tensor)
+    except ImportError:  # pragma: no cover
+        return False
+
+
+def normalise_inputs(descriptors, offsets, d_in: int):
+    """-> (packed, offsets, on_device).  Accepts a list of (T_i, d_in) arrays, a packed
+    NumPy matrix + offsets, or a packed CUDA torch tensor + offsets."""
+    if _is_torch(descriptors):
+        import torch
+        if not descriptors.is_cuda:
+            return normalise_inputs(descriptors.numpy(), None if offsets is None else np.asarray(offsets), d_in)
+        x = descriptors.contiguous().float()
+        if x.ndim != 2 or x.shape[1] != d_in:
+            raise ValueError(f"descriptors must be (rows, {d_in}), got {tuple(x.shape)}")
+        if offsets is None:
+            offsets = torch.tensor([0, x.shape[0]], dtype=torch.int64)
+        offs_host = offsets.detach().cpu().numpy().astype(np.int64) if _is_torch(offsets) else np.asarray(offsets, np.int64)
+        return x, offs_host, True
+    if isinstance(descriptors, np.ndarray) and descriptors.ndim == 2:
+        if descriptors.shape[1] != d_in:
+            raise ValueError(f"descriptors must be (rows, {d_in}), got {descriptors.shape}")
+        x = np.ascontiguousarray(descriptors, dtype=np.float32)
+        offs = np.array([0, x.shape[0]], np.int64) if offsets is None else np.ascontiguousarray(offsets, dtype=np.int64)
+        return x, offs, False
+    descs = [np.asarray(d) for d in descriptors]
+    for d in descs:
+        if d.ndim != 2 or d.shape[1] != d_in:
+            raise ValueError(f"every descriptor matrix must be (T, {d_in}), got {d.shape}")
+    x, offs = pack_descriptors(descs, d_in)
+    return x, offs, False
+
+
+def check_offsets(offs: np.ndarray, rows: int) -> None:
+    if offs.ndim != 1 or offs.size < 1 or offs[0] != 0 or offs[-1] != rows or np.any(np.diff(offs) < 0):
+        raise ValueError("offsets must be non-decreasing int64 with offsets[0] == 0 and offsets[-1] == rows")
+
+
+def run_device(encode_fn, ws_fn, cluster: N.Model, pca: Optional[N.Model], x, offs_host: np.ndarray,
+               out_dim: int, params, images_per_call: int, want_rows_i32: bool):
+    """Device-resident path: loop over image chunks so the workspace stays bounded."""
+    import torch
+    n_images = offs_host.size - 1
+    dev = x.device
+    out = torch.empty((n_images, out_dim), dtype=torch.float32, device=dev)
+    rows_i32 = torch.empty((x.shape[0],), dtype=torch.int32, device=dev) if want_rows_i32 else None
+    offs_dev = torch.as_tensor(offs_host, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    lib = N.lib()
+    pca_h = pca.handle if pca else None
+    ws = None
+    power, order, eps = params
+    with torch.cuda.device(dev):
+        for i0 in range(0, n_images, images_per_call):
+            i1 = min(n_images, i0 + images_per_call)
+            r0, r1 = int(offs_host[i0]), int(offs_host[i1])
+            need = ws_fn(cluster.handle, pca_h, r1 - r0, i1 - i0)
+            if ws is None or ws.numel() < need:
+                ws = torch.empty((need,), dtype=torch.uint8, device=dev)
+            local = offs_dev[i0:i1 + 1] - r0 if i0 else offs_dev[:i1 + 1]
+            N.check(encode_fn(cluster.handle, pca_h, x[r0:r1].data_ptr() if r1 > r0 else x.data_ptr(),
+                              local.data_ptr(), i1 - i0, r1 - r0, power, order, eps, out[i0:i1].data_ptr(),
+                              rows_i32[r0:].data_ptr() if (rows_i32 is not None and r1 > r0) else None,
+                              ws.data_ptr(), ws.numel(), stream))
+            del local
+    return out, rows_i32

@@ -1,0 +1,191 @@
+"""All-pairs cosine similarity with fused top-k, single GPU and row-block sharded.
+
+Replaces the per-query loop of ``pyvisim/eval.py:31-43,69-80,126-132`` (one
+``cosine_similarity`` call that re-normalises the whole database plus a full
+``np.argsort`` *per query*) with: normalise the database once, then for every block of
+query rows one contraction against the database with the k best columns kept per row.
+
+Multi-GPU: rank r owns query rows ``[r*N/W, (r+1)*N/W)``; the
+database is either replicated or resident as W shards that are all-gathered once.  Each
+rank's top-k is final for its rows; the only exchange on the result path is an
+all-gather of the ``(rows/W, k)`` score and index lists (``torch.distributed``, NCCL on
+GPUs, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+
+from . import _native as N
+
+__all__ = ["l2_normalize", "cosine_topk", "all_pairs_topk", "shard_bounds", "merge_topk",
+           "gather_topk", "label_metrics"]
+
+
+def shard_bounds(n: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous, balanced row range of ``rank`` (first ``n % world`` ranks get one more)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def l2_normalize(x, dtype: str = "fp32"):
+    """Row-normalise a CUDA fp32 tensor -> fp32 or bf16 CUDA tensor (zero rows stay zero)."""
+    import torch
+    x = x.contiguous().float()
+    out = torch.empty_like(x, dtype=torch.bfloat16 if dtype == "bf16" else torch.float32)
+    with torch.cuda.device(x.device):
+        N.check(N.lib().pvs_l2_normalize_rows(x.data_ptr(), x.shape[0], x.shape[1], out.data_ptr(),
+                                              N.BF16 if dtype == "bf16" else N.F32,
+                                              torch.cuda.current_stream(x.device).cuda_stream))
+    return out
+
+
+def cosine_topk(queries_n, database_n, k: int, index_offset: int = 0):
+    """Top-k database rows per query row.  Inputs are ALREADY row-normalised CUDA tensors of
+    the same dtype (fp32 or bf16).  Returns (scores fp32 [nq,k], indices int64 [nq,k]),
+    scores descending, lowest index first on exact ties."""
+    import torch
+    if queries_n.dtype != database_n.dtype or queries_n.dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("queries and database must both be float32 or both bfloat16")
+    if queries_n.shape[1] != database_n.shape[1]:
+        raise ValueError("feature dimensions differ")
+    q, db = queries_n.contiguous(), database_n.contiguous()
+    nq, d = q.shape
+    ndb = db.shape[0]
+    dt = N.BF16 if q.dtype == torch.bfloat16 else N.F32
+    scores = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+    idx = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+    lib = N.lib()
+    need = lib.pvs_cosine_topk_workspace_bytes(nq, ndb, d, k, dt)
+    ws = torch.empty((max(int(need), 1),), dtype=torch.uint8, device=q.device)
+    with torch.cuda.device(q.device):
+        N.check(lib.pvs_cosine_topk(q.data_ptr(), db.data_ptr(), dt, nq, ndb, d, k, int(index_offset),
+                                    scores.data_ptr(), idx.data_ptr(), ws.data_ptr(), ws.numel(),
+                                    torch.cuda.current_stream(q.device).cuda_stream))
+    return scores, idx
+
+
+def merge_topk(scores, idx, k: int):
+    """Merge ``parts`` top-k lists per row: inputs [parts, nq, k] -> [nq, k] (database-sharded
+    variant; same ordering rule)."""
+    import torch
+    parts, nq, kk = scores.shape
+    assert kk == k and idx.shape == scores.shape
+    so = torch.empty((nq, k), dtype=torch.float32, device=scores.device)
+    io = torch.empty((nq, k), dtype=torch.int64, device=scores.device)
+    with torch.cuda.device(scores.device):
+        N.check(N.lib().pvs_topk_merge(scores.contiguous().data_ptr(), idx.contiguous().data_ptr(), parts, nq, k,
+                                       so.data_ptr(), io.data_ptr(),
+                                       torch.cuda.current_stream(scores.device).cuda_stream))
+    return so, io
+
+
+def gather_topk(scores, idx, n_total: int, group=None):
+    """All-gather the per-rank ``(rows_r, k)`` lists into ``(n_total, k)`` on every rank.
+    Works on CUDA (NCCL) and CPU (gloo) tensors; row counts may differ by one between ranks."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return scores, idx
+    world = dist.get_world_size(group)
+    k = scores.shape[1]
+    sizes = [shard_bounds(n_total, world, r) for r in range(world)]
+    pad = max(hi - lo for lo, hi in sizes)
+
+    def padded(t):
+        if t.shape[0] == pad:
+            return t.contiguous()
+        p = torch.zeros((pad, k), dtype=t.dtype, device=t.device)
+        p[: t.shape[0]] = t
+        return p
+
+    s_all = torch.empty((world * pad, k), dtype=scores.dtype, device=scores.device)
+    i_all = torch.empty((world * pad, k), dtype=idx.dtype, device=idx.device)
+    dist.all_gather_into_tensor(s_all, padded(scores), group=group)
+    dist.all_gather_into_tensor(i_all, padded(idx), group=group)
+    if all(hi - lo == pad for lo, hi in sizes):
+        return s_all, i_all
+    keep = torch.cat([torch.arange(r * pad, r * pad + (hi - lo)) for r, (lo, hi) in enumerate(sizes)]).to(scores.device)
+    return s_all[keep], i_all[keep]
+
+
+def all_pairs_topk(vectors, k: int, *, dtype: str = "bf16", rank: int = 0, world: int = 1,
+                   database_is_sharded: bool = False, gather: bool = True, group=None,
+                   exclude_self: bool = False):
+    """All-pairs cosine similarity + top-k over a set of image vectors.
+
+    ``vectors``: CUDA fp32 tensor.  With ``database_is_sharded=False`` every rank holds the
+    full ``(N, D)`` set (replicated database) and scores only its own query rows.  With
+    ``database_is_sharded=True`` every rank holds only its ``shard_bounds`` rows; the
+    normalised shards are all-gathered once (bf16 halves that traffic) and the rank's own
+    rows are the queries.  Returns ``(scores, indices)``: for the rank's rows when
+    ``gather=False``, else for all N rows on every rank.
+    """
+    import torch
+    import torch.distributed as dist
+    xn = l2_normalize(vectors, dtype)
+    if world > 1 and database_is_sharded:
+        counts = [hi - lo for lo, hi in (shard_bounds_total(xn.shape[0], world, group, r) for r in range(world))]
+        n_total = sum(counts)
+        pad = max(counts)
+        mine = xn if xn.shape[0] == pad else torch.cat([xn, xn.new_zeros((pad - xn.shape[0], xn.shape[1]))])
+        full = torch.empty((world * pad, xn.shape[1]), dtype=xn.dtype, device=xn.device)
+        dist.all_gather_into_tensor(full, mine.contiguous(), group=group)
+        if any(c != pad for c in counts):
+            keep = torch.cat([torch.arange(r * pad, r * pad + c) for r, c in enumerate(counts)]).to(xn.device)
+            full = full[keep]
+        db, q = full, xn
+    else:
+        n_total = xn.shape[0]
+        lo, hi = shard_bounds(n_total, world, rank)
+        db, q = xn, xn[lo:hi]
+    kk = k + 1 if exclude_self else k
+    scores, idx = cosine_topk(q, db, kk)
+    if exclude_self:
+        lo, _ = shard_bounds(n_total, world, rank)
+        own = torch.arange(lo, lo + q.shape[0], device=idx.device).unsqueeze(1)
+        keep = idx != own
+        # drop the self column where present, else the last column
+        order = torch.argsort((~keep).to(torch.int8), dim=1, stable=True)[:, :k]
+        scores, idx = torch.gather(scores, 1, order), torch.gather(idx, 1, order)
+    if gather and world > 1:
+        return gather_topk(scores, idx, n_total, group)
+    return scores, idx
+
+
+def shard_bounds_total(local_rows: int, world: int, group, r: int) -> tuple[int, int]:
+    """Row range of rank r when only local row counts are known (all ranks call this)."""
+    import torch
+    import torch.distributed as dist
+    cache = getattr(shard_bounds_total, "_cache", None)
+    key = (local_rows, world, id(group))
+    if cache is None or cache[0] != key:
+        t = torch.tensor([local_rows], dtype=torch.int64)
+        if dist.get_backend(group) == "nccl":
+            t = t.cuda()
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t, group=group)
+        counts = [int(o.item()) for o in out]
+        starts = np.concatenate([[0], np.cumsum(counts)])
+        shard_bounds_total._cache = cache = (key, starts)
+    starts = cache[1]
+    return int(starts[r]), int(starts[r + 1])
+
+
+def label_metrics(topk_idx, db_labels, query_labels):
+    """Top-k accuracy hits and per-query average precision (``eval.py:82-98,126-145``,
+    quirk Q6) on the device.  Returns (hits int32 [nq], ap fp32 [nq])."""
+    import torch
+    nq, k = topk_idx.shape
+    dev = topk_idx.device
+    hits = torch.empty((nq,), dtype=torch.int32, device=dev)
+    ap = torch.empty((nq,), dtype=torch.float32, device=dev)
+    dbl = db_labels.to(device=dev, dtype=torch.int32).contiguous()
+    ql = query_labels.to(device=dev, dtype=torch.int32).contiguous()
+    with torch.cuda.device(dev):
+        N.check(N.lib().pvs_topk_label_metrics(topk_idx.contiguous().data_ptr(), dbl.data_ptr(), ql.data_ptr(), nq, k,
+                                               hits.data_ptr(), ap.data_ptr(),
+                                               torch.cuda.current_stream(dev).cuda_stream))
+    return hits, ap
