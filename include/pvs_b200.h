@@ -173,6 +173,12 @@ int pvs_cosine_matrix_host(const float* x_host, int64_t n, const float* y_host, 
 int pvs_cosine_topk_host(const float* q_host, int64_t n_q, const float* db_host, int64_t n_db, int64_t d,
                          int k, int use_bf16, float* scores_out_host, int64_t* idx_out_host);
 
+/* ---- validation hook for the tcgen05 machinery (used by tests/test_gpu_tc.py) ----------
+ * mode 0: tf32 single pass, 1: 3xTF32 (hi+lo parts), 2: bf16 -- C[m,n] = A[m,k] B[n,k]^T;
+ * mode 3: tf32, 4: 3xTF32 with MN-major operands   -- C[m,n] = A[k,m]^T B[k,n]. */
+int pvs_debug_tc_gemm(int mode, const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
+                      float* c_dev, int m, int n, int k, int block_n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

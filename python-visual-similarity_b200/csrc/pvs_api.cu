@@ -711,7 +711,3 @@ extern "C" int pvs_cosine_topk_host(const float* q, int64_t n_q, const float* db
     PVS_CUDA(cudaStreamSynchronize(sl.stream));
     return PVS_OK;
 }
-
-namespace pvs {
-bool tc_available() { return false; }
-}

@@ -1,0 +1,336 @@
+// pvs_tc.cuh -- sm_100a tensor-core machinery shared by the tcgen05 kernels:
+// mbarrier / TMA / tcgen05 (alloc, mma, commit, ld) PTX wrappers, UMMA shared-memory and
+// instruction descriptors, host-side TMA tensor-map encoding, and one warp-specialised
+// persistent kernel skeleton (TMA producer warp -> MMA issuer warp -> 4 epilogue warps,
+// smem ring + double-buffered TMEM accumulators) that every contraction instantiates
+// with a small policy struct.
+//
+// Precision modes of the contraction (all accumulate in fp32 in TMEM):
+//   PASSES == 1 : one tcgen05.mma per k-step (bf16 x bf16 for similarity).
+//   PASSES == 3 : "3xTF32" -- both operands are supplied as tf32-exact hi + lo parts and
+//                 the product is hi*lo + lo*hi + hi*hi, which restores fp32-class accuracy
+//                 (tools/tf32_split_study.py: any cheaper split misses the 1e-4 parity bar).
+#pragma once
+#include <cuda.h>
+#include "pvs_common.cuh"
+
+namespace pvs {
+namespace tc {
+
+// ---------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 6000000000LL) __trap();      // ~3 s at 2 GHz
+    }
+}
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+// 2-D tiled TMA load global -> shared, completion on an mbarrier (c0 = innermost coordinate)
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot_in_smem)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "n"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem]; one elected thread issues on behalf of the CTA
+template <bool BF16>
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    if constexpr (BF16) {
+        asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+                     ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    } else {
+        asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+                     ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    }
+}
+// all previously issued MMAs of this thread arrive on `bar` when they complete
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets lane (base + i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
+{
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------
+// descriptors
+// ---------------------------------------------------------------------------------------
+// Shared-memory matrix descriptor, 128-byte swizzle (bit layout: cute/arch/mma_sm100_desc.hpp).
+//   K-major operand : rows of 128 B (one swizzle span along K); 8-row groups SBO = 1024 B apart.
+//   MN-major operand: rows of 128 B run along M/N; 8 consecutive K rows form one 1024 B atom;
+//                     LBO = byte stride between 128-B column blocks, SBO = between 8-row groups.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;          // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;          // SWIZZLE_128B
+    return d;
+}
+// Instruction descriptor: fp32 accumulate, A/B format tf32 (2) or bf16 (1), majors, N>>3, M>>4
+__host__ __device__ constexpr uint32_t make_idesc(bool bf16, bool a_mn, bool b_mn, int m, int n)
+{
+    return (1u << 4) | ((bf16 ? 1u : 2u) << 7) | ((bf16 ? 1u : 2u) << 10) | ((a_mn ? 1u : 0u) << 15) |
+           ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------
+// host: TMA tensor maps (driver entry point resolved at run time, no libcuda link)
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn();
+// 2-D row-major [rows, cols] tensor with a row pitch of ld elements; box = box_cols x box_rows,
+// box_cols * elem_bytes must be 128 (one swizzle span).
+int make_tmap_2d(CUtensorMap* out, const void* base, bool bf16, int64_t rows, int64_t cols, int64_t ld,
+                 int box_cols, int box_rows);
+
+// ---------------------------------------------------------------------------------------
+// kernel skeleton
+// ---------------------------------------------------------------------------------------
+// Policy P provides:
+//   struct Params; struct Tile { int nkb; ... };
+//   static constexpr: bool BF16; int PASSES, BLOCK_N, STAGES, KSTEPS (k-steps per k-block);
+//                     bool A_MN, B_MN; int A_BYTES, B_BYTES (one precision part of one stage),
+//                     A_LBO, B_LBO (MN-major block stride, bytes); bool EPI_READS_STAGES;
+//                     int SCRATCH_BYTES (extra smem for the epilogue)
+//   __device__ static int   num_tiles(const Params&);
+//   __device__ static Tile  tile(const Params&, int idx);
+//   __device__ static void  load(const Params&, const Tile&, int kb, uint8_t* a_hi, uint8_t* a_lo,
+//                                uint8_t* b_hi, uint8_t* b_lo, uint64_t* bar);     (one thread)
+//   __device__ static void  consume(...)   (only if EPI_READS_STAGES; 128 epilogue threads)
+//   __device__ static void  epilogue(const Params&, const Tile&, uint32_t tmem_acc, int quarter, int lane,
+//                                    uint8_t* scratch, EpiState&);
+template <class P>
+struct Layout {
+    static constexpr int PARTS = P::PASSES == 3 ? 2 : 1;
+    static constexpr int STAGE_BYTES = PARTS * (P::A_BYTES + P::B_BYTES);
+    static constexpr int RING_BYTES = P::STAGES * STAGE_BYTES;
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int SMEM_BYTES = 1024 /*alignment slack*/ + RING_BYTES + BAR_BYTES + P::SCRATCH_BYTES;
+    static constexpr int TMEM_COLS = 2 * P::BLOCK_N <= 32 ? 32 : 2 * P::BLOCK_N <= 64 ? 64 : 2 * P::BLOCK_N <= 128 ? 128
+                                     : 2 * P::BLOCK_N <= 256 ? 256 : 512;
+    static_assert(2 * P::BLOCK_N <= 512, "accumulator does not fit TMEM twice");
+    static_assert(P::A_BYTES % 1024 == 0 && P::B_BYTES % 1024 == 0, "operand tiles must keep 1024-B alignment");
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
+};
+
+constexpr int TC_THREADS = 192;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+
+template <class P>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_kernel(const __grid_constant__ typename P::Params prm)
+{
+    using L = Layout<P>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::RING_BYTES);
+    uint64_t* empty = full + P::STAGES;
+    uint64_t* tfull = empty + P::STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint8_t* scratch = smem + L::RING_BYTES + L::BAR_BYTES;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < P::STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1 + (P::EPI_READS_STAGES ? 4 : 0));
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull[a], 1);
+            mbar_init(&tempty[a], 4);
+        }
+        fence_barrier_init();
+        P::prefetch(prm);
+    }
+    if (warp == 1) tmem_alloc<L::TMEM_COLS>(tmem_slot);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int n_tiles = P::num_tiles(prm);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const typename P::Tile tl = P::tile(prm, t);
+                for (int kb = 0; kb < tl.nkb; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_expect_tx(&full[stage], L::STAGE_BYTES);
+                    uint8_t* sp = smem + stage * L::STAGE_BYTES;
+                    P::load(prm, tl, kb, sp, sp + P::A_BYTES, sp + L::PARTS * P::A_BYTES,
+                            sp + L::PARTS * P::A_BYTES + P::B_BYTES, &full[stage]);
+                    if (++stage == P::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(P::BF16, P::A_MN, P::B_MN, 128, P::BLOCK_N);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const typename P::Tile tl = P::tile(prm, t);
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P::BLOCK_N);
+                for (int kb = 0; kb < tl.nkb; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tcgen05_fence_after();
+                    const uint32_t sp = smem_u32(smem + stage * L::STAGE_BYTES);
+                    const uint32_t a_hi = sp, a_lo = sp + P::A_BYTES;
+                    const uint32_t b_hi = sp + L::PARTS * P::A_BYTES, b_lo = b_hi + P::B_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < P::KSTEPS; ++ks) {
+                        const uint32_t a_off = P::A_MN ? ks * 1024 : ks * 32;
+                        const uint32_t b_off = P::B_MN ? ks * 1024 : ks * 32;
+                        const uint32_t a_l = P::A_MN ? P::A_LBO : 16, b_l = P::B_MN ? P::B_LBO : 16;
+                        const uint64_t da_hi = make_smem_desc(a_hi + a_off, a_l, 1024);
+                        const uint64_t db_hi = make_smem_desc(b_hi + b_off, b_l, 1024);
+                        const uint32_t first = (kb > 0 || ks > 0) ? 1u : 0u;
+                        if constexpr (P::PASSES == 3) {
+                            const uint64_t da_lo = make_smem_desc(a_lo + a_off, a_l, 1024);
+                            const uint64_t db_lo = make_smem_desc(b_lo + b_off, b_l, 1024);
+                            umma<P::BF16>(d_tmem, da_hi, db_lo, idesc, first);
+                            umma<P::BF16>(d_tmem, da_lo, db_hi, idesc, 1u);
+                            umma<P::BF16>(d_tmem, da_hi, db_hi, idesc, 1u);
+                        } else {
+                            umma<P::BF16>(d_tmem, da_hi, db_hi, idesc, first);
+                        }
+                    }
+                    umma_commit(&empty[stage]);          // smem slot free once these MMAs retire
+                    if (++stage == P::STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull[acc]);                // accumulator complete
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        typename P::EpiState st;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const typename P::Tile tl = P::tile(prm, t);
+            P::epi_begin(prm, tl, st, quarter, lane);
+            if constexpr (P::EPI_READS_STAGES) {
+                for (int kb = 0; kb < tl.nkb; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    uint8_t* sp = smem + stage * L::STAGE_BYTES;
+                    P::consume(prm, tl, kb, sp, sp + P::A_BYTES, sp + L::PARTS * P::A_BYTES,
+                               sp + L::PARTS * P::A_BYTES + P::B_BYTES, st, quarter, lane);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[stage]);
+                    if (++stage == P::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+            mbar_wait(&tfull[acc], acc_phase);
+            tcgen05_fence_after();
+            P::epilogue(prm, tl, tmem_base + (uint32_t)(acc * P::BLOCK_N) + ((uint32_t)(quarter * 32) << 16), quarter,
+                        lane, scratch, st);
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<L::TMEM_COLS>(tmem_base);
+}
+
+template <class P>
+int launch_tc(const typename P::Params& prm, int n_tiles, cudaStream_t st)
+{
+    using L = Layout<P>;
+    static bool configured = false;
+    if (!configured) {
+        PVS_CUDA(cudaFuncSetAttribute(tc_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_BYTES));
+        configured = true;
+    }
+    if (n_tiles <= 0) return PVS_OK;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = n_tiles < sms ? n_tiles : sms;     // persistent: one CTA per SM
+    tc_kernel<P><<<grid, TC_THREADS, L::SMEM_BYTES, st>>>(prm);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PVS_ERR_CUDA, "tcgen05 kernel launch failed: %s", cudaGetErrorString(e));
+    return PVS_OK;
+}
+
+}  // namespace tc
+}  // namespace pvs
