@@ -123,17 +123,23 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // descriptors
 // ---------------------------------------------------------------------------------------
 // Shared-memory matrix descriptor, 128-byte swizzle (bit layout: cute/arch/mma_sm100_desc.hpp).
-//   K-major operand : rows of 128 B (one swizzle span along K); 8-row groups SBO = 1024 B apart.
-//   MN-major operand: rows of 128 B run along M/N; 8 consecutive K rows form one 1024 B atom;
-//                     LBO = byte stride between 128-B column blocks, SBO = between 8-row groups.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+//   K-major operand : SWIZZLE_128B (2): rows of 128 B (one swizzle span along K), 16-B chunks
+//                     XOR-ed with (row & 7); 8-row groups SBO = 1024 B apart.
+//   MN-major tf32   : SWIZZLE_128B_BASE32B (1) -- the only MN-major layout tf32 supports
+//                     (cutlass sm100_common.inl:92): rows of 128 B run along M/N, 32-B chunks
+//                     XOR-ed with (row & 3); 4 consecutive K rows form one 512-B atom;
+//                     LBO = byte stride between 128-B column blocks, SBO = between 4-row groups.
+//                     The matching TMA mode is CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+constexpr uint32_t LAYOUT_SW128 = 2, LAYOUT_SW128_BASE32B = 1;
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type)
 {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;          // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;          // SWIZZLE_128B
+    d |= (uint64_t)layout_type << 61;
     return d;
 }
 // Instruction descriptor: fp32 accumulate, A/B format tf32 (2) or bf16 (1), majors, N>>3, M>>4
@@ -153,7 +159,7 @@ EncodeTiledFn encode_tiled_fn();
 // 2-D row-major [rows, cols] tensor with a row pitch of ld elements; box = box_cols x box_rows,
 // box_cols * elem_bytes must be 128 (one swizzle span).
 int make_tmap_2d(CUtensorMap* out, const void* base, bool bf16, int64_t rows, int64_t cols, int64_t ld,
-                 int box_cols, int box_rows);
+                 int box_cols, int box_rows, bool mn_major = false);
 
 // ---------------------------------------------------------------------------------------
 // kernel skeleton
@@ -181,6 +187,7 @@ struct Layout {
     static constexpr int TMEM_COLS = 2 * P::BLOCK_N <= 32 ? 32 : 2 * P::BLOCK_N <= 64 ? 64 : 2 * P::BLOCK_N <= 128 ? 128
                                      : 2 * P::BLOCK_N <= 256 ? 256 : 512;
     static_assert(2 * P::BLOCK_N <= 512, "accumulator does not fit TMEM twice");
+    static_assert(!(P::BF16 && (P::A_MN || P::B_MN)), "MN-major operands are implemented for tf32 only");
     static_assert(P::A_BYTES % 1024 == 0 && P::B_BYTES % 1024 == 0, "operand tiles must keep 1024-B alignment");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
 };
@@ -257,12 +264,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_kernel(const __grid_constant
                         const uint32_t a_off = P::A_MN ? ks * 1024 : ks * 32;
                         const uint32_t b_off = P::B_MN ? ks * 1024 : ks * 32;
                         const uint32_t a_l = P::A_MN ? P::A_LBO : 16, b_l = P::B_MN ? P::B_LBO : 16;
-                        const uint64_t da_hi = make_smem_desc(a_hi + a_off, a_l, 1024);
-                        const uint64_t db_hi = make_smem_desc(b_hi + b_off, b_l, 1024);
+                        const uint32_t a_s = P::A_MN ? 512 : 1024, b_s = P::B_MN ? 512 : 1024;
+                        const uint32_t a_t = P::A_MN ? LAYOUT_SW128_BASE32B : LAYOUT_SW128;
+                        const uint32_t b_t = P::B_MN ? LAYOUT_SW128_BASE32B : LAYOUT_SW128;
+                        const uint64_t da_hi = make_smem_desc(a_hi + a_off, a_l, a_s, a_t);
+                        const uint64_t db_hi = make_smem_desc(b_hi + b_off, b_l, b_s, b_t);
                         const uint32_t first = (kb > 0 || ks > 0) ? 1u : 0u;
                         if constexpr (P::PASSES == 3) {
-                            const uint64_t da_lo = make_smem_desc(a_lo + a_off, a_l, 1024);
-                            const uint64_t db_lo = make_smem_desc(b_lo + b_off, b_l, 1024);
+                            const uint64_t da_lo = make_smem_desc(a_lo + a_off, a_l, a_s, a_t);
+                            const uint64_t db_lo = make_smem_desc(b_lo + b_off, b_l, b_s, b_t);
                             umma<P::BF16>(d_tmem, da_hi, db_lo, idesc, first);
                             umma<P::BF16>(d_tmem, da_lo, db_hi, idesc, 1u);
                             umma<P::BF16>(d_tmem, da_hi, db_hi, idesc, 1u);

@@ -27,7 +27,7 @@ EncodeTiledFn encode_tiled_fn()
 }
 
 int make_tmap_2d(CUtensorMap* out, const void* base, bool bf16, int64_t rows, int64_t cols, int64_t ld,
-                 int box_cols, int box_rows)
+                 int box_cols, int box_rows, bool mn_major)
 {
     EncodeTiledFn fn = encode_tiled_fn();
     PVS_CHECK(fn, PVS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
@@ -42,7 +42,8 @@ int make_tmap_2d(CUtensorMap* out, const void* base, bool bf16, int64_t rows, in
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(out, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                     const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     PVS_CHECK(r == CUDA_SUCCESS, PVS_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return PVS_OK;
 }
@@ -186,11 +187,11 @@ extern "C" int pvs_debug_tc_gemm(int mode, const void* a_hi, const void* a_lo, c
             if ((rc = tc::make_tmap_2d(&p.b_lo, b_lo, false, n, k, k, bk, block_n))) return rc;
         }
     } else {
-        if ((rc = tc::make_tmap_2d(&p.a_hi, a_hi, false, k, m, m, 32, 32))) return rc;
-        if ((rc = tc::make_tmap_2d(&p.b_hi, b_hi, false, k, n, n, 32, 32))) return rc;
+        if ((rc = tc::make_tmap_2d(&p.a_hi, a_hi, false, k, m, m, 32, 32, true))) return rc;
+        if ((rc = tc::make_tmap_2d(&p.b_hi, b_hi, false, k, n, n, 32, 32, true))) return rc;
         if (three) {
-            if ((rc = tc::make_tmap_2d(&p.a_lo, a_lo, false, k, m, m, 32, 32))) return rc;
-            if ((rc = tc::make_tmap_2d(&p.b_lo, b_lo, false, k, n, n, 32, 32))) return rc;
+            if ((rc = tc::make_tmap_2d(&p.a_lo, a_lo, false, k, m, m, 32, 32, true))) return rc;
+            if ((rc = tc::make_tmap_2d(&p.b_lo, b_lo, false, k, n, n, 32, 32, true))) return rc;
         }
     }
     cudaStream_t st = (cudaStream_t)stream;
