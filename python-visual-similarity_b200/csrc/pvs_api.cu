@@ -44,11 +44,11 @@ constexpr int64_t ASSIGN_CHUNK_ROWS = 1 << 18;
 // ---- optional per-stage device timing (CUDA events on the launching stream) -------------
 enum Stage { ST_PCA = 0, ST_KM_SCORES, ST_KM_ARGMIN, ST_VLAD_AGG, ST_GMM_LOGITS, ST_GMM_SOFTMAX, ST_FV_STATS,
              ST_FV_FINALIZE, ST_L2NORM, ST_SIM_GEMM, ST_TOPK_SELECT, ST_TC_VLAD_ASSIGN, ST_TC_FV_POSTERIOR,
-             ST_TC_FV_STATS, ST_TC_SIM_TOPK, ST_COUNT };
+             ST_TC_FV_STATS, ST_TC_SIM_TOPK, ST_TC_FV_PREP, ST_TC_FV_PROJECT, ST_COUNT };
 static const char* kStageNames[ST_COUNT] = {
     "pca_project", "kmeans_scores", "kmeans_argmin", "vlad_aggregate", "gmm_logits", "gmm_softmax", "fv_stats",
     "fv_finalize", "l2_normalize", "sim_gemm", "topk_select", "tc_vlad_assign", "tc_fv_posterior", "tc_fv_stats",
-    "tc_sim_topk"};
+    "tc_sim_topk", "tc_fv_prep", "tc_fv_project"};
 struct StageRec { int stage; cudaEvent_t a, b; };
 static std::mutex g_prof_mu;
 static std::atomic<int> g_prof_on{0};
@@ -218,6 +218,7 @@ extern "C" int pvs_gmm_create(const double* w, const double* mu, const double* c
     m->g_pi = m->pi + k;
     m->g_mu = m->g_pi + k;
     m->g_sig = m->g_mu + kd;
+    if (int s = tc_prepare_model(m)) { pvs_model_destroy(m); return s; }
     *out = m;
     return PVS_OK;
 }
@@ -239,6 +240,7 @@ extern "C" int pvs_pca_create(const float* comp, const float* mean, int d_out, i
     if (int s = upload_block(m, h)) { delete m; return s; }
     m->comp = (const float*)m->block;
     m->bias = m->comp + (size_t)d_out * d_in;
+    if (int s = tc_prepare_model(m)) { pvs_model_destroy(m); return s; }
     *out = m;
     return PVS_OK;
 }
@@ -380,9 +382,19 @@ static FvWs fv_ws(const pvs_model* g, const pvs_model* pca, int64_t rows, int64_
     return w;
 }
 
+static bool fv_use_tc(const pvs_model* g, const pvs_model* pca, int64_t rows, int64_t n_images)
+{
+    return g_path.load() != PVS_PATH_SIMT && tc_fv_supported(g, pca, rows, n_images);
+}
+
 extern "C" size_t pvs_fv_workspace_bytes(const pvs_model* g, const pvs_model* pca, int64_t total_rows, int64_t n_images)
 {
     if (!g || total_rows < 0 || n_images < 0) return 0;
+    if (g->kind == PVS_MODEL_GMM_DIAG && fv_use_tc(g, pca, total_rows, n_images)) {
+        TcFvPlan pl;
+        tc_fv_plan(g, pca, total_rows, n_images, nullptr, &pl);
+        return pl.total;
+    }
     return fv_ws(g, pca, total_rows, n_images).total;
 }
 
@@ -395,6 +407,23 @@ extern "C" int pvs_fv_encode(const pvs_model* g, const pvs_model* pca, const flo
     PVS_CHECK(norm_order > 0.f, PVS_ERR_UNSUPPORTED, "norm_order must be > 0 (or inf), got %g", (double)norm_order);
     if (n_images == 0) return PVS_OK;
     PVS_CHECK(offsets && out && (total_rows == 0 || desc), PVS_ERR_BAD_ARG, "pvs_fv_encode: NULL buffer");
+    if (fv_use_tc(g, pca, total_rows, n_images)) {
+        // tcgen05 path: 3xTF32 contractions, see pvs_tc_fv.cu
+        cudaStream_t st = (cudaStream_t)stream;
+        TcFvPlan pl;
+        tc_fv_plan(g, pca, total_rows, n_images, nullptr, &pl);
+        PVS_CHECK(workspace && workspace_bytes >= pl.total, PVS_ERR_WORKSPACE,
+                  "pvs_fv_encode: workspace %zu < required %zu", workspace_bytes, pl.total);
+        char* ws = (char*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
+        tc_fv_plan(g, pca, total_rows, n_images, ws, &pl);
+        if (int rc = PVS_STAGE(ST_TC_FV_PREP, st, tc_fv_prep(pl, offsets, n_images, total_rows, st))) return rc;
+        if (int rc = PVS_STAGE(ST_TC_FV_PROJECT, st, tc_fv_project(pl, g, pca, desc, total_rows, st))) return rc;
+        if (int rc = PVS_STAGE(ST_TC_FV_POSTERIOR, st, tc_fv_posterior(pl, g, offsets, n_images, total_rows, argmax_out, st))) return rc;
+        if (int rc = PVS_STAGE(ST_TC_FV_STATS, st, tc_fv_stats(pl, offsets, n_images, total_rows, st))) return rc;
+        return PVS_STAGE(ST_FV_FINALIZE, st, launch_fv_finalize(pl.S, g, n_images, power, norm_order, eps, out, st));
+    }
+    PVS_CHECK(g_path.load() != PVS_PATH_TENSOR, PVS_ERR_UNSUPPORTED,
+              "pvs_fv_encode: the tensor-core path handles K=256, D=64 (d_in %% 32 == 0) only");
     const FvWs w = fv_ws(g, pca, total_rows, n_images);
     PVS_CHECK(workspace && workspace_bytes >= w.total, PVS_ERR_WORKSPACE,
               "pvs_fv_encode: workspace %zu < required %zu", workspace_bytes, w.total);

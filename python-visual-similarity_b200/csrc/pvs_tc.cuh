@@ -118,6 +118,36 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// the mirror store: thread i of the warp writes 32 consecutive fp32 columns of lane (base + i)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32])
+{
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// barrier among the 128 epilogue threads only (id 1; id 0 is __syncthreads)
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// tf32 split: x = hi + lo (+ O(2^-22 |x|)), both parts exactly representable in tf32
+__device__ __forceinline__ float tf32_rn(float x)
+{
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void tf32_split(float x, float& hi, float& lo)
+{
+    hi = tf32_rn(x);
+    lo = tf32_rn(x - hi);
+}
 
 // ---------------------------------------------------------------------------------------
 // descriptors
@@ -292,6 +322,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_kernel(const __grid_constant
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0;
         typename P::EpiState st;
+        P::epi_init(prm, scratch, (int)threadIdx.x - 64);
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             const typename P::Tile tl = P::tile(prm, t);
             P::epi_begin(prm, tl, st, quarter, lane);

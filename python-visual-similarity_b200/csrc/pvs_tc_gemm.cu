@@ -85,6 +85,7 @@ struct GemmKMajor {
             tma_load_2d(b_lo, &p.b_lo, bar, kb * BK, t.nb * BLOCK_N);
         }
     }
+    __device__ static void epi_init(const Params&, uint8_t*, int) {}
     __device__ static void epi_begin(const Params&, const Tile&, EpiState&, int, int) {}
     __device__ static void epilogue(const Params& p, const Tile& t, uint32_t tmem, int quarter, int lane, uint8_t*,
                                     EpiState&)
@@ -129,6 +130,7 @@ struct GemmMNMajor {
             if constexpr (PASSES == 3) tma_load_2d(b_lo + b * B_LBO, &p.b_lo, bar, t.nb * BLOCK_N + 32 * b, kb * KT);
         }
     }
+    __device__ static void epi_init(const Params&, uint8_t*, int) {}
     __device__ static void epi_begin(const Params&, const Tile&, EpiState&, int, int) {}
     __device__ static void epilogue(const Params& p, const Tile& t, uint32_t tmem, int quarter, int lane, uint8_t* s,
                                     EpiState& st)

@@ -191,3 +191,9 @@ def profile_read() -> dict:
         if n.value:
             out[lib().pvs_profile_stage_name(s).decode()] = (ms.value, n.value)
     return out
+
+
+def set_path(path: int) -> None:
+    """PATH_AUTO (tensor cores when the shape allows), PATH_SIMT, PATH_TENSOR (error if the
+    shape is not supported by the tcgen05 kernels)."""
+    check(lib().pvs_set_path(int(path)))

@@ -364,3 +364,81 @@ def test_eval_functions(api):
     dbl = np.array([i % 3 for i in range(12)])
     assert np.isclose(acc, O.top_k_accuracy_from_lists(idx[:, :3], dbl, np.array(ql)))
     assert np.isclose(mp, O.top_k_map_from_lists(idx, dbl, np.array(ql)))
+
+
+# ---------------------------------------------------------------------------------------
+# tensor-core (tcgen05, 3xTF32) path vs CUDA-core path
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case,member", [c for c in FV_CASES if c[0] in ("fv_sift_pca", "fv_sift_pca_gmmsampled", "fv_rootsift_pca")])
+def test_fv_tensor_path_matches_golden_and_simt(api, case, member):
+    g = load_golden(case)
+    enc = api.enc.FisherVectorEncoder(feature_extractor=api.feat.Descriptors(128), weights=api.enc.GMMWeights[member])
+    descs = split(g["desc"], g["offsets"])
+    try:
+        api.nat.set_path(api.nat.PATH_TENSOR)
+        out_tc = enc.encode(descs)
+        api.nat.set_path(api.nat.PATH_SIMT)
+        out_simt = enc.encode(descs)
+    finally:
+        api.nat.set_path(api.nat.PATH_AUTO)
+    e_tc, e_simt = rel_l2(out_tc, g["out"]), rel_l2(out_simt, g["out"])
+    assert e_tc <= 1e-4 and e_simt <= 1e-4, (e_tc, e_simt)
+    assert rel_l2(out_tc, out_simt) <= 1e-4
+
+
+def test_fv_tensor_path_ragged_batch_vs_oracle(api):
+    """Ragged T (1, 31, 32, 33, 128, 129, 517, 2000), GMM-sampled descriptors so the
+    posteriors are spread over many components; tensor path forced."""
+    w = load_weights("gmm_k256_sift_pca")
+    p = load_weights("pca_k256_sift_f2")
+    r = np.random.RandomState(5)
+    descs = []
+    for t in (1, 31, 32, 33, 128, 129, 517, 2000):
+        comp = r.choice(256, size=t, p=w["weights"] / w["weights"].sum())
+        y = w["means"][comp] + r.standard_normal((t, 64)) * np.sqrt(w["covariances"][comp])
+        descs.append((y @ p["components"] + p["mean"]).astype(np.float32))
+    enc = api.enc.FisherVectorEncoder(feature_extractor=api.feat.Descriptors(128),
+                                      weights=api.enc.GMMWeights.OXFORD102_K256_SIFT_PCA)
+    try:
+        api.nat.set_path(api.nat.PATH_TENSOR)
+        out = enc.encode(descs)
+    finally:
+        api.nat.set_path(api.nat.PATH_AUTO)
+    ref = O.fv_encode(descs, w["weights"], w["means"], w["covariances"], w["precisions_cholesky"],
+                      pca=(p["components"], p["mean"]))
+    errs = [rel_l2(out[i], ref[i]) for i in range(len(descs))]
+    assert max(errs) <= 1e-4, errs
+
+
+def test_fv_tensor_path_without_pca_d64(api):
+    """K=256, D=64 GMM fed 64-D descriptors directly (no PCA stage)."""
+    w = load_weights("gmm_k256_root_sift_pca")
+    from sklearn.mixture import GaussianMixture
+    gm = GaussianMixture(n_components=256, covariance_type="diag")
+    gm.weights_, gm.means_, gm.covariances_, gm.precisions_cholesky_ = (w["weights"], w["means"], w["covariances"],
+                                                                        w["precisions_cholesky"])
+    gm.n_features_in_ = 64
+    r = np.random.RandomState(2)
+    descs = []
+    for t in (40, 300):
+        comp = r.choice(256, size=t)
+        descs.append((w["means"][comp] + r.standard_normal((t, 64)) * np.sqrt(w["covariances"][comp])).astype(np.float32))
+    enc = api.enc.FisherVectorEncoder(feature_extractor=api.feat.Descriptors(64), gmm_model=gm)
+    try:
+        api.nat.set_path(api.nat.PATH_TENSOR)
+        out = enc.encode(descs)
+    finally:
+        api.nat.set_path(api.nat.PATH_AUTO)
+    ref = O.fv_encode(descs, w["weights"], w["means"], w["covariances"], w["precisions_cholesky"])
+    assert rel_l2(out, ref) <= 1e-4
+
+
+def test_tensor_path_refuses_unsupported_shape(api):
+    enc = api.enc.FisherVectorEncoder(feature_extractor=api.feat.Descriptors(128),
+                                      weights=api.enc.GMMWeights.OXFORD102_K256_SIFT)      # D = 128
+    try:
+        api.nat.set_path(api.nat.PATH_TENSOR)
+        with pytest.raises(api.nat.PvsError):
+            enc.encode([np.ones((5, 128), np.float32)])
+    finally:
+        api.nat.set_path(api.nat.PATH_AUTO)
