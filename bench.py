@@ -195,7 +195,7 @@ def run_ours(args):
         out = step()
     barrier()
     N.lib().pvs_launch_count_reset()
-    N.profile_enable(True)
+    N.profile_enable(not args.no_profile)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
         barrier()
@@ -316,6 +316,7 @@ def main():
     ap.add_argument("--e2e-images", type=int, default=0, help="images in the host-buffer leg (0 = all)")
     ap.add_argument("--cpu-sample", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true", help="skip the per-stage CUDA-event timing")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -416,10 +416,11 @@ extern "C" int pvs_fv_encode(const pvs_model* g, const pvs_model* pca, const flo
                   "pvs_fv_encode: workspace %zu < required %zu", workspace_bytes, pl.total);
         char* ws = (char*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
         tc_fv_plan(g, pca, total_rows, n_images, ws, &pl);
-        if (int rc = PVS_STAGE(ST_TC_FV_PREP, st, tc_fv_prep(pl, offsets, n_images, total_rows, st))) return rc;
-        if (int rc = PVS_STAGE(ST_TC_FV_PROJECT, st, tc_fv_project(pl, g, pca, desc, total_rows, st))) return rc;
-        if (int rc = PVS_STAGE(ST_TC_FV_POSTERIOR, st, tc_fv_posterior(pl, g, offsets, n_images, total_rows, argmax_out, st))) return rc;
-        if (int rc = PVS_STAGE(ST_TC_FV_STATS, st, tc_fv_stats(pl, offsets, n_images, total_rows, st))) return rc;
+        const float* y = pca ? pl.y : desc;
+        if (pca)
+            if (int rc = PVS_STAGE(ST_TC_FV_PROJECT, st, tc_fv_project(pl, pca, desc, total_rows, st))) return rc;
+        if (int rc = PVS_STAGE(ST_TC_FV_POSTERIOR, st, tc_fv_posterior(pl, g, y, total_rows, argmax_out, st))) return rc;
+        if (int rc = PVS_STAGE(ST_TC_FV_STATS, st, tc_fv_stats(pl, y, offsets, n_images, st))) return rc;
         return PVS_STAGE(ST_FV_FINALIZE, st, launch_fv_finalize(pl.S, g, n_images, power, norm_order, eps, out, st));
     }
     PVS_CHECK(g_path.load() != PVS_PATH_TENSOR, PVS_ERR_UNSUPPORTED,

@@ -45,25 +45,18 @@ int launch_label_metrics(const int64_t* idx, const int32_t* db_labels, const int
 bool tc_available();
 int tc_prepare_model(pvs_model* m);
 
-// Fisher vector, K = 256 / D = 64: workspace carve-up and the four tensor-core stages
+// Fisher vector, K = 256 / D = 64: workspace carve-up and the three tensor-core stages
 struct TcFvPlan {
-    float *x_hi, *x_lo;          // tf32 split of the raw descriptors (PCA models only)
-    float *y_hi, *y_lo;          // Yaug = [ y*y | y ], [rows, 128]
-    float *q_hi, *q_lo;          // posteriors, image-padded rows, [q_rows_cap, 256]
+    float* y;                    // [rows, 64] projected descriptors (NULL without PCA: y = input)
+    float* q;                    // [rows, 256] posteriors
     float* S;                    // [n_images, 256, 129]
-    int64_t* qoff;               // [n_images + 1] padded row offsets
-    int* tile_img;               // [n_tiles] image of the first row of each 128-row tile
-    int64_t q_rows_cap;
-    int n_tiles;
+    int n_tiles;                 // 128-row tiles
     size_t total;
 };
 bool tc_fv_supported(const pvs_model* g, const pvs_model* pca, int64_t rows, int64_t n_images);
 int tc_fv_plan(const pvs_model* g, const pvs_model* pca, int64_t rows, int64_t n_images, void* ws, TcFvPlan* plan);
-int tc_fv_prep(const TcFvPlan& pl, const int64_t* offsets, int64_t n_images, int64_t rows, cudaStream_t st);
-int tc_fv_project(const TcFvPlan& pl, const pvs_model* g, const pvs_model* pca, const float* desc, int64_t rows,
-                  cudaStream_t st);
-int tc_fv_posterior(const TcFvPlan& pl, const pvs_model* g, const int64_t* offsets, int64_t n_images, int64_t rows,
-                    int32_t* argmax, cudaStream_t st);
-int tc_fv_stats(const TcFvPlan& pl, const int64_t* offsets, int64_t n_images, int64_t rows, cudaStream_t st);
+int tc_fv_project(const TcFvPlan& pl, const pvs_model* pca, const float* desc, int64_t rows, cudaStream_t st);
+int tc_fv_posterior(const TcFvPlan& pl, const pvs_model* g, const float* y, int64_t rows, int32_t* argmax, cudaStream_t st);
+int tc_fv_stats(const TcFvPlan& pl, const float* y, const int64_t* offsets, int64_t n_images, cudaStream_t st);
 
 }  // namespace pvs

@@ -216,16 +216,19 @@ struct Layout {
     static constexpr int SMEM_BYTES = 1024 /*alignment slack*/ + RING_BYTES + BAR_BYTES + P::SCRATCH_BYTES;
     static constexpr int TMEM_COLS = 2 * P::BLOCK_N <= 32 ? 32 : 2 * P::BLOCK_N <= 64 ? 64 : 2 * P::BLOCK_N <= 128 ? 128
                                      : 2 * P::BLOCK_N <= 256 ? 256 : 512;
+    // threads: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue,
+    // warps 6-9 (only with P::MANUAL) operand producers that load fp32 from global memory,
+    // split it into tf32 hi/lo parts and store the swizzled tiles themselves
+    static constexpr int THREADS = P::MANUAL ? 320 : 192;
+    static constexpr uint32_t FULL_COUNT = (P::TMA_BYTES > 0 ? 1 : 0) + (P::MANUAL ? 4 : 0);
     static_assert(2 * P::BLOCK_N <= 512, "accumulator does not fit TMEM twice");
     static_assert(!(P::BF16 && (P::A_MN || P::B_MN)), "MN-major operands are implemented for tf32 only");
     static_assert(P::A_BYTES % 1024 == 0 && P::B_BYTES % 1024 == 0, "operand tiles must keep 1024-B alignment");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
 };
 
-constexpr int TC_THREADS = 192;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
-
 template <class P>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_kernel(const __grid_constant__ typename P::Params prm)
+__global__ void __launch_bounds__(Layout<P>::THREADS, 1) tc_kernel(const __grid_constant__ typename P::Params prm)
 {
     using L = Layout<P>;
     extern __shared__ uint8_t smem_raw[];
@@ -240,7 +243,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_kernel(const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < P::STAGES; ++s) {
-            mbar_init(&full[s], 1);
+            mbar_init(&full[s], L::FULL_COUNT);
             mbar_init(&empty[s], 1 + (P::EPI_READS_STAGES ? 4 : 0));
         }
         for (int a = 0; a < 2; ++a) {
@@ -258,14 +261,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_kernel(const __grid_constant
     const int n_tiles = P::num_tiles(prm);
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (lane == 0 && P::TMA_BYTES > 0) {
             int stage = 0;
             uint32_t phase = 0;
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
                 const typename P::Tile tl = P::tile(prm, t);
                 for (int kb = 0; kb < tl.nkb; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_expect_tx(&full[stage], L::STAGE_BYTES);
+                    mbar_expect_tx(&full[stage], P::TMA_BYTES);
                     uint8_t* sp = smem + stage * L::STAGE_BYTES;
                     P::load(prm, tl, kb, sp, sp + P::A_BYTES, sp + L::PARTS * P::A_BYTES,
                             sp + L::PARTS * P::A_BYTES + P::B_BYTES, &full[stage]);
@@ -317,6 +320,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_kernel(const __grid_constant
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
+    } else if (warp >= 6) {
+        if constexpr (P::MANUAL) {
+            const int pw = warp - 6;
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const typename P::Tile tl = P::tile(prm, t);
+                for (int kb = 0; kb < tl.nkb; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sp = smem + stage * L::STAGE_BYTES;
+                    P::produce(prm, tl, kb, sp, sp + P::A_BYTES, sp + L::PARTS * P::A_BYTES,
+                               sp + L::PARTS * P::A_BYTES + P::B_BYTES, pw, lane);
+                    fence_proxy_async();                 // generic-proxy stores -> visible to the tensor core
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full[stage]);
+                    if (++stage == P::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
     } else {
         const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
         int stage = 0, acc = 0;
@@ -366,7 +388,7 @@ int launch_tc(const typename P::Params& prm, int n_tiles, cudaStream_t st)
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = n_tiles < sms ? n_tiles : sms;     // persistent: one CTA per SM
-    tc_kernel<P><<<grid, TC_THREADS, L::SMEM_BYTES, st>>>(prm);
+    tc_kernel<P><<<grid, L::THREADS, L::SMEM_BYTES, st>>>(prm);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PVS_ERR_CUDA, "tcgen05 kernel launch failed: %s", cudaGetErrorString(e));
