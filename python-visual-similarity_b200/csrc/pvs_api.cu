@@ -487,9 +487,15 @@ static int64_t topk_block_rows(int64_t n_q, int64_t n_db)
     return qb;
 }
 
+static bool sim_use_tc(int dtype, int64_t n_q, int64_t n_db, int64_t d, int k)
+{
+    return g_path.load() != PVS_PATH_SIMT && tc_sim_supported(dtype, n_q, n_db, d, k);
+}
+
 extern "C" size_t pvs_cosine_topk_workspace_bytes(int64_t n_q, int64_t n_db, int64_t d, int k, int dtype)
 {
     if (n_q < 0 || n_db <= 0 || d <= 0 || k <= 0) return 0;
+    if (sim_use_tc(dtype, n_q, n_db, d, k)) return tc_sim_workspace_bytes(n_q, n_db, k);
     size_t b = align_up((size_t)topk_block_rows(n_q, n_db) * n_db * 4, 256) + 256;
     if (dtype == PVS_BF16) b += align_up((size_t)n_q * d * 4, 256) + align_up((size_t)n_db * d * 4, 256);
     return b;
@@ -505,6 +511,12 @@ extern "C" int pvs_cosine_topk(const void* q, const void* db, int dtype, int64_t
     if (n_q == 0) return PVS_OK;
     PVS_CHECK(q && db && scores_out && idx_out, PVS_ERR_BAD_ARG, "pvs_cosine_topk: NULL buffer");
     PVS_CHECK(d < 2147483647LL && n_db < 2147483647LL, PVS_ERR_BAD_SHAPE, "pvs_cosine_topk: dimension too large");
+    if (sim_use_tc(dtype, n_q, n_db, d, k))
+        return PVS_STAGE(ST_TC_SIM_TOPK, (cudaStream_t)stream,
+                         tc_sim_topk(q, db, n_q, n_db, d, k, db_index_offset, scores_out, idx_out, workspace,
+                                     workspace_bytes, (cudaStream_t)stream));
+    PVS_CHECK(g_path.load() != PVS_PATH_TENSOR, PVS_ERR_UNSUPPORTED,
+              "pvs_cosine_topk: the tensor-core path handles bf16 operands with d %% 8 == 0, d >= 64 only");
     const size_t need = pvs_cosine_topk_workspace_bytes(n_q, n_db, d, k, dtype);
     PVS_CHECK(workspace && workspace_bytes >= need, PVS_ERR_WORKSPACE, "pvs_cosine_topk: workspace %zu < %zu",
               workspace_bytes, need);

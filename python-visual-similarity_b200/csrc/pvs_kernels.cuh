@@ -59,4 +59,10 @@ int tc_fv_project(const TcFvPlan& pl, const pvs_model* pca, const float* desc, i
 int tc_fv_posterior(const TcFvPlan& pl, const pvs_model* g, const float* y, int64_t rows, int32_t* argmax, cudaStream_t st);
 int tc_fv_stats(const TcFvPlan& pl, const float* y, const int64_t* offsets, int64_t n_images, cudaStream_t st);
 
+// similarity + fused top-k on bf16 tensor cores (pvs_tc_sim.cu)
+bool tc_sim_supported(int dtype, int64_t n_q, int64_t n_db, int64_t d, int k);
+size_t tc_sim_workspace_bytes(int64_t n_q, int64_t n_db, int k);
+int tc_sim_topk(const void* q, const void* db, int64_t n_q, int64_t n_db, int64_t d, int k, int64_t idx_offset,
+                float* scores_out, int64_t* idx_out, void* ws, size_t ws_bytes, cudaStream_t st);
+
 }  // namespace pvs

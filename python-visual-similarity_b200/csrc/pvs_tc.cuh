@@ -201,12 +201,20 @@ int make_tmap_2d(CUtensorMap* out, const void* base, bool bf16, int64_t rows, in
 //                     A_LBO, B_LBO (MN-major block stride, bytes); bool EPI_READS_STAGES;
 //                     int SCRATCH_BYTES (extra smem for the epilogue)
 //   __device__ static int   num_tiles(const Params&);
+//   __device__ static int   tile_at(const Params&, int it, int n_tiles);   it-th tile of this CTA or -1
+//                                  (strided_tile() = blockIdx.x + it * gridDim.x is the default order)
 //   __device__ static Tile  tile(const Params&, int idx);
 //   __device__ static void  load(const Params&, const Tile&, int kb, uint8_t* a_hi, uint8_t* a_lo,
 //                                uint8_t* b_hi, uint8_t* b_lo, uint64_t* bar);     (one thread)
 //   __device__ static void  consume(...)   (only if EPI_READS_STAGES; 128 epilogue threads)
 //   __device__ static void  epilogue(const Params&, const Tile&, uint32_t tmem_acc, int quarter, int lane,
 //                                    uint8_t* scratch, EpiState&);
+__device__ __forceinline__ int strided_tile(int it, int n_tiles)
+{
+    const long long t = (long long)blockIdx.x + (long long)it * gridDim.x;
+    return t < n_tiles ? (int)t : -1;
+}
+
 template <class P>
 struct Layout {
     static constexpr int PARTS = P::PASSES == 3 ? 2 : 1;
@@ -264,7 +272,7 @@ __global__ void __launch_bounds__(Layout<P>::THREADS, 1) tc_kernel(const __grid_
         if (lane == 0 && P::TMA_BYTES > 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            for (int it = 0, t; (t = P::tile_at(prm, it, n_tiles)) >= 0; ++it) {
                 const typename P::Tile tl = P::tile(prm, t);
                 for (int kb = 0; kb < tl.nkb; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
@@ -281,7 +289,7 @@ __global__ void __launch_bounds__(Layout<P>::THREADS, 1) tc_kernel(const __grid_
             constexpr uint32_t idesc = make_idesc(P::BF16, P::A_MN, P::B_MN, 128, P::BLOCK_N);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
-            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            for (int it = 0, t; (t = P::tile_at(prm, it, n_tiles)) >= 0; ++it) {
                 const typename P::Tile tl = P::tile(prm, t);
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tcgen05_fence_after();
@@ -325,7 +333,7 @@ __global__ void __launch_bounds__(Layout<P>::THREADS, 1) tc_kernel(const __grid_
             const int pw = warp - 6;
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            for (int it = 0, t; (t = P::tile_at(prm, it, n_tiles)) >= 0; ++it) {
                 const typename P::Tile tl = P::tile(prm, t);
                 for (int kb = 0; kb < tl.nkb; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
@@ -345,7 +353,7 @@ __global__ void __launch_bounds__(Layout<P>::THREADS, 1) tc_kernel(const __grid_
         uint32_t phase = 0, acc_phase = 0;
         typename P::EpiState st;
         P::epi_init(prm, scratch, (int)threadIdx.x - 64);
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (int it = 0, t; (t = P::tile_at(prm, it, n_tiles)) >= 0; ++it) {
             const typename P::Tile tl = P::tile(prm, t);
             P::epi_begin(prm, tl, st, quarter, lane);
             if constexpr (P::EPI_READS_STAGES) {
@@ -375,7 +383,7 @@ __global__ void __launch_bounds__(Layout<P>::THREADS, 1) tc_kernel(const __grid_
 }
 
 template <class P>
-int launch_tc(const typename P::Params& prm, int n_tiles, cudaStream_t st)
+int launch_tc(const typename P::Params& prm, int n_tiles, cudaStream_t st, int grid_override = 0)
 {
     using L = Layout<P>;
     static bool configured = false;
@@ -387,7 +395,7 @@ int launch_tc(const typename P::Params& prm, int n_tiles, cudaStream_t st)
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int grid = n_tiles < sms ? n_tiles : sms;     // persistent: one CTA per SM
+    const int grid = grid_override > 0 ? grid_override : (n_tiles < sms ? n_tiles : sms);   // persistent: one CTA per SM
     tc_kernel<P><<<grid, L::THREADS, L::SMEM_BYTES, st>>>(prm);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();

@@ -87,6 +87,7 @@ struct PcaPolicy {
     static constexpr int TMA_BYTES = 2 * B_BYTES;
     __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.c_hi); tma_prefetch_desc(&p.c_lo); }
     __device__ static int num_tiles(const Params& p) { return p.m_blocks; }
+    __device__ static int tile_at(const Params&, int it, int n) { return strided_tile(it, n); }
     __device__ static Tile tile(const Params& p, int i) { return {p.nkb, i}; }
     __device__ static void load(const Params& p, const Tile&, int kb, uint8_t*, uint8_t*, uint8_t* b_hi, uint8_t* b_lo,
                                 uint64_t* bar)
@@ -116,6 +117,7 @@ struct PcaPolicy {
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             float v[32];
+            __syncwarp();
             tmem_ld32(tmem + half * 32, v);
             tmem_ld_wait();
             if (valid) {
@@ -151,6 +153,7 @@ struct PostPolicy {
     static constexpr int TMA_BYTES = 2 * B_BYTES;
     __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.w_hi); tma_prefetch_desc(&p.w_lo); }
     __device__ static int num_tiles(const Params& p) { return p.m_blocks; }
+    __device__ static int tile_at(const Params&, int it, int n) { return strided_tile(it, n); }
     __device__ static Tile tile(const Params&, int i) { return {FV_2D / 32, i}; }
     __device__ static void load(const Params& p, const Tile&, int kb, uint8_t*, uint8_t*, uint8_t* b_hi, uint8_t* b_lo,
                                 uint64_t* bar)
@@ -185,6 +188,7 @@ struct PostPolicy {
 #pragma unroll 1
         for (int c = 0; c < FV_K; c += 32) {
             float v[32];
+            __syncwarp();
             tmem_ld32(tmem + c, v);
             tmem_ld_wait();
 #pragma unroll
@@ -199,6 +203,7 @@ struct PostPolicy {
 #pragma unroll 1
         for (int c = 0; c < FV_K; c += 32) {
             float v[32];
+            __syncwarp();
             tmem_ld32(tmem + c, v);
             tmem_ld_wait();
 #pragma unroll
@@ -216,6 +221,7 @@ struct PostPolicy {
 #pragma unroll 1
         for (int c = 0; c < FV_K; c += 32) {
             float v[32];
+            __syncwarp();
             tmem_ld32(tmem + c, v);
             tmem_ld_wait();
             if (valid) {
@@ -251,6 +257,7 @@ struct StatsPolicy {
     static constexpr int TMA_BYTES = 0;
     __device__ static void prefetch(const Params&) {}
     __device__ static int num_tiles(const Params& p) { return (int)p.n_images; }
+    __device__ static int tile_at(const Params&, int it, int n) { return strided_tile(it, n); }
     __device__ static Tile tile(const Params& p, int i)
     {
         const int64_t r0 = p.offsets[i];
@@ -335,6 +342,7 @@ struct StatsPolicy {
 #pragma unroll 1
         for (int c = 0; c < FV_K; c += 32) {
             float v[32];
+            __syncwarp();
             tmem_ld32(tmem + c, v);
             tmem_ld_wait();
 #pragma unroll

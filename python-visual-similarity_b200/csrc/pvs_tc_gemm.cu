@@ -75,6 +75,7 @@ struct GemmKMajor {
     static constexpr int TMA_BYTES = STAGE_;
     __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.a_hi); tma_prefetch_desc(&p.b_hi); }
     __device__ static int num_tiles(const Params& p) { return p.m_blocks * p.n_blocks; }
+    __device__ static int tile_at(const Params&, int it, int n) { return strided_tile(it, n); }
     __device__ static Tile tile(const Params& p, int i) { return {p.k / BK, i / p.n_blocks, i % p.n_blocks}; }
     __device__ static void load(const Params& p, const Tile& t, int kb, uint8_t* a_hi, uint8_t* a_lo, uint8_t* b_hi,
                                 uint8_t* b_lo, uint64_t* bar)
@@ -119,6 +120,7 @@ struct GemmMNMajor {
     static constexpr int TMA_BYTES = (PASSES == 3 ? 2 : 1) * (A_BYTES + B_BYTES);
     __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.a_hi); tma_prefetch_desc(&p.b_hi); }
     __device__ static int num_tiles(const Params& p) { return p.m_blocks * p.n_blocks; }
+    __device__ static int tile_at(const Params&, int it, int n) { return strided_tile(it, n); }
     __device__ static Tile tile(const Params& p, int i) { return {(p.k + KT - 1) / KT, i / p.n_blocks, i % p.n_blocks}; }
     __device__ static void load(const Params& p, const Tile& t, int kb, uint8_t* a_hi, uint8_t* a_lo, uint8_t* b_hi,
                                 uint8_t* b_lo, uint64_t* bar)

@@ -442,3 +442,47 @@ def test_tensor_path_refuses_unsupported_shape(api):
             enc.encode([np.ones((5, 128), np.float32)])
     finally:
         api.nat.set_path(api.nat.PATH_AUTO)
+
+
+@pytest.mark.parametrize("nq,ndb,d,k", [(37, 5000, 256, 100), (300, 3000, 1024, 10), (129, 700, 64, 1), (5, 257, 128, 300)])
+def test_topk_tensor_path_bf16_matches_cuda_core_path(api, nq, ndb, d, k):
+    """The tcgen05 similarity/top-k kernel and the CUDA-core path consume the same bf16
+    operands; scores must agree to fp32 accumulation error and the index lists must be
+    identical except where two scores differ by less than that error."""
+    rng = np.random.default_rng(nq + ndb)
+    db = rng.standard_normal((ndb, d)).astype(np.float32)
+    q = db[rng.integers(0, ndb, nq)] + 0.7 * rng.standard_normal((nq, d)).astype(np.float32)
+    qn = api.ret.l2_normalize(torch.from_numpy(q).cuda(), "bf16")
+    dbn = api.ret.l2_normalize(torch.from_numpy(db).cuda(), "bf16")
+    try:
+        api.nat.set_path(api.nat.PATH_TENSOR)
+        s_tc, i_tc = api.ret.cosine_topk(qn, dbn, k, index_offset=7)
+        api.nat.set_path(api.nat.PATH_SIMT)
+        s_cc, i_cc = api.ret.cosine_topk(qn, dbn, k, index_offset=7)
+    finally:
+        api.nat.set_path(api.nat.PATH_AUTO)
+    s_tc, i_tc, s_cc, i_cc = (t.cpu().numpy() for t in (s_tc, i_tc, s_cc, i_cc))
+    kk = min(k, ndb)
+    assert np.all(i_tc[:, kk:] == -1) and np.all(i_cc[:, kk:] == -1)
+    assert np.all(np.diff(s_tc[:, :kk], axis=1) <= 0)
+    assert np.abs(s_tc[:, :kk] - s_cc[:, :kk]).max() <= 2e-6
+    full = (qn.float() @ dbn.float().T).cpu().numpy()
+    for r, c in np.argwhere(i_tc[:, :kk] != i_cc[:, :kk]):
+        assert abs(full[r, i_tc[r, c] - 7] - full[r, i_cc[r, c] - 7]) <= 2e-6
+    # and against the fp64 oracle on the original vectors, bf16 tolerance
+    s_ref, _ = O.cosine_topk(q, db, kk)
+    assert np.abs(s_tc[:, :kk] - s_ref).max() <= 1e-2
+
+
+def test_topk_tensor_path_exact_ties(api):
+    base = np.random.default_rng(2).standard_normal((5, 128)).astype(np.float32)
+    db = np.tile(base, (120, 1))                      # 600 rows: every vector 120 times
+    qn = api.ret.l2_normalize(torch.from_numpy(base[:2]).cuda(), "bf16")
+    dbn = api.ret.l2_normalize(torch.from_numpy(db).cuda(), "bf16")
+    try:
+        api.nat.set_path(api.nat.PATH_TENSOR)
+        _, i = api.ret.cosine_topk(qn, dbn, 10)
+    finally:
+        api.nat.set_path(api.nat.PATH_AUTO)
+    i = i.cpu().numpy()
+    assert np.array_equal(i[0], np.arange(0, 50, 5)) and np.array_equal(i[1], np.arange(1, 51, 5))
