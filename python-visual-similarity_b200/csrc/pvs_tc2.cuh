@@ -1,0 +1,294 @@
+// pvs_tc2.cuh -- CTA-pair (tcgen05 cta_group::2) variant of the warp-specialised skeleton.
+//
+// Two CTAs of a 2-CTA cluster (the two SMs of a TPC) execute ONE tcgen05.mma together:
+// the pair computes a [256 x BLOCK_N] tile, CTA r holds rows [128 r, 128 r + 128) of A and
+// rows [BLOCK_N/2 r, ...) of B in its own shared memory and the [128 x BLOCK_N] slice of the
+// accumulator in its own TMEM.  Compared with two independent 128-row CTAs each B byte is
+// fetched from L2 and written to shared memory once per pair instead of once per CTA, which
+// is what lifts the L2->SMEM feed limit of the single-CTA kernels; and a weight operand of
+// K=256 rows fits resident (half per CTA) where it had to be re-streamed per tile.
+//
+// Roles per CTA (same warp ids in both CTAs):
+//   warp 0      TMA producer (one lane): loads this CTA's operand halves; the transaction
+//               bytes of BOTH CTAs complete on the LEADER's `full` mbarrier
+//   warp 1      leader CTA only: single-thread MMA issuer; both CTAs: TMEM alloc / dealloc
+//   warps 2-5   epilogue, one TMEM lane quarter each, rows of this CTA
+//   warps 6-9   (P::MANUAL) operand producers: fp32 global -> tf32 hi/lo swizzled tiles in
+//               this CTA's shared memory, then a remote arrive on the leader's `full`
+// Barriers: full[s] lives in the leader (peer arrives remotely); empty[s] and tfull[a] exist
+// in both CTAs and are signalled by tcgen05.commit with a 2-CTA multicast; tempty[a] lives
+// in the leader and collects the epilogue warps of both CTAs.
+//
+// Policy P (see pvs_tc.cuh for the single-CTA contract) additionally provides
+//   B_RESIDENT : the whole B operand (all k-blocks) is loaded once per kernel into a
+//                dedicated region and reused by every tile (weights); else B is staged
+//   NKB_RES    : number of resident k-blocks (B_RESIDENT only)
+// and its callbacks receive the CTA rank and pair index instead of reading blockIdx.
+#pragma once
+#include "pvs_tc.cuh"
+
+namespace pvs {
+namespace tc2 {
+using namespace tc;
+
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;      // clears the CTA-rank bit of a shared::cluster address
+
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive (release at cluster scope) on the barrier at the same offset in the LEADER CTA
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_MASK) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cl(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cl(uint64_t* bar, uint32_t parity)
+{
+    if (mbar_try_wait_cl(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_cl(bar, parity)) {
+        if (clock64() - t0 > 6000000000LL) __trap();
+    }
+}
+// TMA load into THIS CTA's shared memory, bytes complete on the LEADER's barrier
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1)
+        : "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc2(uint32_t* slot_in_smem)
+{
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "n"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr)
+{
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+template <bool BF16>
+__device__ __forceinline__ void umma2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    if constexpr (BF16) {
+        asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
+                     ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    } else {
+        asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}"
+                     ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    }
+}
+// completion of all prior MMAs of this thread -> arrive on `bar` in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
+template <class P>
+struct Layout2 {
+    static constexpr int PARTS = P::PASSES == 3 ? 2 : 1;
+    static constexpr int B_STAGE = P::B_RESIDENT ? 0 : PARTS * P::B_BYTES;
+    static constexpr int STAGE_BYTES = PARTS * P::A_BYTES + B_STAGE;
+    static constexpr int RING_BYTES = P::STAGES * STAGE_BYTES;
+    static constexpr int RES_BYTES = P::B_RESIDENT ? P::NKB_RES * PARTS * P::B_BYTES : 0;
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int SMEM_BYTES = 1024 + RING_BYTES + RES_BYTES + BAR_BYTES + P::SCRATCH_BYTES;
+    static constexpr int TMEM_COLS = 2 * P::BLOCK_N <= 32 ? 32 : 2 * P::BLOCK_N <= 64 ? 64 : 2 * P::BLOCK_N <= 128 ? 128
+                                     : 2 * P::BLOCK_N <= 256 ? 256 : 512;
+    static constexpr int THREADS = P::MANUAL ? 320 : 192;
+    // arrivals per phase on the leader's full barrier
+    static constexpr uint32_t FULL_COUNT = (P::TMA_BYTES > 0 ? 1 : 0) + (P::MANUAL ? 8 : 0);
+    static_assert(2 * P::BLOCK_N <= 512, "accumulator does not fit TMEM twice");
+    static_assert(P::BLOCK_N % 16 == 0 && P::BLOCK_N <= 256, "pair MMA needs N % 16 == 0, N <= 256");
+    static_assert(P::A_BYTES % 1024 == 0 && P::B_BYTES % 1024 == 0, "operand tiles must keep 1024-B alignment");
+    static_assert(P::STAGES + 8 <= 30, "barrier block too small");
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
+};
+
+template <class P>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Layout2<P>::THREADS, 1)
+tc2_kernel(const __grid_constant__ typename P::Params prm)
+{
+    using L = Layout2<P>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* res = smem + L::RING_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::RING_BYTES + L::RES_BYTES);
+    uint64_t* empty = full + P::STAGES;
+    uint64_t* tfull = empty + P::STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint64_t* bres = tempty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres + 1);
+    uint8_t* scratch = smem + L::RING_BYTES + L::RES_BYTES + L::BAR_BYTES;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < P::STAGES; ++s) {
+            mbar_init(&full[s], L::FULL_COUNT);
+            mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull[a], 1);
+            mbar_init(&tempty[a], 8);
+        }
+        mbar_init(bres, 1);
+        fence_barrier_init();
+        P::prefetch(prm);
+    }
+    if (warp == 1) tmem_alloc2<L::TMEM_COLS>(tmem_slot);
+    tcgen05_fence_before();
+    cluster_sync_all();                                     // peer barriers initialised, TMEM allocated
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int n_tiles = P::num_tiles(prm);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            if constexpr (P::B_RESIDENT) {
+                if (rank == 0) mbar_expect_tx(bres, 2u * (uint32_t)L::RES_BYTES);
+                P::load_resident(prm, rank, res, bres);
+            }
+            if constexpr (P::TMA_BYTES > 0) {
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int it = 0, t; (t = P::tile_at(prm, it, pair, n_pairs, n_tiles)) >= 0; ++it) {
+                    const typename P::Tile tl = P::tile(prm, t);
+                    for (int kb = 0; kb < tl.nkb; ++kb) {
+                        mbar_wait_cl(&empty[stage], phase ^ 1);
+                        if (rank == 0) mbar_expect_tx(&full[stage], 2u * (uint32_t)P::TMA_BYTES);
+                        uint8_t* sp = smem + stage * L::STAGE_BYTES;
+                        P::load(prm, tl, kb, rank, sp, sp + P::A_BYTES, sp + L::PARTS * P::A_BYTES,
+                                sp + L::PARTS * P::A_BYTES + P::B_BYTES, &full[stage]);
+                        if (++stage == P::STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = make_idesc(P::BF16, false, false, 256, P::BLOCK_N);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            if constexpr (P::B_RESIDENT) mbar_wait_cl(bres, 0);
+            for (int it = 0, t; (t = P::tile_at(prm, it, pair, n_pairs, n_tiles)) >= 0; ++it) {
+                const typename P::Tile tl = P::tile(prm, t);
+                mbar_wait_cl(&tempty[acc], acc_phase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P::BLOCK_N);
+                for (int kb = 0; kb < tl.nkb; ++kb) {
+                    mbar_wait_cl(&full[stage], phase);
+                    tcgen05_fence_after();
+                    const uint32_t sp = smem_u32(smem + stage * L::STAGE_BYTES);
+                    const uint32_t a_hi = sp, a_lo = sp + P::A_BYTES;
+                    const uint32_t b_hi = P::B_RESIDENT ? smem_u32(res) + (uint32_t)(kb * L::PARTS * P::B_BYTES)
+                                                        : sp + L::PARTS * P::A_BYTES;
+                    const uint32_t b_lo = b_hi + P::B_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < P::KSTEPS; ++ks) {
+                        const uint64_t da_hi = make_smem_desc(a_hi + ks * 32, 16, 1024, LAYOUT_SW128);
+                        const uint64_t db_hi = make_smem_desc(b_hi + ks * 32, 16, 1024, LAYOUT_SW128);
+                        const uint32_t first = (kb > 0 || ks > 0) ? 1u : 0u;
+                        if constexpr (P::PASSES == 3) {
+                            const uint64_t da_lo = make_smem_desc(a_lo + ks * 32, 16, 1024, LAYOUT_SW128);
+                            const uint64_t db_lo = make_smem_desc(b_lo + ks * 32, 16, 1024, LAYOUT_SW128);
+                            umma2<P::BF16>(d_tmem, da_hi, db_lo, idesc, first);
+                            umma2<P::BF16>(d_tmem, da_lo, db_hi, idesc, 1u);
+                            umma2<P::BF16>(d_tmem, da_hi, db_hi, idesc, 1u);
+                        } else {
+                            umma2<P::BF16>(d_tmem, da_hi, db_hi, idesc, first);
+                        }
+                    }
+                    umma2_commit(&empty[stage]);
+                    if (++stage == P::STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma2_commit(&tfull[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 6) {
+        if constexpr (P::MANUAL) {
+            const int pw = warp - 6;
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = 0, t; (t = P::tile_at(prm, it, pair, n_pairs, n_tiles)) >= 0; ++it) {
+                const typename P::Tile tl = P::tile(prm, t);
+                for (int kb = 0; kb < tl.nkb; ++kb) {
+                    mbar_wait_cl(&empty[stage], phase ^ 1);
+                    uint8_t* sp = smem + stage * L::STAGE_BYTES;
+                    P::produce(prm, tl, kb, rank, sp, sp + P::A_BYTES, pw, lane);
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_leader(&full[stage]);
+                    if (++stage == P::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        const int quarter = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        typename P::EpiState st;
+        P::epi_init(prm, scratch, (int)threadIdx.x - 64);
+        for (int it = 0, t; (t = P::tile_at(prm, it, pair, n_pairs, n_tiles)) >= 0; ++it) {
+            const typename P::Tile tl = P::tile(prm, t);
+            P::epi_begin(prm, tl, st, rank, quarter, lane);
+            mbar_wait_cl(&tfull[acc], acc_phase);
+            tcgen05_fence_after();
+            P::epilogue(prm, tl, rank, tmem_base + (uint32_t)(acc * P::BLOCK_N) + ((uint32_t)(quarter * 32) << 16), quarter,
+                        lane, scratch, st);
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&tempty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();                                     // nobody exits while the peer may still signal it
+    if (warp == 1) tmem_dealloc2<L::TMEM_COLS>(tmem_base);
+}
+
+template <class P>
+int launch_tc2(const typename P::Params& prm, int n_tiles, cudaStream_t st, int pairs_override = 0)
+{
+    using L = Layout2<P>;
+    static bool configured = false;
+    if (!configured) {
+        PVS_CUDA(cudaFuncSetAttribute(tc2_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_BYTES));
+        configured = true;
+    }
+    if (n_tiles <= 0) return PVS_OK;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int pairs = pairs_override > 0 ? pairs_override : (n_tiles < sms / 2 ? n_tiles : sms / 2);
+    tc2_kernel<P><<<2 * pairs, L::THREADS, L::SMEM_BYTES, st>>>(prm);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PVS_ERR_CUDA, "tcgen05 pair kernel launch failed: %s", cudaGetErrorString(e));
+    return PVS_OK;
+}
+
+}  // namespace tc2
+}  // namespace pvs

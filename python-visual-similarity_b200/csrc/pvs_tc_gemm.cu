@@ -4,6 +4,7 @@
 // pvs_debug_tc_gemm for the GPU tests; the production kernels (pvs_tc_fv.cu,
 // pvs_tc_sim.cu) instantiate the same skeleton with fused epilogues.
 #include "pvs_tc.cuh"
+#include "pvs_tc2.cuh"
 #include "pvs_kernels.cuh"
 
 namespace pvs {
@@ -143,8 +144,70 @@ struct GemmMNMajor {
     }
 };
 
+// CTA-pair variant (cta_group::2): the pair computes a [256 x BLOCK_N] tile; CTA `rank` loads
+// A rows [256 mb + 128 rank, +128) and B rows [BLOCK_N nb + BLOCK_N/2 rank, +BLOCK_N/2).
+// RES_: keep all k-blocks of B resident (k <= 32 * NKB_RES) to validate the resident path.
+template <bool BF16_, int PASSES_, int BLOCK_N_, bool RES_>
+struct GemmPair {
+    using Params = GemmParams;
+    using EpiState = NoState;
+    struct Tile { int nkb, mb, nb; };
+    static constexpr bool BF16 = BF16_, MANUAL = false, B_RESIDENT = RES_;
+    static constexpr int PASSES = PASSES_, BLOCK_N = BLOCK_N_, KSTEPS = 4, NKB_RES = 4;
+    static constexpr int BK = BF16 ? 64 : 32;
+    static constexpr int A_BYTES = 128 * 128, B_BYTES = (BLOCK_N / 2) * 128, SCRATCH_BYTES = 0;
+    static constexpr int PARTS_ = PASSES == 3 ? 2 : 1;
+    static constexpr int TMA_BYTES = PARTS_ * (A_BYTES + (RES_ ? 0 : B_BYTES));
+    static constexpr int STAGES = RES_ ? 2 : ((190 * 1024) / TMA_BYTES >= 4 ? 4 : (190 * 1024) / TMA_BYTES);
+    __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.a_hi); tma_prefetch_desc(&p.b_hi); }
+    __device__ static int num_tiles(const Params& p) { return p.m_blocks * p.n_blocks; }
+    __device__ static int tile_at(const Params&, int it, int pair, int n_pairs, int n)
+    {
+        const long long t = (long long)pair + (long long)it * n_pairs;
+        return t < n ? (int)t : -1;
+    }
+    __device__ static Tile tile(const Params& p, int i) { return {p.k / BK, i / p.n_blocks, i % p.n_blocks}; }
+    __device__ static void load_resident(const Params& p, int rank, uint8_t* res, uint64_t* bar)
+    {
+        for (int kb = 0; kb < NKB_RES; ++kb) {
+            tc2::tma_load_2d_pair(res + (kb * PARTS_) * B_BYTES, &p.b_hi, bar, kb * BK, rank * (BLOCK_N / 2));
+            if constexpr (PASSES == 3)
+                tc2::tma_load_2d_pair(res + (kb * PARTS_ + 1) * B_BYTES, &p.b_lo, bar, kb * BK, rank * (BLOCK_N / 2));
+        }
+    }
+    __device__ static void load(const Params& p, const Tile& t, int kb, int rank, uint8_t* a_hi, uint8_t* a_lo, uint8_t* b_hi,
+                                uint8_t* b_lo, uint64_t* bar)
+    {
+        tc2::tma_load_2d_pair(a_hi, &p.a_hi, bar, kb * BK, t.mb * 256 + rank * 128);
+        if constexpr (PASSES == 3) tc2::tma_load_2d_pair(a_lo, &p.a_lo, bar, kb * BK, t.mb * 256 + rank * 128);
+        if constexpr (!RES_) {
+            tc2::tma_load_2d_pair(b_hi, &p.b_hi, bar, kb * BK, t.nb * BLOCK_N + rank * (BLOCK_N / 2));
+            if constexpr (PASSES == 3) tc2::tma_load_2d_pair(b_lo, &p.b_lo, bar, kb * BK, t.nb * BLOCK_N + rank * (BLOCK_N / 2));
+        }
+    }
+    __device__ static void epi_init(const Params&, uint8_t*, int) {}
+    __device__ static void epi_begin(const Params&, const Tile&, EpiState&, int, int, int) {}
+    __device__ static void epilogue(const Params& p, const Tile& t, int rank, uint32_t tmem, int quarter, int lane, uint8_t*,
+                                    EpiState&)
+    {
+        const int row = t.mb * 256 + rank * 128 + quarter * 32 + lane;
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+            float v[32];
+            tmem_ld32(tmem + c0, v);
+            tmem_ld_wait();
+            if (row < p.m)
+                for (int j = 0; j < 32; ++j) {
+                    const int col = t.nb * BLOCK_N + c0 + j;
+                    if (col < p.n) p.c[(int64_t)row * p.ldc + col] = v[j];
+                }
+        }
+    }
+};
+
 template <class P>
 static int run_gemm(const GemmParams& prm, cudaStream_t st) { return launch_tc<P>(prm, prm.m_blocks * prm.n_blocks, st); }
+template <class P>
+static int run_gemm2(const GemmParams& prm, cudaStream_t st) { return tc2::launch_tc2<P>(prm, prm.m_blocks * prm.n_blocks, st); }
 
 }  // namespace tc
 
@@ -170,27 +233,32 @@ using namespace pvs;
 // mode 2: bf16 (K-major)               a_hi/b_hi bf16
 // mode 3: tf32 single pass, MN-major   a_hi fp32 [k,m], b_hi fp32 [k,n]
 // mode 4: 3xTF32, MN-major
+// mode 5: bf16, CTA pair (cta_group::2)     mode 6: 3xTF32, CTA pair
+// mode 7: 3xTF32, CTA pair, B operand resident in shared memory (k == 128, n == block_n)
 extern "C" int pvs_debug_tc_gemm(int mode, const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
                                  float* c, int m, int n, int k, int block_n, void* stream)
 {
     PVS_CHECK(tc_available(), PVS_ERR_UNSUPPORTED, "tcgen05 path needs an sm_100 device");
-    PVS_CHECK(mode >= 0 && mode <= 4, PVS_ERR_BAD_ARG, "unknown mode %d", mode);
+    PVS_CHECK(mode >= 0 && mode <= 7, PVS_ERR_BAD_ARG, "unknown mode %d", mode);
     PVS_CHECK(block_n == 64 || block_n == 128 || block_n == 256, PVS_ERR_BAD_ARG, "block_n must be 64/128/256");
-    const bool bf16 = mode == 2, mn = mode >= 3, three = mode == 1 || mode == 4;
+    const bool bf16 = mode == 2 || mode == 5, mn = mode == 3 || mode == 4, three = mode == 1 || mode == 4 || mode >= 6;
+    const bool pair = mode >= 5;
     PVS_CHECK(a_hi && b_hi && c && (!three || (a_lo && b_lo)), PVS_ERR_BAD_ARG, "NULL operand");
     tc::GemmParams p{};
     p.c = c; p.ldc = n; p.m = m; p.n = n; p.k = k;
-    p.m_blocks = (m + 127) / 128;
+    p.m_blocks = (m + (pair ? 255 : 127)) / (pair ? 256 : 128);
     p.n_blocks = (n + block_n - 1) / block_n;
     int rc;
     if (!mn) {
         const int bk = bf16 ? 64 : 32;
+        const int brows = pair ? block_n / 2 : block_n;          // a pair CTA loads half of the B tile
         PVS_CHECK(k % bk == 0, PVS_ERR_BAD_SHAPE, "k must be a multiple of %d", bk);
+        PVS_CHECK(mode != 7 || (k == 128 && n <= block_n), PVS_ERR_BAD_SHAPE, "mode 7 needs k == 128 and n <= block_n");
         if ((rc = tc::make_tmap_2d(&p.a_hi, a_hi, bf16, m, k, k, bk, 128))) return rc;
-        if ((rc = tc::make_tmap_2d(&p.b_hi, b_hi, bf16, n, k, k, bk, block_n))) return rc;
+        if ((rc = tc::make_tmap_2d(&p.b_hi, b_hi, bf16, n, k, k, bk, brows))) return rc;
         if (three) {
             if ((rc = tc::make_tmap_2d(&p.a_lo, a_lo, false, m, k, k, bk, 128))) return rc;
-            if ((rc = tc::make_tmap_2d(&p.b_lo, b_lo, false, n, k, k, bk, block_n))) return rc;
+            if ((rc = tc::make_tmap_2d(&p.b_lo, b_lo, false, n, k, k, bk, brows))) return rc;
         }
     } else {
         if ((rc = tc::make_tmap_2d(&p.a_hi, a_hi, false, k, m, m, 32, 32, true))) return rc;
@@ -203,6 +271,9 @@ extern "C" int pvs_debug_tc_gemm(int mode, const void* a_hi, const void* a_lo, c
     cudaStream_t st = (cudaStream_t)stream;
 #define RUN(BN)                                                                                  \
     switch (mode) {                                                                              \
+        case 5: return tc::run_gemm2<tc::GemmPair<true, 1, BN, false>>(p, st);                   \
+        case 6: return tc::run_gemm2<tc::GemmPair<false, 3, BN, false>>(p, st);                  \
+        case 7: return tc::run_gemm2<tc::GemmPair<false, 3, BN, true>>(p, st);                   \
         case 0: return tc::run_gemm<tc::GemmKMajor<false, 1, BN>>(p, st);                        \
         case 1: return tc::run_gemm<tc::GemmKMajor<false, 3, BN>>(p, st);                        \
         case 2: return tc::run_gemm<tc::GemmKMajor<true, 1, BN>>(p, st);                         \

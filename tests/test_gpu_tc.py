@@ -83,3 +83,45 @@ def test_mnmajor_tf32_and_3xtf32(nat, m, n, k, block_n):
     assert (c1.double() - ref1).abs().max().item() <= 1e-4 * k ** 0.5 + 1e-5
     c3 = run(nat, 4, a_hi, a_lo, b_hi, b_lo, m, n, k, block_n)
     assert (c3.double() - ref).abs().max().item() <= 2e-6 * k + 5e-5
+
+
+@pytest.mark.parametrize("block_n", [128, 256])
+@pytest.mark.parametrize("m,n,k", [(256, 256, 64), (256, 512, 1024), (700, 300, 256), (1000, 1000, 2048)])
+def test_pair_bf16(nat, m, n, k, block_n):
+    """cta_group::2: two CTAs of a cluster issue one MMA; each loads half of A and half of B."""
+    g = torch.Generator(device="cuda").manual_seed(11 + m)
+    a = torch.randn((m, k), device="cuda", generator=g).bfloat16()
+    b = torch.randn((n, k), device="cuda", generator=g).bfloat16()
+    c = run(nat, 5, a, None, b, None, m, n, k, block_n)
+    ref = a.double() @ b.double().T
+    assert torch.isfinite(c).all()
+    assert (c.double() - ref).abs().max().item() <= 1e-3 * k ** 0.5
+
+
+@pytest.mark.parametrize("block_n", [128, 256])
+@pytest.mark.parametrize("m,n,k", [(256, 256, 32), (300, 512, 96), (1000, 256, 512)])
+def test_pair_3xtf32(nat, m, n, k, block_n):
+    g = torch.Generator(device="cuda").manual_seed(m + n + k)
+    a = torch.randn((m, k), device="cuda", generator=g)
+    b = torch.randn((n, k), device="cuda", generator=g)
+    ref = (a.double() @ b.double().T)
+    a_hi, a_lo = split(a)
+    b_hi, b_lo = split(b)
+    c3 = run(nat, 6, a_hi, a_lo, b_hi, b_lo, m, n, k, block_n)
+    err = (c3.double() - ref).abs().max().item()
+    assert err <= 2e-6 * k + 5e-5, f"pair 3xTF32 max abs err {err}"
+
+
+@pytest.mark.parametrize("m,n", [(256, 256), (5000, 256), (130, 200)])
+def test_pair_3xtf32_resident_b(nat, m, n):
+    """weights-resident variant: all k-blocks of B loaded once per kernel, reused by every tile"""
+    k = 128
+    g = torch.Generator(device="cuda").manual_seed(m)
+    a = torch.randn((m, k), device="cuda", generator=g)
+    b = torch.randn((n, k), device="cuda", generator=g)
+    ref = (a.double() @ b.double().T)
+    a_hi, a_lo = split(a)
+    b_hi, b_lo = split(b)
+    c3 = run(nat, 7, a_hi, a_lo, b_hi, b_lo, m, n, k, 256)
+    err = (c3.double() - ref).abs().max().item()
+    assert err <= 2e-6 * k + 5e-5, f"pair resident-B 3xTF32 max abs err {err}"
