@@ -165,6 +165,7 @@ extern "C" int pvs_kmeans_create(const float* centers, int k, int d, pvs_model**
     const float* b = (const float*)m->block;
     m->centers = b;
     m->c2 = b + (size_t)k * d;
+    if (int s = tc_prepare_kmeans(m)) { pvs_model_destroy(m); return s; }
     *out = m;
     return PVS_OK;
 }
@@ -287,12 +288,19 @@ extern "C" int pvs_pca_project(const pvs_model* pca, const float* x, int64_t row
                                     pca->bias, (cudaStream_t)stream));
 }
 
+static bool assign_use_tc(const pvs_model* km, int64_t rows)
+{
+    return g_path.load() != PVS_PATH_SIMT && tc_assign_supported(km, rows);
+}
+
 extern "C" int pvs_kmeans_assign(const pvs_model* km, const float* y, int64_t rows, int32_t* labels, void* stream)
 {
     PVS_CHECK(km && km->kind == PVS_MODEL_KMEANS, PVS_ERR_BAD_ARG, "pvs_kmeans_assign: not a K-Means model");
     PVS_CHECK(rows >= 0 && (rows == 0 || (y && labels)), PVS_ERR_BAD_ARG, "pvs_kmeans_assign: bad buffers");
     if (rows == 0) return PVS_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    if (assign_use_tc(km, rows)) return PVS_STAGE(ST_TC_VLAD_ASSIGN, st, tc_vlad_assign(km, y, rows, labels, st));
+    PVS_CHECK(g_path.load() != PVS_PATH_TENSOR, PVS_ERR_UNSUPPORTED, "pvs_kmeans_assign: the tensor-core path handles k <= 256 only");
     const int64_t chunk = rows < ASSIGN_CHUNK_ROWS ? rows : ASSIGN_CHUNK_ROWS;
     float* scores = nullptr;
     PVS_CUDA(cudaMallocAsync((void**)&scores, (size_t)chunk * km->k * sizeof(float), st));
@@ -359,13 +367,18 @@ extern "C" int pvs_vlad_encode(const pvs_model* km, const pvs_model* pca, const 
     float* scores = (float*)(ws + w.scores);
     int32_t* labels = labels_out ? labels_out : (int32_t*)(ws + w.labels);
     const int64_t chunk = total_rows < ASSIGN_CHUNK_ROWS ? total_rows : ASSIGN_CHUNK_ROWS;
-    for (int64_t r = 0; r < total_rows; r += chunk) {
+    const bool tc = assign_use_tc(km, total_rows);
+    PVS_CHECK(tc || g_path.load() != PVS_PATH_TENSOR, PVS_ERR_UNSUPPORTED,
+              "pvs_vlad_encode: the tensor-core assignment handles k <= 256 only");
+    if (tc)
+        if (int rc = PVS_STAGE(ST_TC_VLAD_ASSIGN, st, tc_vlad_assign(km, y, total_rows, labels, st))) return rc;
+    for (int64_t r = 0; r < total_rows && !tc; r += chunk) {
         const int64_t n = total_rows - r < chunk ? total_rows - r : chunk;
         if (int rc = PVS_STAGE(ST_KM_SCORES, st, launch_gemm_nt(y + r * km->d, km->d, km->centers, km->d, scores, km->k, n,
                                                                 km->k, km->d, 0, -2.f, km->c2, st))) return rc;
         if (int rc = PVS_STAGE(ST_KM_ARGMIN, st, launch_row_argmin(scores, n, km->k, labels + r, st))) return rc;
     }
-    return PVS_STAGE(ST_VLAD_AGG, st, launch_vlad_aggregate(y, km->d, labels, offsets, n_images, km->centers, km->k,
+    return PVS_STAGE(ST_VLAD_AGG, st, launch_vlad_aggregate(y, km->d, labels, offsets, n_images, total_rows, km->centers, km->k,
                                                             power, norm_order, eps, out, st));
 }
 

@@ -19,8 +19,8 @@ int launch_row_argmin(const float* S, int64_t rows, int k, int32_t* labels, cuda
 
 // ---- VLAD aggregation + normalisation ---------------------------------------------------
 int launch_vlad_aggregate(const float* y, int d, const int32_t* labels, const int64_t* offsets,
-                          int64_t n_images, const float* centers, int k, float power, float norm_order,
-                          float eps, float* out, cudaStream_t st);
+                          int64_t n_images, int64_t total_rows, const float* centers, int k, float power,
+                          float norm_order, float eps, float* out, cudaStream_t st);
 
 // ---- Fisher vector statistics + gradients ------------------------------------------------
 // S [n_images, k, 2d+1] = per image ( q^T [y | y*y] , sum_t q ) / T
@@ -44,6 +44,11 @@ int launch_label_metrics(const int64_t* idx, const int32_t* db_labels, const int
 //      is outside what the kernel handles so the caller can take the SIMT path -------------
 bool tc_available();
 int tc_prepare_model(pvs_model* m);
+
+// VLAD hard assignment (pvs_tc_vlad.cu): 3xTF32 scores + fused arg-min, any d, k <= 256
+int tc_prepare_kmeans(pvs_model* m);
+bool tc_assign_supported(const pvs_model* km, int64_t rows);
+int tc_vlad_assign(const pvs_model* km, const float* x, int64_t rows, int32_t* labels, cudaStream_t st);
 
 // Fisher vector, K = 256 / D = 64: workspace carve-up and the three tensor-core stages
 struct TcFvPlan {

@@ -205,86 +205,266 @@ __device__ __forceinline__ float norm_finish(float acc, float ord)
 }
 
 // =====================================================================================
-// VLAD aggregation: one warp per (image, cluster); members visited in descriptor order,
-// so the fp32 accumulation order is exactly the reference's sequential loop
-// (vlad.py:102-104).  Each descriptor row is read once, each output row written once.
+// VLAD aggregation (vlad.py:98-111).  One CTA per image:
+//   1. histogram of the image's labels in shared memory, exclusive scan -> start[k]
+//   2. stable placement (warp 0, __match_any_sync): members[] = descriptor indices grouped
+//      by cluster, in descriptor order inside each cluster
+//   3. one warp per cluster walks its member list and accumulates (x_t - c) in registers in
+//      exactly the reference's sequential order, then applies the signed power and the
+//      per-cluster ord-norm and writes the K x D block once (empty clusters: zeros).
+// Every descriptor row is read once (coalesced, VEC floats per lane) and every output row
+// written once; the label scan that the previous kernel repeated per cluster is gone.
+// Images with more descriptors than the shared-memory member list holds fall back to a
+// ballot scan of the labels per cluster (same arithmetic, same order).
 // =====================================================================================
 namespace {
-template <int NACC>
+template <int VEC> struct VecT;
+template <> struct VecT<1> { using type = float; };
+template <> struct VecT<2> { using type = float2; };
+template <> struct VecT<4> { using type = float4; };
+
+template <int VEC>
+__device__ __forceinline__ void ld_vec(const float* p, float (&v)[VEC])
+{
+    if constexpr (VEC == 4) { const float4 t = __ldg(reinterpret_cast<const float4*>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    else if constexpr (VEC == 2) { const float2 t = __ldg(reinterpret_cast<const float2*>(p)); v[0] = t.x; v[1] = t.y; }
+    else v[0] = __ldg(p);
+}
+template <int VEC>
+__device__ __forceinline__ void st_vec(float* p, const float (&v)[VEC])
+{
+    if constexpr (VEC == 4) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    else if constexpr (VEC == 2) *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+    else *p = v[0];
+}
+
+// acc += row - cv for one member row; lane owns elements (lane + 32 j) * VEC + v
+template <int VEC, int N>
+__device__ __forceinline__ void add_row(const float* __restrict__ row, int d, int lane, const float (&cv)[N][VEC], float (&acc)[N][VEC])
+{
+    float x[N][VEC];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        const int e = (lane + 32 * j) * VEC;
+        if (e < d) ld_vec<VEC>(row + e, x[j]);
+        else
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) x[j][v] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[j][v] += x[j][v] - cv[j][v];
+}
+
+template <int VEC, int N, bool FAST>
 __global__ void __launch_bounds__(256)
 vlad_aggregate_kernel(const float* __restrict__ y, int d, const int32_t* __restrict__ labels,
                       const int64_t* __restrict__ offsets, const float* __restrict__ centers, int k,
-                      int k_per_cta, float power, float ord, float eps, float* __restrict__ out)
+                      int k_per_cta, int t_cap, float power, float ord, float eps, float* __restrict__ out)
 {
+    extern __shared__ int sm_i[];
+    int* count = sm_i;                 // [k]   histogram, then fill cursor
+    int* start = sm_i + k;             // [k+1] exclusive scan
+    int* members = start + k + 1;      // [t_cap]
     const int64_t img = blockIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     const int64_t r0 = offsets[img];
     const int T = (int)(offsets[img + 1] - r0);
     const int kbeg = blockIdx.y * k_per_cta;
     const int kend = min(k, kbeg + k_per_cta);
     const int32_t* lab = labels + r0;
+    const bool sorted = T <= t_cap;
+
+    if (sorted) {
+        for (int j = tid; j < k; j += blockDim.x) count[j] = 0;
+        __syncthreads();
+        for (int t = tid; t < T; t += blockDim.x) atomicAdd(&count[lab[t]], 1);
+        __syncthreads();
+        if (warp == 0) {
+            int carry = 0;
+            for (int base = 0; base < k; base += 32) {
+                const int v = base + lane < k ? count[base + lane] : 0;
+                int incl = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += u; }
+                if (base + lane < k) { start[base + lane] = carry + incl - v; count[base + lane] = 0; }
+                carry += __shfl_sync(FULL, incl, 31);
+            }
+            if (lane == 0) start[k] = carry;
+            __syncwarp();
+            // stable placement: descriptors in order, 32 at a time
+            for (int t0 = 0; t0 < T; t0 += 32) {
+                const int t = t0 + lane;
+                const bool valid = t < T;
+                const int l = valid ? lab[t] : -1 - lane;                 // invalid lanes match nobody
+                const unsigned m = __match_any_sync(FULL, l);
+                const int rank = __popc(m & ((1u << lane) - 1u));
+                int base = 0;
+                if (valid) base = count[l];
+                __syncwarp();
+                if (valid) {
+                    members[start[l] + base + rank] = t;
+                    if (rank == 0) count[l] = base + __popc(m);
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+    }
 
     for (int c = kbeg + warp; c < kend; c += nw) {
-        float acc[NACC], cv[NACC];
+        float acc[N][VEC], cv[N][VEC];
 #pragma unroll
-        for (int j = 0; j < NACC; ++j) {
-            const int dd = lane + 32 * j;
-            acc[j] = 0.f;
-            cv[j] = dd < d ? centers[(int64_t)c * d + dd] : 0.f;
+        for (int j = 0; j < N; ++j) {
+            const int e = (lane + 32 * j) * VEC;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) { acc[j][v] = 0.f; cv[j][v] = 0.f; }
+            if (e < d) ld_vec<VEC>(centers + (int64_t)c * d + e, cv[j]);
         }
-        for (int t0 = 0; t0 < T; t0 += 32) {
-            const int l = (t0 + lane < T) ? lab[t0 + lane] : -1;
-            unsigned m = __ballot_sync(FULL, l == c);
-            while (m) {
-                const int b = __ffs(m) - 1;
-                m &= m - 1;
-                const float* row = y + (r0 + t0 + b) * (int64_t)d;
+        int n_members;
+        if (sorted) {
+            const int s0 = start[c];
+            n_members = start[c + 1] - s0;
+            int i = 0;
+            for (; i + 2 <= n_members; i += 2) {                          // two rows in flight, added in order
+                const float* ra = y + (r0 + members[s0 + i]) * (int64_t)d;
+                const float* rb = y + (r0 + members[s0 + i + 1]) * (int64_t)d;
+                float xa[N][VEC], xb[N][VEC];
 #pragma unroll
-                for (int j = 0; j < NACC; ++j) {
-                    const int dd = lane + 32 * j;
-                    if (dd < d) acc[j] += row[dd] - cv[j];
+                for (int j = 0; j < N; ++j) {
+                    const int e = (lane + 32 * j) * VEC;
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) { xa[j][v] = 0.f; xb[j][v] = 0.f; }
+                    if (e < d) { ld_vec<VEC>(ra + e, xa[j]); ld_vec<VEC>(rb + e, xb[j]); }
+                }
+#pragma unroll
+                for (int j = 0; j < N; ++j)
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) { acc[j][v] += xa[j][v] - cv[j][v]; acc[j][v] += xb[j][v] - cv[j][v]; }
+            }
+            if (i < n_members) add_row<VEC, N>(y + (r0 + members[s0 + i]) * (int64_t)d, d, lane, cv, acc);
+        } else {
+            n_members = 0;
+            for (int t0 = 0; t0 < T; t0 += 32) {
+                const int l = (t0 + lane < T) ? lab[t0 + lane] : -1;
+                unsigned m = __ballot_sync(FULL, l == c);
+                n_members += __popc(m);
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    add_row<VEC, N>(y + (r0 + t0 + b) * (int64_t)d, d, lane, cv, acc);
                 }
             }
         }
+        float* orow = out + (img * k + c) * (int64_t)d;
+        if (n_members == 0) {                                              // 0 / (0 + eps) = 0
+            const float z[VEC] = {};
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                const int e = (lane + 32 * j) * VEC;
+                if (e < d) st_vec<VEC>(orow + e, z);
+            }
+            continue;
+        }
         float nrm = 0.f;
 #pragma unroll
-        for (int j = 0; j < NACC; ++j) {
-            acc[j] = signed_pow(acc[j], power);
-            if (lane + 32 * j < d) nrm = norm_combine(nrm, norm_term(acc[j], ord), ord);
+        for (int j = 0; j < N; ++j) {
+            const int e = (lane + 32 * j) * VEC;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                if constexpr (FAST) {
+                    nrm = fmaf(acc[j][v], acc[j][v], nrm);                 // padding lanes hold 0
+                } else {
+                    acc[j][v] = signed_pow(acc[j][v], power);
+                    if (e < d) nrm = norm_combine(nrm, norm_term(acc[j][v], ord), ord);
+                }
+            }
+        }
+        float den;
+        if constexpr (FAST) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(FULL, nrm, o);
+            den = sqrtf(nrm) + eps;
+        } else {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) nrm = norm_combine(nrm, __shfl_xor_sync(FULL, nrm, o), ord);
+            den = norm_finish(nrm, ord) + eps;
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) nrm = norm_combine(nrm, __shfl_xor_sync(FULL, nrm, o), ord);
-        const float den = norm_finish(nrm, ord) + eps;
-        float* orow = out + (img * k + c) * (int64_t)d;
+        for (int j = 0; j < N; ++j) {
+            const int e = (lane + 32 * j) * VEC;
+            float o[VEC];
 #pragma unroll
-        for (int j = 0; j < NACC; ++j) {
-            const int dd = lane + 32 * j;
-            if (dd < d) orow[dd] = acc[j] / den;
+            for (int v = 0; v < VEC; ++v) o[v] = acc[j][v] / den;
+            if (e < d) st_vec<VEC>(orow + e, o);
         }
     }
+}
+
+template <int VEC, int N>
+int launch_vlad_agg(dim3 grid, size_t smem, cudaStream_t st, bool fast, const float* y, int d, const int32_t* labels,
+                    const int64_t* offsets, const float* centers, int k, int k_per_cta, int t_cap, float power, float ord,
+                    float eps, float* out)
+{
+    if (fast) {
+        if (smem > 48 * 1024) PVS_CUDA(cudaFuncSetAttribute(vlad_aggregate_kernel<VEC, N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PVS_LAUNCH((vlad_aggregate_kernel<VEC, N, true>), grid, 256, smem, st, y, d, labels, offsets, centers, k, k_per_cta, t_cap, power, ord, eps, out);
+    } else {
+        if (smem > 48 * 1024) PVS_CUDA(cudaFuncSetAttribute(vlad_aggregate_kernel<VEC, N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PVS_LAUNCH((vlad_aggregate_kernel<VEC, N, false>), grid, 256, smem, st, y, d, labels, offsets, centers, k, k_per_cta, t_cap, power, ord, eps, out);
+    }
+    return PVS_OK;
 }
 }  // namespace
 
 int launch_vlad_aggregate(const float* y, int d, const int32_t* labels, const int64_t* offsets,
-                          int64_t n_images, const float* centers, int k, float power, float norm_order,
-                          float eps, float* out, cudaStream_t st)
+                          int64_t n_images, int64_t total_rows, const float* centers, int k, float power,
+                          float norm_order, float eps, float* out, cudaStream_t st)
 {
     if (n_images <= 0) return PVS_OK;
     PVS_CHECK(d <= 2048, PVS_ERR_UNSUPPORTED, "VLAD aggregation supports d <= 2048 (got %d)", d);
+    PVS_CHECK(k <= 8192, PVS_ERR_UNSUPPORTED, "VLAD aggregation supports k <= 8192 (got %d)", k);
     // enough CTAs to fill the machine when there are few images (README quick start: 2)
     int groups = 1;
     while (groups < 32 && n_images * groups < 2 * 148 && (k / (groups * 2)) >= 8) groups *= 2;
     const int k_per_cta = (int)ceil_div(k, groups);
     dim3 grid((unsigned)n_images, (unsigned)ceil_div(k, k_per_cta));
-#define VA(N) PVS_LAUNCH(vlad_aggregate_kernel<N>, grid, 256, 0, st, y, d, labels, offsets, centers, k, k_per_cta, power, norm_order, eps, out)
-    if (d <= 64) VA(2);
-    else if (d <= 128) VA(4);
-    else if (d <= 256) VA(8);
-    else if (d <= 544) VA(17);
-    else if (d <= 1024) VA(32);
-    else VA(64);
+    // member-list capacity: a few times the mean image size, so ordinary images take the
+    // sorted path and shared memory still leaves several CTAs per SM
+    int64_t avg = total_rows / n_images + 1;
+    int t_cap = 1024;
+    while (t_cap < 4 * avg && t_cap < 32768) t_cap <<= 1;
+    const size_t smem = ((size_t)2 * k + 1 + t_cap) * sizeof(int);
+    const bool fast = power == 1.f && norm_order == 2.f;
+    const bool a16 = d % 4 == 0 && (((uintptr_t)y | (uintptr_t)centers | (uintptr_t)out) & 15) == 0;
+    const bool a8 = d % 2 == 0 && (((uintptr_t)y | (uintptr_t)centers | (uintptr_t)out) & 7) == 0;
+#define VA(V, NN) return launch_vlad_agg<V, NN>(grid, smem, st, fast, y, d, labels, offsets, centers, k, k_per_cta, t_cap, power, norm_order, eps, out)
+    if (a16) {
+        const int n = (int)ceil_div(d / 4, 32);
+        if (n <= 1) VA(4, 1);
+        if (n <= 2) VA(4, 2);
+        if (n <= 4) VA(4, 4);
+        if (n <= 8) VA(4, 8);
+        VA(4, 16);
+    }
+    if (a8) {
+        const int n = (int)ceil_div(d / 2, 32);
+        if (n <= 1) VA(2, 1);
+        if (n <= 2) VA(2, 2);
+        if (n <= 4) VA(2, 4);
+        if (n <= 9) VA(2, 9);
+        if (n <= 16) VA(2, 16);
+        VA(2, 32);
+    }
+    const int n = (int)ceil_div(d, 32);
+    if (n <= 2) VA(1, 2);
+    if (n <= 4) VA(1, 4);
+    if (n <= 8) VA(1, 8);
+    if (n <= 17) VA(1, 17);
+    if (n <= 32) VA(1, 32);
+    VA(1, 64);
 #undef VA
-    return PVS_OK;
 }
 
 // =====================================================================================

@@ -13,8 +13,11 @@
 //               bytes of BOTH CTAs complete on the LEADER's `full` mbarrier
 //   warp 1      leader CTA only: single-thread MMA issuer; both CTAs: TMEM alloc / dealloc
 //   warps 2-5   epilogue, one TMEM lane quarter each, rows of this CTA
-//   warps 6-9   (P::MANUAL) operand producers: fp32 global -> tf32 hi/lo swizzled tiles in
-//               this CTA's shared memory, then a remote arrive on the leader's `full`
+//   warps 6..   (P::MANUAL) operand producers: fp32 global -> tf32 hi/lo swizzled tiles in
+//               this CTA's shared memory, then a remote arrive on the leader's `full`.
+//               P::PGROUPS groups of four warps; group g fills the k-blocks with running
+//               index == g (mod PGROUPS), so PGROUPS stages are being loaded at any time
+//               (the loads are latency-bound: this is what buys memory-level parallelism)
 // Barriers: full[s] lives in the leader (peer arrives remotely); empty[s] and tfull[a] exist
 // in both CTAs and are signalled by tcgen05.commit with a 2-CTA multicast; tempty[a] lives
 // in the leader and collects the epilogue warps of both CTAs.
@@ -44,16 +47,20 @@ __device__ __forceinline__ void cluster_sync_all()
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive (release at cluster scope) on the barrier at the same offset in the LEADER CTA
+// arrive on the barrier at the same offset in the LEADER CTA.  Default (.release.cta)
+// semantics on purpose: a cluster-scope release / acquire makes ptxas emit MEMBAR.ALL.GPU
+// and an L1 invalidate (CCTL.IVALL) around every arrive / wait, which tripled the fill
+// latency of the operand producers.  What crosses the CTA boundary here is shared memory
+// read by the tensor core (async proxy), ordered by fence.proxy.async + the mbarrier itself.
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar)
 {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_MASK) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_MASK) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_cl(uint64_t* bar, uint32_t parity)
 {
     uint32_t ok;
     asm volatile(
-        "{\n .reg .pred p;\n mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
@@ -115,13 +122,14 @@ struct Layout2 {
     static constexpr int SMEM_BYTES = 1024 + RING_BYTES + RES_BYTES + BAR_BYTES + P::SCRATCH_BYTES;
     static constexpr int TMEM_COLS = 2 * P::BLOCK_N <= 32 ? 32 : 2 * P::BLOCK_N <= 64 ? 64 : 2 * P::BLOCK_N <= 128 ? 128
                                      : 2 * P::BLOCK_N <= 256 ? 256 : 512;
-    static constexpr int THREADS = P::MANUAL ? 320 : 192;
+    static constexpr int THREADS = P::MANUAL ? 192 + 128 * P::PGROUPS : 192;
     // arrivals per phase on the leader's full barrier
     static constexpr uint32_t FULL_COUNT = (P::TMA_BYTES > 0 ? 1 : 0) + (P::MANUAL ? 8 : 0);
     static_assert(2 * P::BLOCK_N <= 512, "accumulator does not fit TMEM twice");
     static_assert(P::BLOCK_N % 16 == 0 && P::BLOCK_N <= 256, "pair MMA needs N % 16 == 0, N <= 256");
     static_assert(P::A_BYTES % 1024 == 0 && P::B_BYTES % 1024 == 0, "operand tiles must keep 1024-B alignment");
     static_assert(P::STAGES + 8 <= 30, "barrier block too small");
+    static_assert(!P::MANUAL || (P::PGROUPS >= 1 && P::PGROUPS <= P::STAGES), "one stage per producer group at least");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
 };
 
@@ -229,19 +237,20 @@ tc2_kernel(const __grid_constant__ typename P::Params prm)
         }
     } else if (warp >= 6) {
         if constexpr (P::MANUAL) {
-            const int pw = warp - 6;
-            int stage = 0;
-            uint32_t phase = 0;
+            const int pw = (warp - 6) & 3, grp = (warp - 6) >> 2;
+            long long idx = 0;                               // running k-block index over all tiles of this pair
             for (int it = 0, t; (t = P::tile_at(prm, it, pair, n_pairs, n_tiles)) >= 0; ++it) {
                 const typename P::Tile tl = P::tile(prm, t);
-                for (int kb = 0; kb < tl.nkb; ++kb) {
+                for (int kb = 0; kb < tl.nkb; ++kb, ++idx) {
+                    if ((int)(idx % P::PGROUPS) != grp) continue;
+                    const int stage = (int)(idx % P::STAGES);
+                    const uint32_t phase = (uint32_t)((idx / P::STAGES) & 1);
                     mbar_wait_cl(&empty[stage], phase ^ 1);
                     uint8_t* sp = smem + stage * L::STAGE_BYTES;
                     P::produce(prm, tl, kb, rank, sp, sp + P::A_BYTES, pw, lane);
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_leader(&full[stage]);
-                    if (++stage == P::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }

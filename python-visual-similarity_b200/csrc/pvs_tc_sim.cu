@@ -82,7 +82,7 @@ struct SimPolicy {
     using EpiState = SimState;
     struct Tile { int nkb, qb, dbb, stripe; bool first, last; };
     static constexpr bool BF16 = true, MANUAL = false, B_RESIDENT = false;
-    static constexpr int CAP = CAP_, PASSES = 1, BLOCK_N = 256, KSTEPS = 4, NKB_RES = 0;
+    static constexpr int CAP = CAP_, PASSES = 1, BLOCK_N = 256, KSTEPS = 4, NKB_RES = 0, PGROUPS = 1;
     static constexpr int A_BYTES = 128 * 128, B_BYTES = 128 * 128, TMA_BYTES = A_BYTES + B_BYTES;
     static constexpr int SCRATCH_BYTES = CAP <= 512 ? 0 : 4 * CAP * 8;
     static constexpr int STAGES = (226 * 1024 - 1024 - 256 - SCRATCH_BYTES) / TMA_BYTES;
@@ -136,7 +136,7 @@ struct SimPolicy {
         if constexpr (REG_SELECT) {
             unsigned long long e[NPL];
 #pragma unroll
-            for (int j = 0; j < NPL; ++j) e[j] = (lane + 32 * j < n) ? base[lane + 32 * j] : 0ull;
+            for (int j = 0; j < NPL; ++j) e[j] = (lane + 32 * j < n) ? __ldcg(base + lane + 32 * j) : 0ull;   // L2: written by another lane
             if (n > p.k) {
                 // k-th largest key: radix search from the top, two bits per step; the three
                 // counts of a step travel in one warp reduction (each <= 512 < 2^10)
@@ -183,7 +183,7 @@ struct SimPolicy {
         } else {
             int np2 = 32;
             while (np2 < n) np2 <<= 1;
-            for (int i = lane; i < np2; i += 32) sm[i] = i < n ? base[i] : 0ull;
+            for (int i = lane; i < np2; i += 32) sm[i] = i < n ? __ldcg(base + i) : 0ull;
             __syncwarp();
             warp_bitonic_desc(sm, np2, lane);
             m = n < p.k ? n : p.k;

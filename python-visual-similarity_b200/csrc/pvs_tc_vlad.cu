@@ -1,0 +1,201 @@
+// pvs_tc_vlad.cu -- VLAD hard assignment on tcgen05 tensor cores (3xTF32, CTA pairs).
+//
+// Replaces KMeans.predict at pyvisim/encoders/vlad.py:95 (sklearn _k_means_lloyd.pyx
+// _update_chunk_dense: one sgemm per 256-row chunk, then a strict `<` arg-min scan over
+// ||c||^2 - 2 x.c).  Here a pair of CTAs scores a [256 descriptors x 256 centres] tile:
+//   A  = descriptor rows, loaded as fp32 by four producer warps per CTA, split into tf32
+//        hi/lo parts in registers and stored as 128-byte-swizzled UMMA tiles
+//   B  = centres (hi/lo split once at model creation, zero-padded to a multiple of 32
+//        columns); resident in shared memory for D = 64 / 128 (half of the centres per CTA),
+//        streamed by TMA otherwise (D = 514: 17 k-blocks)
+//   D  = x.c in TMEM (fp32, error-compensated: hi*lo + lo*hi + hi*hi)
+// Epilogue: each thread owns one descriptor (one TMEM lane), scans its 256 scores
+// ||c||^2 - 2 acc in column order with a strict `<` (lowest index wins ties, like the
+// reference) and writes the int32 label.  The score matrix never leaves the SM.
+#include <string.h>
+#include "pvs_tc2.cuh"
+#include "pvs_kernels.cuh"
+
+namespace pvs {
+namespace tc2 {
+
+struct AssignParams {
+    CUtensorMap c_hi, c_lo;            // centres [k, d_pad] fp32 (hi / lo parts), box 32 cols x 128 rows
+    const float* x;                    // [rows, d]
+    const float* c2;                   // [k] squared norms
+    int32_t* labels;                   // [rows]
+    int64_t rows;
+    int d, k, nkb, m_blocks;
+};
+struct AssignState {};
+
+__device__ __forceinline__ uint32_t swz128(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+
+// one warp fills rows [32 pw, 32 pw + 32) of a [128 rows x 32 floats] K-major tile (hi and lo
+// parts) from src[row * d + col0 ...]; columns >= d and rows >= rows_total read as zero.
+// VEC = floats per load the row alignment allows (4: d % 4 == 0, 2: d % 2 == 0, else 1).
+template <int VEC>
+__device__ __forceinline__ void fill_tile_rows(const float* __restrict__ src, int d, int64_t row0, int64_t rows_total,
+                                               int col0, uint8_t* hi, uint8_t* lo, int pw, int lane)
+{
+    const int c = lane & 7;                                   // 16-byte chunk inside the 128-byte row
+    const int col = col0 + c * 4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = pw * 32 + i * 4 + (lane >> 3);
+        const int64_t gr = row0 + r;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gr < rows_total) {
+            const float* p = src + gr * (int64_t)d + col;
+            if constexpr (VEC == 4) {
+                if (col < d) v = __ldg(reinterpret_cast<const float4*>(p));
+            } else if constexpr (VEC == 2) {
+                if (col < d) { const float2 t = __ldg(reinterpret_cast<const float2*>(p)); v.x = t.x; v.y = t.y; }
+                if (col + 2 < d) { const float2 t = __ldg(reinterpret_cast<const float2*>(p + 2)); v.z = t.x; v.w = t.y; }
+            } else {
+                if (col < d) v.x = __ldg(p);
+                if (col + 1 < d) v.y = __ldg(p + 1);
+                if (col + 2 < d) v.z = __ldg(p + 2);
+                if (col + 3 < d) v.w = __ldg(p + 3);
+            }
+        }
+        float4 h, l;
+        tf32_split(v.x, h.x, l.x);
+        tf32_split(v.y, h.y, l.y);
+        tf32_split(v.z, h.z, l.z);
+        tf32_split(v.w, h.w, l.w);
+        const uint32_t off = swz128(r, c);
+        *reinterpret_cast<float4*>(hi + off) = h;
+        *reinterpret_cast<float4*>(lo + off) = l;
+    }
+}
+
+template <bool RES_, int NKB_, int VEC_>
+struct AssignPolicy {
+    using Params = AssignParams;
+    using EpiState = AssignState;
+    struct Tile { int nkb, mb; };
+    static constexpr bool BF16 = false, MANUAL = true, B_RESIDENT = RES_;
+    static constexpr int PASSES = 3, BLOCK_N = 256, KSTEPS = 4, NKB_RES = NKB_, STAGES = 3, PGROUPS = 3;
+    static constexpr int A_BYTES = 128 * 128, B_BYTES = 128 * 128, SCRATCH_BYTES = 1024;
+    static constexpr int TMA_BYTES = RES_ ? 0 : 2 * B_BYTES;
+    __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.c_hi); tma_prefetch_desc(&p.c_lo); }
+    __device__ static int num_tiles(const Params& p) { return p.m_blocks; }
+    __device__ static int tile_at(const Params&, int it, int pair, int n_pairs, int n)
+    {
+        const long long t = (long long)pair + (long long)it * n_pairs;
+        return t < n ? (int)t : -1;
+    }
+    __device__ static Tile tile(const Params& p, int i) { return {p.nkb, i}; }
+    __device__ static void load_resident(const Params& p, int rank, uint8_t* res, uint64_t* bar)
+    {
+        for (int kb = 0; kb < NKB_RES; ++kb) {
+            tma_load_2d_pair(res + (2 * kb) * B_BYTES, &p.c_hi, bar, kb * 32, rank * 128);
+            tma_load_2d_pair(res + (2 * kb + 1) * B_BYTES, &p.c_lo, bar, kb * 32, rank * 128);
+        }
+    }
+    __device__ static void load(const Params& p, const Tile&, int kb, int rank, uint8_t*, uint8_t*, uint8_t* b_hi,
+                                uint8_t* b_lo, uint64_t* bar)
+    {
+        tma_load_2d_pair(b_hi, &p.c_hi, bar, kb * 32, rank * 128);
+        tma_load_2d_pair(b_lo, &p.c_lo, bar, kb * 32, rank * 128);
+    }
+    __device__ static void produce(const Params& p, const Tile& t, int kb, int rank, uint8_t* a_hi, uint8_t* a_lo, int pw,
+                                   int lane)
+    {
+        fill_tile_rows<VEC_>(p.x, p.d, (int64_t)t.mb * 256 + rank * 128, p.rows, kb * 32, a_hi, a_lo, pw, lane);
+    }
+    __device__ static void epi_init(const Params& p, uint8_t* scratch, int tid)
+    {
+        float* c2 = reinterpret_cast<float*>(scratch);
+        for (int j = tid; j < BLOCK_N; j += 128) c2[j] = j < p.k ? p.c2[j] : INFINITY;   // padded centres never win
+        epi_barrier();
+    }
+    __device__ static void epi_begin(const Params&, const Tile&, EpiState&, int, int, int) {}
+    __device__ static void epilogue(const Params& p, const Tile& t, int rank, uint32_t tmem, int quarter, int lane,
+                                    uint8_t* scratch, EpiState&)
+    {
+        const float* c2 = reinterpret_cast<const float*>(scratch);
+        const int64_t row = (int64_t)t.mb * 256 + rank * 128 + quarter * 32 + lane;
+        float best = INFINITY;
+        int bi = 0;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 32) {
+            float v[32];
+            tmem_ld32(tmem + c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float s = fmaf(-2.f, v[j], c2[c + j]);
+                if (s < best) { best = s; bi = c + j; }
+            }
+        }
+        if (row < p.rows) p.labels[row] = bi;
+    }
+};
+
+}  // namespace tc2
+
+using namespace tc2;
+
+// K-Means model preparation: zero-padded [k, d_pad] hi / lo copies of the centres
+int tc_prepare_kmeans(pvs_model* m)
+{
+    if (!tc_available() || m->kind != PVS_MODEL_KMEANS || m->k > 256) return PVS_OK;
+    const int d_pad = (m->d + 31) / 32 * 32;
+    const size_t n = (size_t)m->k * d_pad;
+    std::vector<float> hc((size_t)m->k * m->d), hi(n, 0.f), lo(n, 0.f);
+    PVS_CUDA(cudaMemcpy(hc.data(), m->centers, hc.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    for (int j = 0; j < m->k; ++j)
+        for (int i = 0; i < m->d; ++i) {
+            // round-to-nearest-away at 13 dropped mantissa bits == cvt.rna.tf32.f32 for finite values
+            const float x = hc[(size_t)j * m->d + i];
+            uint32_t u;
+            memcpy(&u, &x, 4);
+            uint32_t uh = (u + 0x1000u) & 0xFFFFE000u;
+            float h;
+            memcpy(&h, &uh, 4);
+            const float r = x - h;
+            memcpy(&u, &r, 4);
+            uint32_t ul = (u + 0x1000u) & 0xFFFFE000u;
+            float l;
+            memcpy(&l, &ul, 4);
+            hi[(size_t)j * d_pad + i] = h;
+            lo[(size_t)j * d_pad + i] = l;
+        }
+    float* buf = nullptr;
+    PVS_CUDA(cudaMalloc((void**)&buf, 2 * n * sizeof(float)));
+    cudaError_t e = cudaMemcpy(buf, hi.data(), n * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(buf + n, lo.data(), n * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(buf); return fail(PVS_ERR_CUDA, "centre upload failed: %s", cudaGetErrorString(e)); }
+    m->tc0 = buf;
+    m->tc1 = buf + n;
+    m->tc_ld = d_pad;
+    return PVS_OK;
+}
+
+bool tc_assign_supported(const pvs_model* km, int64_t rows)
+{
+    return tc_available() && km->tc0 && km->k <= 256 && km->k >= 8 && rows / 256 + 2 < 2147483647LL;
+}
+
+int tc_vlad_assign(const pvs_model* km, const float* x, int64_t rows, int32_t* labels, cudaStream_t st)
+{
+    if (rows <= 0) return PVS_OK;
+    AssignParams p{};
+    int rc;
+    if ((rc = make_tmap_2d(&p.c_hi, km->tc0, false, km->k, km->tc_ld, km->tc_ld, 32, 128))) return rc;
+    if ((rc = make_tmap_2d(&p.c_lo, km->tc1, false, km->k, km->tc_ld, km->tc_ld, 32, 128))) return rc;
+    p.x = x; p.c2 = km->c2; p.labels = labels; p.rows = rows;
+    p.d = km->d; p.k = km->k; p.nkb = km->tc_ld / 32;
+    p.m_blocks = (int)ceil_div(rows, 256);
+    const bool a16 = ((uintptr_t)x & 15) == 0 && km->d % 4 == 0;
+    const bool a8 = ((uintptr_t)x & 7) == 0 && km->d % 2 == 0;
+    if (km->d == 64 && a16) return launch_tc2<AssignPolicy<true, 2, 4>>(p, p.m_blocks, st);
+    if (km->d == 128 && a16) return launch_tc2<AssignPolicy<true, 4, 4>>(p, p.m_blocks, st);
+    if (a16) return launch_tc2<AssignPolicy<false, 0, 4>>(p, p.m_blocks, st);
+    if (a8) return launch_tc2<AssignPolicy<false, 0, 2>>(p, p.m_blocks, st);
+    return launch_tc2<AssignPolicy<false, 0, 1>>(p, p.m_blocks, st);
+}
+
+}  // namespace pvs
