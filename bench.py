@@ -146,6 +146,59 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max, "reasons": sorted(self.reasons)}
 
 
+
+# --------------------------------------------------------------------------------------
+# other BASELINE.json metrics, measured in the same run (N=1 only): VLAD images/s and
+# all-pairs similarity TFLOP/s + top-k queries/s at single-GPU sizes
+# --------------------------------------------------------------------------------------
+def run_extras(dev, pk):
+    import torch
+    from pyvisim_b200 import _native as N, retrieval
+    from pyvisim_b200.encoders import VLADEncoder
+    from pyvisim_b200.encoders._base_encoder import kmeans_from_centers
+    from pyvisim_b200.features import Descriptors
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps, out
+
+    out = {}
+    g = torch.Generator(device=dev).manual_seed(7)
+    for name, (n, T, D) in {"vlad_c1_rootsift128": (1024, 2000, 128), "vlad_c3_vgg514": (8192, 196, 514)}.items():
+        x = torch.randn((n * T, D), device=dev, generator=g)
+        if D == 128:                                      # RootSIFT-like: non-negative, unit L2
+            x = x.abs_()
+            x = (x / (x.sum(1, keepdim=True) + 1e-7)).sqrt_()
+        centers = x[torch.randperm(n * T, device=dev, generator=g)[:256]].cpu().numpy()
+        enc = VLADEncoder(feature_extractor=Descriptors(D), kmeans_model=kmeans_from_centers(centers))
+        offs = torch.arange(n + 1, dtype=torch.int64) * T
+        ms, _ = timed(lambda: enc.encode_descriptors(x, offs, images_per_call=4096), 3)
+        alg = T * D * 4 + 256 * D * 4
+        out[name] = {"images_per_s": n / ms * 1e3, "images": n, "descriptors_per_image": T, "d": D, "k": 256,
+                     "frac_of_hbm_peak": alg * n / ms / 1e6 / pk["hbm_gbs"], "weights": "random-init K-Means (no file bundled)"}
+        del x, enc
+    n, d, k = 16384, 32768, 100
+    v = torch.empty((n, d), dtype=torch.bfloat16, device=dev)
+    for r in range(0, n, 4096):                           # VLAD-shaped rows: 256 unit blocks of 128, ~15 % empty
+        b = torch.randn((4096, d // 128, 128), device=dev, generator=g)
+        b = b / b.norm(dim=2, keepdim=True)
+        b = b * (torch.rand((4096, d // 128, 1), device=dev, generator=g) > 0.15)
+        b = b.reshape(4096, -1)
+        v[r:r + 4096] = (b / b.norm(dim=1, keepdim=True).clamp_min(1e-30)).bfloat16()
+    ms, _ = timed(lambda: retrieval.cosine_topk(v, v, k), 2)
+    tf = 2.0 * n * n * d / ms / 1e9
+    out["all_pairs_cosine_top100"] = {"tflops": tf, "queries_per_s": n / ms * 1e3, "n": n, "d": d, "k": k, "dtype": "bf16",
+                                      "frac_of_bf16_sustained_peak": tf / pk["bf16_tflops_sustained"],
+                                      "frac_of_bf16_burst_peak": tf / pk["bf16_tflops"]}
+    return out
+
 # --------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------
@@ -246,6 +299,10 @@ def run_ours(args):
                        "fv_stats": 2 * T * K * 2 * D, "tc_fv_posterior": 2 * T * K * 2 * D,
                        "tc_fv_stats": 2 * T * K * 2 * D}
     bytes_per_image = {"gmm_softmax": 2 * T * K * 4, "fv_finalize": K * (2 * D + 1) * 4 + out_dim * 4 * 3}
+    # DRAM bytes per image of each kernel from the committed `ncu --set full` capture
+    # (profiles/ncu_fv_pair_r01.txt: dram read + write per launch of 512 images)
+    ncu_dram_bytes_per_image = {"tc_fv_project": (0.524403e9 + 230.873e6) / 512, "tc_fv_posterior": (0.262483e9 + 991.868e6) / 512,
+                                "tc_fv_stats": (1.310766e9 + 63.2998e6) / 512}
     roofline = None
     if dominant[0]:
         name, (ms, n) = dominant
@@ -254,9 +311,13 @@ def run_ours(args):
         if name in flops_per_image:
             ach = flops_per_image[name] * imgs_per_launch / (per_launch_ms / 1e3) / 1e12
             peak = pk["bf16_tflops_sustained"]
+            traffic = ncu_dram_bytes_per_image.get(name)
             roofline = {"bound": "tensor", "kernel": name, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                        "frac": ach / peak, "traffic": None,
-                        "peak_source": f"bf16 dense sustained, {pk['source']} (kernel runs inside a long step)"}
+                        "frac": ach / peak, "traffic": traffic * imgs_per_launch if traffic else None,
+                        "peak_source": f"bf16 dense sustained, {pk['source']} (kernel runs inside a long step)",
+                        "note": "fp32-accurate 3xTF32 contraction: three tf32 MMAs per algorithmic product, so the "
+                                "ceiling of this kernel is peak/6; frac_of_3xtf32_ceiling = frac * 6",
+                        "frac_of_3xtf32_ceiling": 6 * ach / peak}
         else:
             ach = bytes_per_image.get(name, 0) * imgs_per_launch / (per_launch_ms / 1e3) / 1e9
             roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
@@ -278,6 +339,12 @@ def run_ours(args):
                "sample": f"first {sample} of {n_img} images, {dt:.1f} s, NumPy/OpenBLAS default threads",
                "parity_rel_l2_vs_gpu": err}
 
+    extra = None
+    if rank == 0 and world == 1 and not args.no_extra:
+        del x
+        torch.cuda.empty_cache()
+        extra = run_extras(dev, pk)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -296,6 +363,7 @@ def run_ours(args):
                          "frac_of_hbm_peak": path_gbs / pk["hbm_gbs"]},
             "stages_ms": {k: round(v[0] / args.steps, 4) for k, v in stages.items()},
             "cpu_baseline": cpu,
+            "extra": extra,
             "clocks": clocks.summary(),
             "checksum": checksum,
         }
@@ -316,6 +384,7 @@ def main():
     ap.add_argument("--e2e-images", type=int, default=0, help="images in the host-buffer leg (0 = all)")
     ap.add_argument("--cpu-sample", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the VLAD / similarity side measurements")
     ap.add_argument("--no-profile", action="store_true", help="skip the per-stage CUDA-event timing")
     args = ap.parse_args()
     if args.impl == "reference":

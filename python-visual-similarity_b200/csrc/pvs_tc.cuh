@@ -227,7 +227,7 @@ struct Layout {
     // threads: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue,
     // warps 6-9 (only with P::MANUAL) operand producers that load fp32 from global memory,
     // split it into tf32 hi/lo parts and store the swizzled tiles themselves
-    static constexpr int THREADS = P::MANUAL ? 320 : 192;
+    static constexpr int THREADS = P::MANUAL ? 192 + 128 * P::PGROUPS : 192;
     static constexpr uint32_t FULL_COUNT = (P::TMA_BYTES > 0 ? 1 : 0) + (P::MANUAL ? 4 : 0);
     static_assert(2 * P::BLOCK_N <= 512, "accumulator does not fit TMEM twice");
     static_assert(!(P::BF16 && (P::A_MN || P::B_MN)), "MN-major operands are implemented for tf32 only");
@@ -330,12 +330,16 @@ __global__ void __launch_bounds__(Layout<P>::THREADS, 1) tc_kernel(const __grid_
         }
     } else if (warp >= 6) {
         if constexpr (P::MANUAL) {
-            const int pw = warp - 6;
-            int stage = 0;
-            uint32_t phase = 0;
+            // P::PGROUPS groups of four producer warps; group g fills the k-blocks whose
+            // running index is g (mod PGROUPS), so several stages are being loaded at once
+            const int pw = (warp - 6) & 3, grp = (warp - 6) >> 2;
+            long long idx = 0;
             for (int it = 0, t; (t = P::tile_at(prm, it, n_tiles)) >= 0; ++it) {
                 const typename P::Tile tl = P::tile(prm, t);
-                for (int kb = 0; kb < tl.nkb; ++kb) {
+                for (int kb = 0; kb < tl.nkb; ++kb, ++idx) {
+                    if ((int)(idx % P::PGROUPS) != grp) continue;
+                    const int stage = (int)(idx % P::STAGES);
+                    const uint32_t phase = (uint32_t)((idx / P::STAGES) & 1);
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* sp = smem + stage * L::STAGE_BYTES;
                     P::produce(prm, tl, kb, sp, sp + P::A_BYTES, sp + L::PARTS * P::A_BYTES,
@@ -343,7 +347,6 @@ __global__ void __launch_bounds__(Layout<P>::THREADS, 1) tc_kernel(const __grid_
                     fence_proxy_async();                 // generic-proxy stores -> visible to the tensor core
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&full[stage]);
-                    if (++stage == P::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }

@@ -19,6 +19,7 @@
 //                              Q tiles while they sit in shared memory
 //                                                              (fisher_vector.py:102-104)
 #include "pvs_tc.cuh"
+#include "pvs_tc2.cuh"
 #include "pvs_kernels.cuh"
 
 namespace pvs {
@@ -27,7 +28,7 @@ namespace tc {
 constexpr int FV_K = 256;     // mixture components
 constexpr int FV_D = 64;      // dims after PCA
 constexpr int FV_2D = 128;
-constexpr int ST_KT = 32;     // contraction rows (descriptors) per stats stage
+constexpr int ST_KT = 16;     // contraction rows (descriptors) per stats stage
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void split4(const float4& v, float4& h, float4& l)
@@ -82,7 +83,7 @@ struct PcaPolicy {
     using EpiState = NoEpiState;
     struct Tile { int nkb, mb; };
     static constexpr bool BF16 = false, A_MN = false, B_MN = false, EPI_READS_STAGES = false, MANUAL = true;
-    static constexpr int PASSES = 3, BLOCK_N = FV_D, KSTEPS = 4, STAGES = 4;
+    static constexpr int PASSES = 3, BLOCK_N = FV_D, KSTEPS = 4, STAGES = 4, PGROUPS = 2;
     static constexpr int A_BYTES = 128 * 128, B_BYTES = BLOCK_N * 128, A_LBO = 0, B_LBO = 0, SCRATCH_BYTES = 256;
     static constexpr int TMA_BYTES = 2 * B_BYTES;
     __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.c_hi); tma_prefetch_desc(&p.c_lo); }
@@ -148,7 +149,7 @@ struct PostPolicy {
     using EpiState = NoEpiState;
     struct Tile { int nkb, mb; };
     static constexpr bool BF16 = false, A_MN = false, B_MN = false, EPI_READS_STAGES = false, MANUAL = true;
-    static constexpr int PASSES = 3, BLOCK_N = FV_K, KSTEPS = 4, STAGES = 2;
+    static constexpr int PASSES = 3, BLOCK_N = FV_K, KSTEPS = 4, STAGES = 2, PGROUPS = 2;
     static constexpr int A_BYTES = 128 * 128, B_BYTES = BLOCK_N * 128, A_LBO = 0, B_LBO = 0, SCRATCH_BYTES = 1024;
     static constexpr int TMA_BYTES = 2 * B_BYTES;
     __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.w_hi); tma_prefetch_desc(&p.w_lo); }
@@ -251,7 +252,7 @@ struct StatsPolicy {
     struct Tile { int nkb; int t; int64_t img, r0; };
     static constexpr bool BF16 = false, A_MN = true, B_MN = true, EPI_READS_STAGES = true, MANUAL = true;
     static constexpr int KT = ST_KT;
-    static constexpr int PASSES = 3, BLOCK_N = FV_K, STAGES = 2, KSTEPS = KT / 8;
+    static constexpr int PASSES = 3, BLOCK_N = FV_K, STAGES = 4, KSTEPS = KT / 8, PGROUPS = 2;
     static constexpr int A_LBO = KT * 128, B_LBO = KT * 128;          // one [KT rows x 128 B] block per 32 columns
     static constexpr int A_BYTES = (FV_2D / 32) * A_LBO, B_BYTES = (FV_K / 32) * B_LBO, SCRATCH_BYTES = 0;
     static constexpr int TMA_BYTES = 0;
@@ -265,16 +266,17 @@ struct StatsPolicy {
         return {(t + KT - 1) / KT, t, (int64_t)i, r0};
     }
     __device__ static void load(const Params&, const Tile&, int, uint8_t*, uint8_t*, uint8_t*, uint8_t*, uint64_t*) {}
-    // producer warp pw owns descriptor rows [8 pw, 8 pw + 8) of the stage; rows past the end
-    // of the image are written as zeros (that is what makes ragged T exact)
+    // producer warp pw owns descriptor rows [RPW pw, RPW pw + RPW) of the stage; rows past the
+    // end of the image are written as zeros (that is what makes ragged T exact)
+    static constexpr int RPW = KT / 4;
     __device__ static void produce(const Params& p, const Tile& t, int kb, uint8_t* a_hi, uint8_t* a_lo, uint8_t* b_hi,
                                    uint8_t* b_lo, int pw, int lane)
     {
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
         // Q: 64 float4 per row -> two per lane; column block = c4 / 8
 #pragma unroll
-        for (int rr = 0; rr < 8; ++rr) {
-            const int r = pw * 8 + rr;
+        for (int rr = 0; rr < RPW; ++rr) {
+            const int r = pw * RPW + rr;
             const int tt = kb * KT + r;
             const bool valid = tt < t.t;
             const float* qrow = p.q + (t.r0 + tt) * FV_K;
@@ -292,8 +294,8 @@ struct StatsPolicy {
         // Y: 16 float4 per row -> half a warp per row, two rows per pass; writes y*y into
         // column blocks 0,1 and y into blocks 2,3
 #pragma unroll
-        for (int pr = 0; pr < 4; ++pr) {
-            const int r = pw * 8 + pr * 2 + (lane >> 4);
+        for (int pr = 0; pr < RPW / 2; ++pr) {
+            const int r = pw * RPW + pr * 2 + (lane >> 4);
             const int tt = kb * KT + r;
             const int c4 = lane & 15;
             const float4 v = (tt < t.t) ? ldg4(p.y + (t.r0 + tt) * FV_D + c4 * 4) : z;
@@ -353,6 +355,188 @@ struct StatsPolicy {
         Simg[(int64_t)(j + 1) * LD + FV_2D] = empty ? nanv : st.s0b * inv_t;
     }
 };
+
+
+// ---------------------------------------------------------------------------------------
+// CTA-pair versions of project and posterior (pvs_tc2.cuh): the weight operand is resident
+// in shared memory (half per CTA) instead of being re-streamed from L2 for every tile, and
+// three producer groups keep three operand stages in flight.
+// ---------------------------------------------------------------------------------------
+}  // namespace tc
+namespace tc2 {
+using tc::FV_D;
+using tc::FV_K;
+using tc::FV_2D;
+using tc::fill_kmajor_32rows;
+using tc::PcaParams;
+using tc::PostParams;
+using tc::NoEpiState;
+
+// Y = X C^T + b, d_in == 128: pair tile [256 rows x 64], C resident (32 rows of C per CTA)
+struct PcaPairPolicy {
+    using Params = PcaParams;
+    using EpiState = NoEpiState;
+    struct Tile { int nkb, mb; };
+    static constexpr bool BF16 = false, MANUAL = true, B_RESIDENT = true;
+    static constexpr int PASSES = 3, BLOCK_N = FV_D, KSTEPS = 4, NKB_RES = 4, STAGES = 4, PGROUPS = 4;
+    static constexpr int A_BYTES = 128 * 128, B_BYTES = (FV_D / 2) * 128, SCRATCH_BYTES = 256, TMA_BYTES = 0;
+    __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.c_hi); tma_prefetch_desc(&p.c_lo); }
+    __device__ static int num_tiles(const Params& p) { return p.m_blocks; }
+    __device__ static int tile_at(const Params&, int it, int pair, int n_pairs, int n)
+    {
+        const long long t = (long long)pair + (long long)it * n_pairs;
+        return t < n ? (int)t : -1;
+    }
+    __device__ static Tile tile(const Params& p, int i) { return {p.nkb, i}; }
+    __device__ static void load_resident(const Params& p, int rank, uint8_t* res, uint64_t* bar)
+    {
+        for (int kb = 0; kb < NKB_RES; ++kb) {
+            tma_load_2d_pair(res + (2 * kb) * B_BYTES, &p.c_hi, bar, kb * 32, rank * (FV_D / 2));
+            tma_load_2d_pair(res + (2 * kb + 1) * B_BYTES, &p.c_lo, bar, kb * 32, rank * (FV_D / 2));
+        }
+    }
+    __device__ static void load(const Params&, const Tile&, int, int, uint8_t*, uint8_t*, uint8_t*, uint8_t*, uint64_t*) {}
+    __device__ static void produce(const Params& p, const Tile& t, int kb, int rank, uint8_t* a_hi, uint8_t* a_lo, int pw,
+                                   int lane)
+    {
+        fill_kmajor_32rows<false>(p.x, p.d_in, (int64_t)t.mb * 256 + rank * 128, p.rows, kb * 32, a_hi, a_lo, pw, lane);
+    }
+    __device__ static void epi_init(const Params& p, uint8_t* scratch, int tid)
+    {
+        float* b = reinterpret_cast<float*>(scratch);
+        if (tid < FV_D) b[tid] = p.bias[tid];
+        epi_barrier();
+    }
+    __device__ static void epi_begin(const Params&, const Tile&, EpiState&, int, int, int) {}
+    __device__ static void epilogue(const Params& p, const Tile& t, int rank, uint32_t tmem, int quarter, int lane,
+                                    uint8_t* scratch, EpiState&)
+    {
+        const float* bias = reinterpret_cast<const float*>(scratch);
+        const int64_t row = (int64_t)t.mb * 256 + rank * 128 + quarter * 32 + lane;
+        const bool valid = row < p.rows;
+        float4* o = reinterpret_cast<float4*>(p.y + row * FV_D);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float v[32];
+            tmem_ld32(tmem + half * 32, v);
+            tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    o[(half * 32 + j) >> 2] = make_float4(v[j] + bias[half * 32 + j], v[j + 1] + bias[half * 32 + j + 1],
+                                                          v[j + 2] + bias[half * 32 + j + 2], v[j + 3] + bias[half * 32 + j + 3]);
+            }
+        }
+    }
+};
+
+// logits + softmax -> Q: pair tile [256 rows x 256 components], W = [-P/2 | mu P] resident
+struct PostPairPolicy {
+    using Params = PostParams;
+    using EpiState = NoEpiState;
+    struct Tile { int nkb, mb; };
+    static constexpr bool BF16 = false, MANUAL = true, B_RESIDENT = true;
+    static constexpr int PASSES = 3, BLOCK_N = FV_K, KSTEPS = 4, NKB_RES = FV_2D / 32, STAGES = 2, PGROUPS = 2;
+    static constexpr int A_BYTES = 128 * 128, B_BYTES = (FV_K / 2) * 128, TMA_BYTES = 0;
+    static constexpr int SCRATCH_BYTES = 1024 + 4 * 4096;     // cst + one [32 x 32] fp32 staging tile per epilogue warp
+    __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.w_hi); tma_prefetch_desc(&p.w_lo); }
+    __device__ static int num_tiles(const Params& p) { return p.m_blocks; }
+    __device__ static int tile_at(const Params&, int it, int pair, int n_pairs, int n)
+    {
+        const long long t = (long long)pair + (long long)it * n_pairs;
+        return t < n ? (int)t : -1;
+    }
+    __device__ static Tile tile(const Params&, int i) { return {FV_2D / 32, i}; }
+    __device__ static void load_resident(const Params& p, int rank, uint8_t* res, uint64_t* bar)
+    {
+        for (int kb = 0; kb < NKB_RES; ++kb) {
+            tma_load_2d_pair(res + (2 * kb) * B_BYTES, &p.w_hi, bar, kb * 32, rank * (FV_K / 2));
+            tma_load_2d_pair(res + (2 * kb + 1) * B_BYTES, &p.w_lo, bar, kb * 32, rank * (FV_K / 2));
+        }
+    }
+    __device__ static void load(const Params&, const Tile&, int, int, uint8_t*, uint8_t*, uint8_t*, uint8_t*, uint64_t*) {}
+    // operand columns [0,64) are y*y, [64,128) are y
+    __device__ static void produce(const Params& p, const Tile& t, int kb, int rank, uint8_t* a_hi, uint8_t* a_lo, int pw,
+                                   int lane)
+    {
+        const int64_t row0 = (int64_t)t.mb * 256 + rank * 128;
+        if (kb < 2) fill_kmajor_32rows<true>(p.y, FV_D, row0, p.rows, kb * 32, a_hi, a_lo, pw, lane);
+        else fill_kmajor_32rows<false>(p.y, FV_D, row0, p.rows, (kb - 2) * 32, a_hi, a_lo, pw, lane);
+    }
+    __device__ static void epi_init(const Params& p, uint8_t* scratch, int tid)
+    {
+        float* c = reinterpret_cast<float*>(scratch);
+        c[tid] = p.cst[tid];
+        c[tid + 128] = p.cst[tid + 128];
+        epi_barrier();
+    }
+    __device__ static void epi_begin(const Params&, const Tile&, EpiState&, int, int, int) {}
+    __device__ static void epilogue(const Params& p, const Tile& t, int rank, uint32_t tmem, int quarter, int lane,
+                                    uint8_t* scratch, EpiState&)
+    {
+        const float* cst = reinterpret_cast<const float*>(scratch);
+        const int64_t row = (int64_t)t.mb * 256 + rank * 128 + quarter * 32 + lane;
+        const bool valid = row < p.rows;
+        // pass 1: row maximum (and arg-max, lowest index on ties)
+        float mx = -INFINITY;
+        int mi = 0;
+#pragma unroll 1
+        for (int c = 0; c < FV_K; c += 32) {
+            float v[32];
+            tmem_ld32(tmem + c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float x = v[j] + cst[c + j];
+                if (x > mx) { mx = x; mi = c + j; }
+            }
+        }
+        const float base = (mx > -INFINITY && mx < INFINITY) ? mx : 0.f;
+        // pass 2: e = exp(l - max), stashed back into the accumulator columns
+        float sum = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < FV_K; c += 32) {
+            float v[32];
+            tmem_ld32(tmem + c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                v[j] = __expf(v[j] + cst[c + j] - base);
+                sum += v[j];
+            }
+            tmem_st32(tmem + c, v);
+        }
+        tmem_st_wait();
+        const float inv = 1.f / sum;
+        if (valid && p.argmax) p.argmax[row] = mi;
+        // pass 3: q = e / sum.  A thread owns a row, so storing straight from registers would
+        // scatter 16-byte pieces over 32 rows per instruction; each [32 rows x 32 cols] chunk
+        // goes through a swizzled shared-memory tile instead and leaves as full 128-byte
+        // row segments (8 lanes per row, 4 rows per instruction).
+        float* stg = reinterpret_cast<float*>(scratch + 1024) + quarter * 1024;
+        const int64_t wrow0 = (int64_t)t.mb * 256 + rank * 128 + quarter * 32;
+#pragma unroll 1
+        for (int c = 0; c < FV_K; c += 32) {
+            float v[32];
+            tmem_ld32(tmem + c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4)
+                *reinterpret_cast<float4*>(stg + lane * 32 + ((j4 ^ (lane & 7)) << 2)) =
+                    make_float4(v[4 * j4] * inv, v[4 * j4 + 1] * inv, v[4 * j4 + 2] * inv, v[4 * j4 + 3] * inv);
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int rr = it * 4 + (lane >> 3), cc = lane & 7;
+                const float4 q4 = *reinterpret_cast<const float4*>(stg + rr * 32 + ((cc ^ (rr & 7)) << 2));
+                if (wrow0 + rr < p.rows) *reinterpret_cast<float4*>(p.q + (wrow0 + rr) * FV_K + c + cc * 4) = q4;
+            }
+            __syncwarp();
+        }
+    }
+};
+}  // namespace tc2
+namespace tc {
 
 // one-off tf32 split of a weight matrix (model creation)
 __global__ void split_kernel(const float4* __restrict__ x, int64_t n4, float4* __restrict__ hi, float4* __restrict__ lo)
@@ -422,6 +606,12 @@ int tc_fv_project(const TcFvPlan& pl, const pvs_model* pca, const float* desc, i
     if ((rc = make_tmap_2d(&p.c_lo, pca->tc1, false, pca->d, pca->d_in, pca->d_in, 32, FV_D))) return rc;
     p.x = desc; p.bias = pca->bias; p.y = pl.y; p.rows = rows;
     p.m_blocks = pl.n_tiles; p.nkb = pca->d_in / 32; p.d_in = pca->d_in;
+    if (pca->d_in == 128) {                                   // CTA pairs, C resident (32 rows per CTA)
+        if ((rc = make_tmap_2d(&p.c_hi, pca->tc0, false, pca->d, pca->d_in, pca->d_in, 32, FV_D / 2))) return rc;
+        if ((rc = make_tmap_2d(&p.c_lo, pca->tc1, false, pca->d, pca->d_in, pca->d_in, 32, FV_D / 2))) return rc;
+        p.m_blocks = (int)ceil_div(rows, 256);
+        return tc2::launch_tc2<tc2::PcaPairPolicy>(p, p.m_blocks, st);
+    }
     return launch_tc<PcaPolicy>(p, p.m_blocks, st);
 }
 
@@ -431,10 +621,11 @@ int tc_fv_posterior(const TcFvPlan& pl, const pvs_model* g, const float* y, int6
     PVS_CHECK(((uintptr_t)y & 15) == 0, PVS_ERR_BAD_ARG, "descriptor buffer must be 16-byte aligned");
     PostParams p{};
     int rc;
-    if ((rc = make_tmap_2d(&p.w_hi, g->tc0, false, FV_K, FV_2D, FV_2D, 32, FV_K))) return rc;
-    if ((rc = make_tmap_2d(&p.w_lo, g->tc1, false, FV_K, FV_2D, FV_2D, 32, FV_K))) return rc;
-    p.y = y; p.cst = g->cst; p.q = pl.q; p.argmax = argmax; p.rows = rows; p.m_blocks = pl.n_tiles;
-    return launch_tc<PostPolicy>(p, p.m_blocks, st);
+    if ((rc = make_tmap_2d(&p.w_hi, g->tc0, false, FV_K, FV_2D, FV_2D, 32, FV_K / 2))) return rc;
+    if ((rc = make_tmap_2d(&p.w_lo, g->tc1, false, FV_K, FV_2D, FV_2D, 32, FV_K / 2))) return rc;
+    p.y = y; p.cst = g->cst; p.q = pl.q; p.argmax = argmax; p.rows = rows;
+    p.m_blocks = (int)ceil_div(rows, 256);                    // CTA pairs: 256-row tiles, W resident
+    return tc2::launch_tc2<tc2::PostPairPolicy>(p, p.m_blocks, st);
 }
 
 int tc_fv_stats(const TcFvPlan& pl, const float* y, const int64_t* offsets, int64_t n_images, cudaStream_t st)

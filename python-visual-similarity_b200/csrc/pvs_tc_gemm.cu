@@ -68,7 +68,7 @@ struct GemmKMajor {
     using EpiState = NoState;
     struct Tile { int nkb, mb, nb; };
     static constexpr bool BF16 = BF16_, A_MN = false, B_MN = false, EPI_READS_STAGES = false, MANUAL = false;
-    static constexpr int PASSES = PASSES_, BLOCK_N = BLOCK_N_, KSTEPS = 4;
+    static constexpr int PASSES = PASSES_, BLOCK_N = BLOCK_N_, KSTEPS = 4, PGROUPS = 1;
     static constexpr int BK = BF16 ? 64 : 32;                       // elements per 128-B span
     static constexpr int A_BYTES = 128 * 128, B_BYTES = BLOCK_N * 128, A_LBO = 0, B_LBO = 0, SCRATCH_BYTES = 0;
     static constexpr int STAGE_ = (PASSES == 3 ? 2 : 1) * (A_BYTES + B_BYTES);
@@ -115,7 +115,7 @@ struct GemmMNMajor {
     struct Tile { int nkb, mb, nb; };
     static constexpr bool BF16 = false, A_MN = true, B_MN = true, EPI_READS_STAGES = false, MANUAL = false;
     static constexpr int KT = 32;                                   // contraction rows per stage
-    static constexpr int PASSES = PASSES_, BLOCK_N = BLOCK_N_, STAGES = 2, KSTEPS = KT / 8;
+    static constexpr int PASSES = PASSES_, BLOCK_N = BLOCK_N_, STAGES = 2, KSTEPS = KT / 8, PGROUPS = 1;
     static constexpr int A_LBO = KT * 128, B_LBO = KT * 128;        // one [KT x 128 B] box per 32 columns
     static constexpr int A_BYTES = 4 * A_LBO, B_BYTES = (BLOCK_N / 32) * B_LBO, SCRATCH_BYTES = 0;
     static constexpr int TMA_BYTES = (PASSES == 3 ? 2 : 1) * (A_BYTES + B_BYTES);
