@@ -26,8 +26,11 @@ int launch_vlad_aggregate(const float* y, int d, const int32_t* labels, const in
 // S [n_images, k, 2d+1] = per image ( q^T [y | y*y] , sum_t q ) / T
 int launch_fv_stats(const float* q, const float* y, int d, int k, const int64_t* offsets,
                     int64_t n_images, float* S, cudaStream_t st);
-int launch_fv_finalize(const float* S, const pvs_model* gmm, int64_t n_images, float power,
-                       float norm_order, float eps, float* out, cudaStream_t st);
+// S rows have pitch ld (2d+1 with s0 in the last column, or 2d with s0 given as `parts`
+// raw partial sums per image in s0part [n_images, parts, k] that still need / T)
+int launch_fv_finalize(const float* S, int ld, const float* s0part, int parts, const int64_t* offsets,
+                       const pvs_model* gmm, int64_t n_images, float power, float norm_order, float eps,
+                       float* out, cudaStream_t st);
 
 // ---- similarity / top-k --------------------------------------------------------------------
 int launch_l2_normalize(const float* x, int64_t n, int64_t d, void* out, int out_dtype, cudaStream_t st);
@@ -54,7 +57,8 @@ int tc_vlad_assign(const pvs_model* km, const float* x, int64_t rows, int32_t* l
 struct TcFvPlan {
     float* y;                    // [rows, 64] projected descriptors (NULL without PCA: y = input)
     float* q;                    // [rows, 256] posteriors
-    float* S;                    // [n_images, 256, 129]
+    float* S;                    // [n_images, 256, 128] first/second-order sums / T
+    float* s0part;               // [n_images, 8, 256] raw zeroth-order partial sums
     int n_tiles;                 // 128-row tiles
     size_t total;
 };

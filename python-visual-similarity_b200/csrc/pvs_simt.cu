@@ -542,59 +542,100 @@ fv_stats_kernel(const float* __restrict__ q, const float* __restrict__ y, int d,
 }
 
 // gradients wrt (pi, mu, sigma), analytic normalisation, signed power, global ord-norm
-__global__ void __launch_bounds__(256)
-fv_finalize_kernel(const float* __restrict__ S, int k, int d, const float* __restrict__ mu,
+// (fisher_vector.py:107-132).  One CTA of 1024 threads per image.  The kernel is bound by
+// the latency of its loads (statistics + four model tables per element), so it is written
+// for memory-level parallelism: s0 goes to shared memory first, then every thread handles
+// four independent elements per step with all their loads issued before the arithmetic.
+// Two passes over the statistics (the second one hits L1/L2): the first only accumulates
+// the norm, the second recomputes each element and writes it scaled, so the output is
+// written exactly once and never read back.  FAST = (power 0.5, ord 2), the defaults:
+// |sqrt|x||^2 = |x|, so the norm pass needs no square roots at all.
+template <bool FAST>
+__global__ void __launch_bounds__(1024)
+fv_finalize_kernel(const float* __restrict__ S, int ld, const float* __restrict__ s0part, int parts,
+                   const int64_t* __restrict__ offsets, int k, int d, const float* __restrict__ mu,
                    const float* __restrict__ var, const float* __restrict__ pi,
                    const float* __restrict__ g_pi, const float* __restrict__ g_mu,
                    const float* __restrict__ g_sig, float power, float ord, float eps,
                    float* __restrict__ out)
 {
-    __shared__ float red[8];
+    extern __shared__ float s0s[];                          // [k]
+    __shared__ float red[32];
     __shared__ float s_den;
     const int64_t img = blockIdx.x;
-    const int ld = 2 * d + 1;
+    const int tid = threadIdx.x, nt = blockDim.x;
     const int kd = k * d;
     const float* Simg = S + img * (int64_t)k * ld;
     float* o = out + img * (int64_t)(2 * kd + k);
-    float part = 0.f;
-    for (int e = threadIdx.x; e < kd; e += blockDim.x) {
-        const int j = e / d, dd = e - j * d;
-        const float s0 = Simg[(int64_t)j * ld + 2 * d];
-        const float s1 = Simg[(int64_t)j * ld + dd];
-        const float s2 = Simg[(int64_t)j * ld + d + dd];
-        const float m = mu[e], v = var[e];
-        float dm = (s1 - s0 * m) * g_mu[e];
-        float ds = (-s2 - s0 * m * m + s0 * v + 2.f * s1 * m) * g_sig[e];
-        dm = signed_pow(dm, power);
-        ds = signed_pow(ds, power);
-        o[k + e] = dm;
-        o[k + kd + e] = ds;
-        part = norm_combine(part, norm_term(dm, ord), ord);
-        part = norm_combine(part, norm_term(ds, ord), ord);
+    if (s0part) {
+        const float inv_t = 1.f / (float)(offsets[img + 1] - offsets[img]);   // T == 0 -> inf -> NaN, as the reference
+        for (int j = tid; j < k; j += nt) {
+            float t = 0.f;
+            for (int q = 0; q < parts; ++q) t += s0part[(img * parts + q) * (int64_t)k + j];
+            s0s[j] = t * inv_t;
+        }
+    } else {
+        for (int j = tid; j < k; j += nt) s0s[j] = Simg[(int64_t)j * ld + 2 * d];
     }
-    for (int j = threadIdx.x; j < k; j += blockDim.x) {
-        const float s0 = Simg[(int64_t)j * ld + 2 * d];
-        const float dp = signed_pow((s0 - pi[j]) * g_pi[j], power);
-        o[j] = dp;
-        part = norm_combine(part, norm_term(dp, ord), ord);
-    }
+    __syncthreads();
+    float den = 0.f;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        float part = 0.f;
+        for (int e0 = tid; e0 < kd; e0 += 4 * nt) {
+            float s1[4], s2[4], m[4], v[4], gm[4], gs[4], s0[4];
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) part = norm_combine(part, __shfl_xor_sync(FULL, part, off), ord);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float t = red[0];
-        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) t = norm_combine(t, red[w], ord);
-        s_den = norm_finish(t, ord) + eps;
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * nt;
+                if (e < kd) {
+                    const int j = e / d, dd = e - j * d;
+                    s1[u] = Simg[(int64_t)j * ld + dd];
+                    s2[u] = Simg[(int64_t)j * ld + d + dd];
+                    m[u] = mu[e]; v[u] = var[e]; gm[u] = g_mu[e]; gs[u] = g_sig[e];
+                    s0[u] = s0s[j];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * nt;
+                if (e < kd) {
+                    const float dm = (s1[u] - s0[u] * m[u]) * gm[u];
+                    const float ds = (-s2[u] - s0[u] * m[u] * m[u] + s0[u] * v[u] + 2.f * s1[u] * m[u]) * gs[u];
+                    if (pass == 0) {
+                        if (FAST) part += fabsf(dm) + fabsf(ds);
+                        else {
+                            part = norm_combine(part, norm_term(signed_pow(dm, power), ord), ord);
+                            part = norm_combine(part, norm_term(signed_pow(ds, power), ord), ord);
+                        }
+                    } else if (FAST) {
+                        o[k + e] = copysignf(sqrtf(fabsf(dm)), dm) / den;
+                        o[k + kd + e] = copysignf(sqrtf(fabsf(ds)), ds) / den;
+                    } else {
+                        o[k + e] = signed_pow(dm, power) / den;
+                        o[k + kd + e] = signed_pow(ds, power) / den;
+                    }
+                }
+            }
+        }
+        for (int j = tid; j < k; j += nt) {
+            const float dp = (s0s[j] - pi[j]) * g_pi[j];
+            if (pass == 0) part = FAST ? part + fabsf(dp) : norm_combine(part, norm_term(signed_pow(dp, power), ord), ord);
+            else o[j] = (FAST ? copysignf(sqrtf(fabsf(dp)), dp) : signed_pow(dp, power)) / den;
+        }
+        if (pass == 0) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) part = norm_combine(part, __shfl_xor_sync(FULL, part, off), ord);
+            if ((tid & 31) == 0) red[tid >> 5] = part;
+            __syncthreads();
+            if (tid == 0) {
+                float t = red[0];
+                for (int w = 1; w < (nt >> 5); ++w) t = norm_combine(t, red[w], ord);
+                s_den = (FAST ? sqrtf(t) : norm_finish(t, ord)) + eps;
+            }
+            __syncthreads();
+            den = s_den;
+        }
     }
-    __syncthreads();
-    const float den = s_den;
-    // every thread rescales exactly the elements it wrote above (no cross-thread hazard)
-    for (int e = threadIdx.x; e < kd; e += blockDim.x) {
-        o[k + e] = o[k + e] / den;
-        o[k + kd + e] = o[k + kd + e] / den;
-    }
-    for (int j = threadIdx.x; j < k; j += blockDim.x) o[j] = o[j] / den;
 }
 }  // namespace
 
@@ -610,12 +651,18 @@ int launch_fv_stats(const float* q, const float* y, int d, int k, const int64_t*
     return PVS_OK;
 }
 
-int launch_fv_finalize(const float* S, const pvs_model* g, int64_t n_images, float power, float norm_order,
-                       float eps, float* out, cudaStream_t st)
+int launch_fv_finalize(const float* S, int ld, const float* s0part, int parts, const int64_t* offsets,
+                       const pvs_model* g, int64_t n_images, float power, float norm_order, float eps, float* out,
+                       cudaStream_t st)
 {
     if (n_images <= 0) return PVS_OK;
-    PVS_LAUNCH(fv_finalize_kernel, (unsigned)n_images, 256, 0, st, S, g->k, g->d, g->mu, g->var, g->pi,
-               g->g_pi, g->g_mu, g->g_sig, power, norm_order, eps, out);
+    PVS_CHECK(g->k <= 12000, PVS_ERR_UNSUPPORTED, "fv_finalize supports k <= 12000 (got %d)", g->k);
+    if (power == 0.5f && norm_order == 2.f)
+        PVS_LAUNCH(fv_finalize_kernel<true>, (unsigned)n_images, 1024, (size_t)g->k * sizeof(float), st, S, ld, s0part, parts, offsets, g->k, g->d,
+                   g->mu, g->var, g->pi, g->g_pi, g->g_mu, g->g_sig, power, norm_order, eps, out);
+    else
+        PVS_LAUNCH(fv_finalize_kernel<false>, (unsigned)n_images, 1024, (size_t)g->k * sizeof(float), st, S, ld, s0part, parts, offsets, g->k, g->d,
+                   g->mu, g->var, g->pi, g->g_pi, g->g_mu, g->g_sig, power, norm_order, eps, out);
     return PVS_OK;
 }
 

@@ -331,23 +331,44 @@ __global__ void __launch_bounds__(Layout<P>::THREADS, 1) tc_kernel(const __grid_
     } else if (warp >= 6) {
         if constexpr (P::MANUAL) {
             // P::PGROUPS groups of four producer warps; group g fills the k-blocks whose
-            // running index is g (mod PGROUPS), so several stages are being loaded at once
+            // running index is g (mod PGROUPS).  fetch() issues the global loads of a k-block
+            // into registers, store() splits and writes the swizzled tiles; the loads of the
+            // group's NEXT k-block are in flight while it waits for that stage to drain.
             const int pw = (warp - 6) & 3, grp = (warp - 6) >> 2;
             long long idx = 0;
-            for (int it = 0, t; (t = P::tile_at(prm, it, n_tiles)) >= 0; ++it) {
-                const typename P::Tile tl = P::tile(prm, t);
-                for (int kb = 0; kb < tl.nkb; ++kb, ++idx) {
-                    if ((int)(idx % P::PGROUPS) != grp) continue;
-                    const int stage = (int)(idx % P::STAGES);
-                    const uint32_t phase = (uint32_t)((idx / P::STAGES) & 1);
-                    mbar_wait(&empty[stage], phase ^ 1);
-                    uint8_t* sp = smem + stage * L::STAGE_BYTES;
-                    P::produce(prm, tl, kb, sp, sp + P::A_BYTES, sp + L::PARTS * P::A_BYTES,
-                               sp + L::PARTS * P::A_BYTES + P::B_BYTES, pw, lane);
-                    fence_proxy_async();                 // generic-proxy stores -> visible to the tensor core
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&full[stage]);
+            int it = 0, kb = 0;
+            int t = P::tile_at(prm, 0, n_tiles);
+            typename P::Tile tl{};
+            if (t >= 0) tl = P::tile(prm, t);
+            auto seek = [&]() {
+                while (t >= 0) {
+                    if (kb >= tl.nkb) {
+                        ++it; kb = 0;
+                        t = P::tile_at(prm, it, n_tiles);
+                        if (t >= 0) tl = P::tile(prm, t);
+                        continue;
+                    }
+                    if ((int)(idx % P::PGROUPS) == grp) return;
+                    ++kb; ++idx;
                 }
+            };
+            seek();
+            typename P::Regs cur;
+            typename P::PState ps{};                         // per-warp producer state that lives across k-blocks
+            if (t >= 0) P::fetch(prm, tl, kb, pw, lane, cur);
+            while (t >= 0) {
+                const int stage = (int)(idx % P::STAGES);
+                const uint32_t phase = (uint32_t)((idx / P::STAGES) & 1);
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* sp = smem + stage * L::STAGE_BYTES;
+                P::store(prm, tl, kb, cur, sp, sp + P::A_BYTES, sp + L::PARTS * P::A_BYTES,
+                         sp + L::PARTS * P::A_BYTES + P::B_BYTES, pw, grp, lane, ps);
+                fence_proxy_async();                     // generic-proxy stores -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[stage]);
+                ++kb; ++idx;
+                seek();
+                if (t >= 0) P::fetch(prm, tl, kb, pw, lane, cur);
             }
         }
     } else {

@@ -26,6 +26,9 @@
 //   B_RESIDENT : the whole B operand (all k-blocks) is loaded once per kernel into a
 //                dedicated region and reused by every tile (weights); else B is staged
 //   NKB_RES    : number of resident k-blocks (B_RESIDENT only)
+//   ACC_INIT   : the epilogue warps pre-load every accumulator buffer (P::acc_init, e.g. a
+//                per-column constant) before the MMA warp may use it, and the first MMA of a
+//                tile accumulates onto that instead of overwriting
 // and its callbacks receive the CTA rank and pair index instead of reading blockIdx.
 #pragma once
 #include "pvs_tc.cuh"
@@ -202,7 +205,8 @@ tc2_kernel(const __grid_constant__ typename P::Params prm)
             if constexpr (P::B_RESIDENT) mbar_wait_cl(bres, 0);
             for (int it = 0, t; (t = P::tile_at(prm, it, pair, n_pairs, n_tiles)) >= 0; ++it) {
                 const typename P::Tile tl = P::tile(prm, t);
-                mbar_wait_cl(&tempty[acc], acc_phase ^ 1);
+                // ACC_INIT: the buffer must have been initialised (phase n) rather than merely be free
+                mbar_wait_cl(&tempty[acc], P::ACC_INIT ? acc_phase : acc_phase ^ 1);
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P::BLOCK_N);
                 for (int kb = 0; kb < tl.nkb; ++kb) {
@@ -217,7 +221,7 @@ tc2_kernel(const __grid_constant__ typename P::Params prm)
                     for (int ks = 0; ks < P::KSTEPS; ++ks) {
                         const uint64_t da_hi = make_smem_desc(a_hi + ks * 32, 16, 1024, LAYOUT_SW128);
                         const uint64_t db_hi = make_smem_desc(b_hi + ks * 32, 16, 1024, LAYOUT_SW128);
-                        const uint32_t first = (kb > 0 || ks > 0) ? 1u : 0u;
+                        const uint32_t first = (P::ACC_INIT || kb > 0 || ks > 0) ? 1u : 0u;
                         if constexpr (P::PASSES == 3) {
                             const uint64_t da_lo = make_smem_desc(a_lo + ks * 32, 16, 1024, LAYOUT_SW128);
                             const uint64_t db_lo = make_smem_desc(b_lo + ks * 32, 16, 1024, LAYOUT_SW128);
@@ -237,21 +241,43 @@ tc2_kernel(const __grid_constant__ typename P::Params prm)
         }
     } else if (warp >= 6) {
         if constexpr (P::MANUAL) {
+            // Operand producers.  fetch() only issues the global loads of a k-block into
+            // registers, store() splits and writes the swizzled tiles.  The loads of the NEXT
+            // k-block of this group are issued before waiting for its stage to drain, so the
+            // global-memory latency overlaps the wait instead of following it.
             const int pw = (warp - 6) & 3, grp = (warp - 6) >> 2;
             long long idx = 0;                               // running k-block index over all tiles of this pair
-            for (int it = 0, t; (t = P::tile_at(prm, it, pair, n_pairs, n_tiles)) >= 0; ++it) {
-                const typename P::Tile tl = P::tile(prm, t);
-                for (int kb = 0; kb < tl.nkb; ++kb, ++idx) {
-                    if ((int)(idx % P::PGROUPS) != grp) continue;
-                    const int stage = (int)(idx % P::STAGES);
-                    const uint32_t phase = (uint32_t)((idx / P::STAGES) & 1);
-                    mbar_wait_cl(&empty[stage], phase ^ 1);
-                    uint8_t* sp = smem + stage * L::STAGE_BYTES;
-                    P::produce(prm, tl, kb, rank, sp, sp + P::A_BYTES, pw, lane);
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_leader(&full[stage]);
+            int it = 0, kb = 0;
+            int t = P::tile_at(prm, 0, pair, n_pairs, n_tiles);
+            typename P::Tile tl{};
+            if (t >= 0) tl = P::tile(prm, t);
+            auto seek = [&]() {                              // advance to the next k-block owned by this group
+                while (t >= 0) {
+                    if (kb >= tl.nkb) {
+                        ++it; kb = 0;
+                        t = P::tile_at(prm, it, pair, n_pairs, n_tiles);
+                        if (t >= 0) tl = P::tile(prm, t);
+                        continue;
+                    }
+                    if ((int)(idx % P::PGROUPS) == grp) return;
+                    ++kb; ++idx;
                 }
+            };
+            seek();
+            typename P::Regs cur;
+            if (t >= 0) P::fetch(prm, tl, kb, rank, pw, lane, cur);
+            while (t >= 0) {
+                const int stage = (int)(idx % P::STAGES);
+                const uint32_t phase = (uint32_t)((idx / P::STAGES) & 1);
+                mbar_wait_cl(&empty[stage], phase ^ 1);
+                uint8_t* sp = smem + stage * L::STAGE_BYTES;
+                P::store(prm, tl, kb, cur, sp, sp + P::A_BYTES, pw, lane);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_leader(&full[stage]);
+                ++kb; ++idx;
+                seek();
+                if (t >= 0) P::fetch(prm, tl, kb, rank, pw, lane, cur);
             }
         }
     } else {
@@ -260,13 +286,26 @@ tc2_kernel(const __grid_constant__ typename P::Params prm)
         uint32_t acc_phase = 0;
         typename P::EpiState st;
         P::epi_init(prm, scratch, (int)threadIdx.x - 64);
+        if constexpr (P::ACC_INIT) {
+            for (int a = 0; a < 2; ++a) {
+                P::acc_init(prm, tmem_base + (uint32_t)(a * P::BLOCK_N) + ((uint32_t)(quarter * 32) << 16), lane, scratch);
+                tmem_st_wait();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_leader(&tempty[a]);
+            }
+        }
         for (int it = 0, t; (t = P::tile_at(prm, it, pair, n_pairs, n_tiles)) >= 0; ++it) {
             const typename P::Tile tl = P::tile(prm, t);
             P::epi_begin(prm, tl, st, rank, quarter, lane);
             mbar_wait_cl(&tfull[acc], acc_phase);
             tcgen05_fence_after();
-            P::epilogue(prm, tl, rank, tmem_base + (uint32_t)(acc * P::BLOCK_N) + ((uint32_t)(quarter * 32) << 16), quarter,
-                        lane, scratch, st);
+            const uint32_t tacc = tmem_base + (uint32_t)(acc * P::BLOCK_N) + ((uint32_t)(quarter * 32) << 16);
+            P::epilogue(prm, tl, rank, tacc, quarter, lane, scratch, st);
+            if constexpr (P::ACC_INIT) {
+                P::acc_init(prm, tacc, lane, scratch);
+                tmem_st_wait();
+            }
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(&tempty[acc]);

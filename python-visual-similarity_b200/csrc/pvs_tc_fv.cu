@@ -43,23 +43,33 @@ __device__ __forceinline__ uint32_t sw128_off(int r, int c) { return (uint32_t)(
 // MN-major SWIZZLE_128B_BASE32B block [rows x 128 B]: row r, 16-B chunk c (32-B chunk c>>1 is swizzled)
 __device__ __forceinline__ uint32_t sw32_off(int r, int c) { return (uint32_t)(r * 128 + ((((c >> 1) ^ (r & 3)) << 5) | ((c & 1) << 4))); }
 
-// one warp fills rows [32 pw, 32 pw + 32) of a [128 rows x 32 floats] K-major operand tile
-// from src[row * ld + col0 ...], optionally squaring, rows >= rows_total read as zero
-template <bool SQUARE>
-__device__ __forceinline__ void fill_kmajor_32rows(const float* __restrict__ src, int64_t ld, int64_t row0, int64_t rows_total,
-                                                   int col0, uint8_t* hi, uint8_t* lo, int pw, int lane)
+// One warp owns rows [32 pw, 32 pw + 32) of a [128 rows x 32 floats] K-major operand tile.
+// fetch: 8 coalesced 16-byte loads per lane from src[row * ld + col0 ...] (rows >= rows_total
+// read as zero); store: optional squaring, tf32 hi/lo split, swizzled 16-byte stores.
+struct KRegs { float4 v[8]; };
+__device__ __forceinline__ void fetch_kmajor_32rows(const float* __restrict__ src, int64_t ld, int64_t row0, int64_t rows_total,
+                                                    int col0, int pw, int lane, KRegs& r)
 {
     const int c = lane & 7;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const int r = pw * 32 + i * 4 + (lane >> 3);
-        const int64_t gr = row0 + r;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gr < rows_total) v = ldg4(src + gr * ld + col0 + c * 4);
+        const int64_t gr = row0 + pw * 32 + i * 4 + (lane >> 3);
+        r.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gr < rows_total) r.v[i] = ldg4(src + gr * ld + col0 + c * 4);
+    }
+}
+template <bool SQUARE>
+__device__ __forceinline__ void store_kmajor_32rows(const KRegs& r, uint8_t* hi, uint8_t* lo, int pw, int lane)
+{
+    const int c = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int row = pw * 32 + i * 4 + (lane >> 3);
+        float4 v = r.v[i];
         if (SQUARE) { v.x *= v.x; v.y *= v.y; v.z *= v.z; v.w *= v.w; }
         float4 h, l;
         split4(v, h, l);
-        const uint32_t off = sw128_off(r, c);
+        const uint32_t off = sw128_off(row, c);
         *reinterpret_cast<float4*>(hi + off) = h;
         *reinterpret_cast<float4*>(lo + off) = l;
     }
@@ -96,10 +106,16 @@ struct PcaPolicy {
         tma_load_2d(b_hi, &p.c_hi, bar, kb * 32, 0);
         tma_load_2d(b_lo, &p.c_lo, bar, kb * 32, 0);
     }
-    __device__ static void produce(const Params& p, const Tile& t, int kb, uint8_t* a_hi, uint8_t* a_lo, uint8_t*,
-                                   uint8_t*, int pw, int lane)
+    using Regs = KRegs;
+    __device__ static void fetch(const Params& p, const Tile& t, int kb, int pw, int lane, Regs& r)
     {
-        fill_kmajor_32rows<false>(p.x, p.d_in, (int64_t)t.mb * 128, p.rows, kb * 32, a_hi, a_lo, pw, lane);
+        fetch_kmajor_32rows(p.x, p.d_in, (int64_t)t.mb * 128, p.rows, kb * 32, pw, lane, r);
+    }
+    struct PState {};
+    __device__ static void store(const Params&, const Tile&, int, const Regs& r, uint8_t* a_hi, uint8_t* a_lo, uint8_t*,
+                                 uint8_t*, int pw, int, int lane, PState&)
+    {
+        store_kmajor_32rows<false>(r, a_hi, a_lo, pw, lane);
     }
     __device__ static void epi_init(const Params& p, uint8_t* scratch, int tid)
     {
@@ -144,96 +160,6 @@ struct PostParams {
     int m_blocks;
 };
 
-struct PostPolicy {
-    using Params = PostParams;
-    using EpiState = NoEpiState;
-    struct Tile { int nkb, mb; };
-    static constexpr bool BF16 = false, A_MN = false, B_MN = false, EPI_READS_STAGES = false, MANUAL = true;
-    static constexpr int PASSES = 3, BLOCK_N = FV_K, KSTEPS = 4, STAGES = 2, PGROUPS = 2;
-    static constexpr int A_BYTES = 128 * 128, B_BYTES = BLOCK_N * 128, A_LBO = 0, B_LBO = 0, SCRATCH_BYTES = 1024;
-    static constexpr int TMA_BYTES = 2 * B_BYTES;
-    __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.w_hi); tma_prefetch_desc(&p.w_lo); }
-    __device__ static int num_tiles(const Params& p) { return p.m_blocks; }
-    __device__ static int tile_at(const Params&, int it, int n) { return strided_tile(it, n); }
-    __device__ static Tile tile(const Params&, int i) { return {FV_2D / 32, i}; }
-    __device__ static void load(const Params& p, const Tile&, int kb, uint8_t*, uint8_t*, uint8_t* b_hi, uint8_t* b_lo,
-                                uint64_t* bar)
-    {
-        tma_load_2d(b_hi, &p.w_hi, bar, kb * 32, 0);
-        tma_load_2d(b_lo, &p.w_lo, bar, kb * 32, 0);
-    }
-    // operand columns [0,64) are y*y, [64,128) are y: k-blocks 0,1 square Y[:, 0:32], Y[:, 32:64]
-    __device__ static void produce(const Params& p, const Tile& t, int kb, uint8_t* a_hi, uint8_t* a_lo, uint8_t*,
-                                   uint8_t*, int pw, int lane)
-    {
-        if (kb < 2) fill_kmajor_32rows<true>(p.y, FV_D, (int64_t)t.mb * 128, p.rows, kb * 32, a_hi, a_lo, pw, lane);
-        else fill_kmajor_32rows<false>(p.y, FV_D, (int64_t)t.mb * 128, p.rows, (kb - 2) * 32, a_hi, a_lo, pw, lane);
-    }
-    __device__ static void epi_init(const Params& p, uint8_t* scratch, int tid)
-    {
-        float* c = reinterpret_cast<float*>(scratch);
-        c[tid] = p.cst[tid];
-        c[tid + 128] = p.cst[tid + 128];
-        epi_barrier();
-    }
-    __device__ static void epi_begin(const Params&, const Tile&, EpiState&, int, int) {}
-    __device__ static void epilogue(const Params& p, const Tile& t, uint32_t tmem, int quarter, int lane,
-                                    uint8_t* scratch, EpiState&)
-    {
-        const float* cst = reinterpret_cast<const float*>(scratch);
-        const int64_t row = (int64_t)t.mb * 128 + quarter * 32 + lane;
-        const bool valid = row < p.rows;
-        // pass 1: row maximum (and arg-max, lowest index on ties)
-        float mx = -INFINITY;
-        int mi = 0;
-#pragma unroll 1
-        for (int c = 0; c < FV_K; c += 32) {
-            float v[32];
-            __syncwarp();
-            tmem_ld32(tmem + c, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float x = v[j] + cst[c + j];
-                if (x > mx) { mx = x; mi = c + j; }
-            }
-        }
-        const float base = (mx > -INFINITY && mx < INFINITY) ? mx : 0.f;
-        // pass 2: e = exp(l - max), stashed back into the accumulator columns
-        float sum = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < FV_K; c += 32) {
-            float v[32];
-            __syncwarp();
-            tmem_ld32(tmem + c, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                v[j] = __expf(v[j] + cst[c + j] - base);
-                sum += v[j];
-            }
-            tmem_st32(tmem + c, v);
-        }
-        tmem_st_wait();
-        const float inv = 1.f / sum;
-        if (valid && p.argmax) p.argmax[row] = mi;
-        // pass 3: q = e / sum
-        float4* o = reinterpret_cast<float4*>(p.q + row * FV_K);
-#pragma unroll 1
-        for (int c = 0; c < FV_K; c += 32) {
-            float v[32];
-            __syncwarp();
-            tmem_ld32(tmem + c, v);
-            tmem_ld_wait();
-            if (valid) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    o[(c + j) >> 2] = make_float4(v[j] * inv, v[j + 1] * inv, v[j + 2] * inv, v[j + 3] * inv);
-            }
-        }
-    }
-};
-
 // ---------------------------------------------------------------------------------------
 // stats: S_i = [y*y | y]_i^T Q_i / T_i  and  s0 = column means of Q_i
 // ---------------------------------------------------------------------------------------
@@ -241,16 +167,16 @@ struct StatsParams {
     const float* y;                           // [rows, 64]
     const float* q;                           // [rows, 256]
     const int64_t* offsets;
-    float* S;                                 // [n_images, 256, 129]: [k][ s1 (64) | s2 (64) | s0 ]
+    float* S;                                 // [n_images, 256, 128]: [k][ s1 (64) | s2 (64) ], already / T
+    float* s0part;                            // [n_images, 8, 256]: raw column sums of Q per producer warp
     int64_t n_images;
 };
-struct StatsState { float s0a, s0b; };
 
 struct StatsPolicy {
     using Params = StatsParams;
-    using EpiState = StatsState;
+    using EpiState = NoEpiState;
     struct Tile { int nkb; int t; int64_t img, r0; };
-    static constexpr bool BF16 = false, A_MN = true, B_MN = true, EPI_READS_STAGES = true, MANUAL = true;
+    static constexpr bool BF16 = false, A_MN = true, B_MN = true, EPI_READS_STAGES = false, MANUAL = true;
     static constexpr int KT = ST_KT;
     static constexpr int PASSES = 3, BLOCK_N = FV_K, STAGES = 4, KSTEPS = KT / 8, PGROUPS = 2;
     static constexpr int A_LBO = KT * 128, B_LBO = KT * 128;          // one [KT rows x 128 B] block per 32 columns
@@ -269,36 +195,54 @@ struct StatsPolicy {
     // producer warp pw owns descriptor rows [RPW pw, RPW pw + RPW) of the stage; rows past the
     // end of the image are written as zeros (that is what makes ragged T exact)
     static constexpr int RPW = KT / 4;
-    __device__ static void produce(const Params& p, const Tile& t, int kb, uint8_t* a_hi, uint8_t* a_lo, uint8_t* b_hi,
-                                   uint8_t* b_lo, int pw, int lane)
+    struct Regs { float4 q[RPW * 2]; float4 y[RPW / 2]; };
+    __device__ static void fetch(const Params& p, const Tile& t, int kb, int pw, int lane, Regs& g)
     {
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        // Q: 64 float4 per row -> two per lane; column block = c4 / 8
+        // Q: 64 float4 per row -> two per lane
+#pragma unroll
+        for (int rr = 0; rr < RPW; ++rr) {
+            const int tt = kb * KT + pw * RPW + rr;
+            const float* qrow = p.q + (t.r0 + tt) * FV_K;
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) g.q[rr * 2 + h2] = tt < t.t ? ldg4(qrow + (lane + 32 * h2) * 4) : z;
+        }
+        // Y: 16 float4 per row -> half a warp per row, two rows per pass
+#pragma unroll
+        for (int pr = 0; pr < RPW / 2; ++pr) {
+            const int tt = kb * KT + pw * RPW + pr * 2 + (lane >> 4);
+            g.y[pr] = tt < t.t ? ldg4(p.y + (t.r0 + tt) * FV_D + (lane & 15) * 4) : z;
+        }
+    }
+    // zeroth-order statistics: every producer lane keeps the running column sums of the Q
+    // values it handles (8 components per lane) and writes them out once per image; the
+    // eight per-warp partials are added up by fv_finalize.  (Reading the Q tiles back from
+    // shared memory for this cost more shared-memory bandwidth than the MMAs had left.)
+    struct PState { float4 s0[2]; };
+    __device__ static void store(const Params& p, const Tile& t, int kb, const Regs& g, uint8_t* a_hi, uint8_t* a_lo,
+                                 uint8_t* b_hi, uint8_t* b_lo, int pw, int grp, int lane, PState& ps)
+    {
 #pragma unroll
         for (int rr = 0; rr < RPW; ++rr) {
             const int r = pw * RPW + rr;
-            const int tt = kb * KT + r;
-            const bool valid = tt < t.t;
-            const float* qrow = p.q + (t.r0 + tt) * FV_K;
 #pragma unroll
             for (int h2 = 0; h2 < 2; ++h2) {
                 const int c4 = lane + 32 * h2;
-                const float4 v = valid ? ldg4(qrow + c4 * 4) : z;
+                const float4 qv = g.q[rr * 2 + h2];
+                ps.s0[h2].x += qv.x; ps.s0[h2].y += qv.y; ps.s0[h2].z += qv.z; ps.s0[h2].w += qv.w;
                 float4 h, l;
-                split4(v, h, l);
+                split4(qv, h, l);
                 const uint32_t off = (uint32_t)((c4 >> 3) * B_LBO) + sw32_off(r, c4 & 7);
                 *reinterpret_cast<float4*>(b_hi + off) = h;
                 *reinterpret_cast<float4*>(b_lo + off) = l;
             }
         }
-        // Y: 16 float4 per row -> half a warp per row, two rows per pass; writes y*y into
-        // column blocks 0,1 and y into blocks 2,3
+        // y*y goes into column blocks 0,1 and y into blocks 2,3
 #pragma unroll
         for (int pr = 0; pr < RPW / 2; ++pr) {
             const int r = pw * RPW + pr * 2 + (lane >> 4);
-            const int tt = kb * KT + r;
             const int c4 = lane & 15;
-            const float4 v = (tt < t.t) ? ldg4(p.y + (t.r0 + tt) * FV_D + c4 * 4) : z;
+            const float4 v = g.y[pr];
             const float4 s = make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w);
             float4 h, l;
             const uint32_t off = (uint32_t)((c4 >> 3) * A_LBO) + sw32_off(r, c4 & 7);
@@ -309,35 +253,21 @@ struct StatsPolicy {
             *reinterpret_cast<float4*>(a_hi + 2 * A_LBO + off) = h;
             *reinterpret_cast<float4*>(a_lo + 2 * A_LBO + off) = l;
         }
+        if (kb + PGROUPS >= t.nkb) {                       // this group's last k-block of the image
+            float4* dst = reinterpret_cast<float4*>(p.s0part + ((t.img * (PGROUPS * 4) + grp * 4 + pw) * FV_K));
+            dst[lane] = ps.s0[0];
+            dst[lane + 32] = ps.s0[1];
+            ps.s0[0] = ps.s0[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
     __device__ static void epi_init(const Params&, uint8_t*, int) {}
-    __device__ static void epi_begin(const Params&, const Tile&, EpiState& st, int, int) { st.s0a = st.s0b = 0.f; }
-    // column sums of the Q tile in shared memory: epilogue thread e owns components 2e, 2e+1
-    __device__ static void consume(const Params&, const Tile&, int, uint8_t*, uint8_t*, uint8_t* b_hi, uint8_t* b_lo,
-                                   EpiState& st, int quarter, int lane)
-    {
-        const int j = (quarter * 32 + lane) * 2;
-        const int c = j & 31;                                   // column inside the 32-wide block
-        const uint32_t blk_off = (uint32_t)((j >> 5) * B_LBO);
-        float a = 0.f, b = 0.f;
-#pragma unroll 8
-        for (int r = 0; r < KT; ++r) {
-            const uint32_t off = blk_off + sw32_off(r, c >> 2) + (uint32_t)((c & 3) * 4);
-            const float2 h = *reinterpret_cast<const float2*>(b_hi + off);
-            const float2 l = *reinterpret_cast<const float2*>(b_lo + off);
-            a += h.x + l.x;
-            b += h.y + l.y;
-        }
-        st.s0a += a;
-        st.s0b += b;
-    }
+    __device__ static void epi_begin(const Params&, const Tile&, EpiState&, int, int) {}
     __device__ static void epilogue(const Params& p, const Tile& t, uint32_t tmem, int quarter, int lane, uint8_t*,
-                                    EpiState& st)
+                                    EpiState&)
     {
-        constexpr int LD = FV_2D + 1;
         const int e = quarter * 32 + lane;                 // operand row: [0,64) = y*y, [64,128) = y
-        const int n = e < FV_D ? FV_D + e : e - FV_D;      // column in the [ s1 | s2 | s0 ] layout
-        float* Simg = p.S + t.img * (int64_t)FV_K * LD;
+        const int n = e < FV_D ? FV_D + e : e - FV_D;      // column in the [ s1 | s2 ] layout
+        float* Simg = p.S + t.img * (int64_t)FV_K * FV_2D;
         const float inv_t = 1.f / (float)t.t;              // T == 0 -> NaN, like the reference
         const bool empty = t.nkb == 0;
         const float nanv = __int_as_float(0x7fc00000);
@@ -348,11 +278,8 @@ struct StatsPolicy {
             tmem_ld32(tmem + c, v);
             tmem_ld_wait();
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) Simg[(int64_t)(c + jj) * LD + n] = empty ? nanv : v[jj] * inv_t;
+            for (int jj = 0; jj < 32; ++jj) Simg[(int64_t)(c + jj) * FV_2D + n] = empty ? nanv : v[jj] * inv_t;
         }
-        const int j = e * 2;
-        Simg[(int64_t)j * LD + FV_2D] = empty ? nanv : st.s0a * inv_t;
-        Simg[(int64_t)(j + 1) * LD + FV_2D] = empty ? nanv : st.s0b * inv_t;
     }
 };
 
@@ -367,7 +294,9 @@ namespace tc2 {
 using tc::FV_D;
 using tc::FV_K;
 using tc::FV_2D;
-using tc::fill_kmajor_32rows;
+using tc::KRegs;
+using tc::fetch_kmajor_32rows;
+using tc::store_kmajor_32rows;
 using tc::PcaParams;
 using tc::PostParams;
 using tc::NoEpiState;
@@ -377,7 +306,7 @@ struct PcaPairPolicy {
     using Params = PcaParams;
     using EpiState = NoEpiState;
     struct Tile { int nkb, mb; };
-    static constexpr bool BF16 = false, MANUAL = true, B_RESIDENT = true;
+    static constexpr bool BF16 = false, MANUAL = true, B_RESIDENT = true, ACC_INIT = false;
     static constexpr int PASSES = 3, BLOCK_N = FV_D, KSTEPS = 4, NKB_RES = 4, STAGES = 4, PGROUPS = 4;
     static constexpr int A_BYTES = 128 * 128, B_BYTES = (FV_D / 2) * 128, SCRATCH_BYTES = 256, TMA_BYTES = 0;
     __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.c_hi); tma_prefetch_desc(&p.c_lo); }
@@ -396,10 +325,14 @@ struct PcaPairPolicy {
         }
     }
     __device__ static void load(const Params&, const Tile&, int, int, uint8_t*, uint8_t*, uint8_t*, uint8_t*, uint64_t*) {}
-    __device__ static void produce(const Params& p, const Tile& t, int kb, int rank, uint8_t* a_hi, uint8_t* a_lo, int pw,
-                                   int lane)
+    using Regs = KRegs;
+    __device__ static void fetch(const Params& p, const Tile& t, int kb, int rank, int pw, int lane, Regs& r)
     {
-        fill_kmajor_32rows<false>(p.x, p.d_in, (int64_t)t.mb * 256 + rank * 128, p.rows, kb * 32, a_hi, a_lo, pw, lane);
+        fetch_kmajor_32rows(p.x, p.d_in, (int64_t)t.mb * 256 + rank * 128, p.rows, kb * 32, pw, lane, r);
+    }
+    __device__ static void store(const Params&, const Tile&, int, const Regs& r, uint8_t* a_hi, uint8_t* a_lo, int pw, int lane)
+    {
+        store_kmajor_32rows<false>(r, a_hi, a_lo, pw, lane);
     }
     __device__ static void epi_init(const Params& p, uint8_t* scratch, int tid)
     {
@@ -435,7 +368,7 @@ struct PostPairPolicy {
     using Params = PostParams;
     using EpiState = NoEpiState;
     struct Tile { int nkb, mb; };
-    static constexpr bool BF16 = false, MANUAL = true, B_RESIDENT = true;
+    static constexpr bool BF16 = false, MANUAL = true, B_RESIDENT = true, ACC_INIT = true;
     static constexpr int PASSES = 3, BLOCK_N = FV_K, KSTEPS = 4, NKB_RES = FV_2D / 32, STAGES = 2, PGROUPS = 2;
     static constexpr int A_BYTES = 128 * 128, B_BYTES = (FV_K / 2) * 128, TMA_BYTES = 0;
     static constexpr int SCRATCH_BYTES = 1024 + 4 * 4096;     // cst + one [32 x 32] fp32 staging tile per epilogue warp
@@ -456,12 +389,15 @@ struct PostPairPolicy {
     }
     __device__ static void load(const Params&, const Tile&, int, int, uint8_t*, uint8_t*, uint8_t*, uint8_t*, uint64_t*) {}
     // operand columns [0,64) are y*y, [64,128) are y
-    __device__ static void produce(const Params& p, const Tile& t, int kb, int rank, uint8_t* a_hi, uint8_t* a_lo, int pw,
-                                   int lane)
+    using Regs = KRegs;
+    __device__ static void fetch(const Params& p, const Tile& t, int kb, int rank, int pw, int lane, Regs& r)
     {
-        const int64_t row0 = (int64_t)t.mb * 256 + rank * 128;
-        if (kb < 2) fill_kmajor_32rows<true>(p.y, FV_D, row0, p.rows, kb * 32, a_hi, a_lo, pw, lane);
-        else fill_kmajor_32rows<false>(p.y, FV_D, row0, p.rows, (kb - 2) * 32, a_hi, a_lo, pw, lane);
+        fetch_kmajor_32rows(p.y, FV_D, (int64_t)t.mb * 256 + rank * 128, p.rows, (kb & 1) * 32, pw, lane, r);
+    }
+    __device__ static void store(const Params&, const Tile&, int kb, const Regs& r, uint8_t* a_hi, uint8_t* a_lo, int pw, int lane)
+    {
+        if (kb < 2) store_kmajor_32rows<true>(r, a_hi, a_lo, pw, lane);
+        else store_kmajor_32rows<false>(r, a_hi, a_lo, pw, lane);
     }
     __device__ static void epi_init(const Params& p, uint8_t* scratch, int tid)
     {
@@ -470,29 +406,56 @@ struct PostPairPolicy {
         c[tid + 128] = p.cst[tid + 128];
         epi_barrier();
     }
+    // every lane (descriptor row) of an accumulator buffer starts from the per-component constant
+    __device__ static void acc_init(const Params&, uint32_t tmem, int, uint8_t* scratch)
+    {
+        const float4* cst4 = reinterpret_cast<const float4*>(scratch);
+#pragma unroll 1
+        for (int c = 0; c < FV_K; c += 32) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 t = cst4[(c >> 2) + j];
+                v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+            }
+            tmem_st32(tmem + c, v);
+        }
+    }
     __device__ static void epi_begin(const Params&, const Tile&, EpiState&, int, int, int) {}
     __device__ static void epilogue(const Params& p, const Tile& t, int rank, uint32_t tmem, int quarter, int lane,
                                     uint8_t* scratch, EpiState&)
     {
-        const float* cst = reinterpret_cast<const float*>(scratch);
         const int64_t row = (int64_t)t.mb * 256 + rank * 128 + quarter * 32 + lane;
         const bool valid = row < p.rows;
-        // pass 1: row maximum (and arg-max, lowest index on ties)
+        // The accumulator was pre-loaded with cst (acc_init), so the TMEM columns hold the
+        // complete logits.  pass 1: row maximum (arg-max only when the caller asked for it)
         float mx = -INFINITY;
         int mi = 0;
+        if (p.argmax) {
 #pragma unroll 1
-        for (int c = 0; c < FV_K; c += 32) {
-            float v[32];
-            tmem_ld32(tmem + c, v);
-            tmem_ld_wait();
+            for (int c = 0; c < FV_K; c += 32) {
+                float v[32];
+                tmem_ld32(tmem + c, v);
+                tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float x = v[j] + cst[c + j];
-                if (x > mx) { mx = x; mi = c + j; }
+                for (int j = 0; j < 32; ++j)
+                    if (v[j] > mx) { mx = v[j]; mi = c + j; }     // strict >: lowest index on ties
+            }
+        } else {
+#pragma unroll 1
+            for (int c = 0; c < FV_K; c += 32) {
+                float v[32];
+                tmem_ld32(tmem + c, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) mx = fmaxf(mx, v[j]);
             }
         }
         const float base = (mx > -INFINITY && mx < INFINITY) ? mx : 0.f;
-        // pass 2: e = exp(l - max), stashed back into the accumulator columns
+        // pass 2: e = exp(l - max) = 2^(l log2e - max log2e): one FFMA + one MUFU per logit;
+        // e is stashed back into the accumulator columns
+        constexpr float LOG2E = 1.4426950408889634f;
+        const float nb = -base * LOG2E;
         float sum = 0.f;
 #pragma unroll 1
         for (int c = 0; c < FV_K; c += 32) {
@@ -501,8 +464,10 @@ struct PostPairPolicy {
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                v[j] = __expf(v[j] + cst[c + j] - base);
-                sum += v[j];
+                float e;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(v[j], LOG2E, nb)));
+                v[j] = e;
+                sum += e;
             }
             tmem_st32(tmem + c, v);
         }
@@ -591,7 +556,8 @@ int tc_fv_plan(const pvs_model* g, const pvs_model* pca, int64_t rows, int64_t n
     pl->n_tiles = (int)ceil_div(rows, 128);
     pl->y = pca ? (float*)take((size_t)rows * FV_D * 4) : nullptr;
     pl->q = (float*)take((size_t)rows * FV_K * 4);
-    pl->S = (float*)take((size_t)n_images * FV_K * (FV_2D + 1) * 4);
+    pl->S = (float*)take((size_t)n_images * FV_K * FV_2D * 4);
+    pl->s0part = (float*)take((size_t)n_images * 8 * FV_K * 4);
     pl->total = off + 1024;
     return PVS_OK;
 }
@@ -632,7 +598,9 @@ int tc_fv_stats(const TcFvPlan& pl, const float* y, const int64_t* offsets, int6
 {
     if (n_images <= 0) return PVS_OK;
     StatsParams p{};
-    p.y = y; p.q = pl.q; p.offsets = offsets; p.S = pl.S; p.n_images = n_images;
+    p.y = y; p.q = pl.q; p.offsets = offsets; p.S = pl.S; p.s0part = pl.s0part; p.n_images = n_images;
+    // a producer group only writes its partial when it owned a k-block of the image
+    PVS_CUDA(cudaMemsetAsync(pl.s0part, 0, (size_t)n_images * 8 * FV_K * 4, st));
     return launch_tc<StatsPolicy>(p, (int)n_images, st);
 }
 

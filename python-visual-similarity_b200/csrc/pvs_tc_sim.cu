@@ -81,7 +81,7 @@ struct SimPolicy {
     using Params = SimParams;
     using EpiState = SimState;
     struct Tile { int nkb, qb, dbb, stripe; bool first, last; };
-    static constexpr bool BF16 = true, MANUAL = false, B_RESIDENT = false;
+    static constexpr bool BF16 = true, MANUAL = false, B_RESIDENT = false, ACC_INIT = false;
     static constexpr int CAP = CAP_, PASSES = 1, BLOCK_N = 256, KSTEPS = 4, NKB_RES = 0, PGROUPS = 1;
     static constexpr int A_BYTES = 128 * 128, B_BYTES = 128 * 128, TMA_BYTES = A_BYTES + B_BYTES;
     static constexpr int SCRATCH_BYTES = CAP <= 512 ? 0 : 4 * CAP * 8;

@@ -31,19 +31,19 @@ struct AssignState {};
 
 __device__ __forceinline__ uint32_t swz128(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
-// one warp fills rows [32 pw, 32 pw + 32) of a [128 rows x 32 floats] K-major tile (hi and lo
-// parts) from src[row * d + col0 ...]; columns >= d and rows >= rows_total read as zero.
-// VEC = floats per load the row alignment allows (4: d % 4 == 0, 2: d % 2 == 0, else 1).
+// One warp owns rows [32 pw, 32 pw + 32) of a [128 rows x 32 floats] K-major tile (hi and lo
+// parts).  fetch: loads from src[row * d + col0 ...]; columns >= d and rows >= rows_total
+// read as zero.  VEC = floats per load the row alignment allows (4: d % 4 == 0,
+// 2: d % 2 == 0, else 1).  store: tf32 split + swizzled 16-byte stores.
+struct ARegs { float4 v[8]; };
 template <int VEC>
-__device__ __forceinline__ void fill_tile_rows(const float* __restrict__ src, int d, int64_t row0, int64_t rows_total,
-                                               int col0, uint8_t* hi, uint8_t* lo, int pw, int lane)
+__device__ __forceinline__ void fetch_tile_rows(const float* __restrict__ src, int d, int64_t row0, int64_t rows_total,
+                                                int col0, int pw, int lane, ARegs& g)
 {
-    const int c = lane & 7;                                   // 16-byte chunk inside the 128-byte row
-    const int col = col0 + c * 4;
+    const int col = col0 + (lane & 7) * 4;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const int r = pw * 32 + i * 4 + (lane >> 3);
-        const int64_t gr = row0 + r;
+        const int64_t gr = row0 + pw * 32 + i * 4 + (lane >> 3);
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (gr < rows_total) {
             const float* p = src + gr * (int64_t)d + col;
@@ -59,6 +59,16 @@ __device__ __forceinline__ void fill_tile_rows(const float* __restrict__ src, in
                 if (col + 3 < d) v.w = __ldg(p + 3);
             }
         }
+        g.v[i] = v;
+    }
+}
+__device__ __forceinline__ void store_tile_rows(const ARegs& g, uint8_t* hi, uint8_t* lo, int pw, int lane)
+{
+    const int c = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = pw * 32 + i * 4 + (lane >> 3);
+        const float4 v = g.v[i];
         float4 h, l;
         tf32_split(v.x, h.x, l.x);
         tf32_split(v.y, h.y, l.y);
@@ -75,7 +85,7 @@ struct AssignPolicy {
     using Params = AssignParams;
     using EpiState = AssignState;
     struct Tile { int nkb, mb; };
-    static constexpr bool BF16 = false, MANUAL = true, B_RESIDENT = RES_;
+    static constexpr bool BF16 = false, MANUAL = true, B_RESIDENT = RES_, ACC_INIT = false;
     static constexpr int PASSES = 3, BLOCK_N = 256, KSTEPS = 4, NKB_RES = NKB_, STAGES = 3, PGROUPS = 3;
     static constexpr int A_BYTES = 128 * 128, B_BYTES = 128 * 128, SCRATCH_BYTES = 1024;
     static constexpr int TMA_BYTES = RES_ ? 0 : 2 * B_BYTES;
@@ -100,10 +110,14 @@ struct AssignPolicy {
         tma_load_2d_pair(b_hi, &p.c_hi, bar, kb * 32, rank * 128);
         tma_load_2d_pair(b_lo, &p.c_lo, bar, kb * 32, rank * 128);
     }
-    __device__ static void produce(const Params& p, const Tile& t, int kb, int rank, uint8_t* a_hi, uint8_t* a_lo, int pw,
-                                   int lane)
+    using Regs = ARegs;
+    __device__ static void fetch(const Params& p, const Tile& t, int kb, int rank, int pw, int lane, Regs& g)
     {
-        fill_tile_rows<VEC_>(p.x, p.d, (int64_t)t.mb * 256 + rank * 128, p.rows, kb * 32, a_hi, a_lo, pw, lane);
+        fetch_tile_rows<VEC_>(p.x, p.d, (int64_t)t.mb * 256 + rank * 128, p.rows, kb * 32, pw, lane, g);
+    }
+    __device__ static void store(const Params&, const Tile&, int, const Regs& g, uint8_t* a_hi, uint8_t* a_lo, int pw, int lane)
+    {
+        store_tile_rows(g, a_hi, a_lo, pw, lane);
     }
     __device__ static void epi_init(const Params& p, uint8_t* scratch, int tid)
     {
