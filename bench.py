@@ -353,7 +353,7 @@ def run_ours(args):
             "config": {"workload": desc, "images_per_gpu": n_img, "descriptors_per_image": T, "d_in": d_in,
                        "k": K, "d": D, "weights": "bundled gmm_k256_sift_pca + pca_k256_sift_f2",
                        "l2": "inputs (8.4 GB/GPU) larger than L2, no flush", "parallelism": f"dp{world} (images sharded, no collective)",
-                       "images_per_call": args.images_per_call},
+                       "images_per_call": args.images_per_call or "4 per SM (592)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(e_rows * d_in * 4 + (e2e_images + 1) * 8),
                     "d2h_bytes_per_step": int(e2e_images * out_dim * 4), "images": e2e_images,
                     "matches_device_path": e2e_ok},
@@ -380,7 +380,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--images", type=int, default=0, help="override images per GPU (debug)")
-    ap.add_argument("--images-per-call", type=int, default=512)
+    ap.add_argument("--images-per-call", type=int, default=0, help="0 = library default (4 per SM)")
     ap.add_argument("--e2e-images", type=int, default=0, help="images in the host-buffer leg (0 = all)")
     ap.add_argument("--cpu-sample", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")

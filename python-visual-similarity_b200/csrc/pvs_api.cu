@@ -434,7 +434,7 @@ extern "C" int pvs_fv_encode(const pvs_model* g, const pvs_model* pca, const flo
             if (int rc = PVS_STAGE(ST_TC_FV_PROJECT, st, tc_fv_project(pl, pca, desc, total_rows, st))) return rc;
         if (int rc = PVS_STAGE(ST_TC_FV_POSTERIOR, st, tc_fv_posterior(pl, g, y, total_rows, argmax_out, st))) return rc;
         if (int rc = PVS_STAGE(ST_TC_FV_STATS, st, tc_fv_stats(pl, y, offsets, n_images, st))) return rc;
-        return PVS_STAGE(ST_FV_FINALIZE, st, launch_fv_finalize(pl.S, 2 * g->d, pl.s0part, 8, offsets, g, n_images, power,
+        return PVS_STAGE(ST_FV_FINALIZE, st, launch_fv_finalize(pl.S, 2 * g->d, pl.s0part, TC_FV_S0_PARTS, offsets, g, n_images, power,
                                                                  norm_order, eps, out, st));
     }
     PVS_CHECK(g_path.load() != PVS_PATH_TENSOR, PVS_ERR_UNSUPPORTED,

@@ -54,11 +54,12 @@ bool tc_assign_supported(const pvs_model* km, int64_t rows);
 int tc_vlad_assign(const pvs_model* km, const float* x, int64_t rows, int32_t* labels, cudaStream_t st);
 
 // Fisher vector, K = 256 / D = 64: workspace carve-up and the three tensor-core stages
+constexpr int TC_FV_S0_PARTS = 16;   // producer warps of the stats kernel, one zeroth-order partial each
 struct TcFvPlan {
     float* y;                    // [rows, 64] projected descriptors (NULL without PCA: y = input)
     float* q;                    // [rows, 256] posteriors
     float* S;                    // [n_images, 256, 128] first/second-order sums / T
-    float* s0part;               // [n_images, 8, 256] raw zeroth-order partial sums
+    float* s0part;               // [n_images, TC_FV_S0_PARTS, 256] raw zeroth-order partial sums
     int n_tiles;                 // 128-row tiles
     size_t total;
 };

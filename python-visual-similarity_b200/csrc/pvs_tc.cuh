@@ -12,6 +12,7 @@
 //                 (tools/tf32_split_study.py: any cheaper split misses the 1e-4 parity bar).
 #pragma once
 #include <cuda.h>
+#include <stdlib.h>
 #include "pvs_common.cuh"
 
 namespace pvs {
@@ -215,6 +216,17 @@ __device__ __forceinline__ int strided_tile(int it, int n_tiles)
     return t < n_tiles ? (int)t : -1;
 }
 
+#ifdef PVS_TIMING
+// cycles summed over CTAs: [0] MMA wait full, [1] MMA wait tempty, [2] MMA total,
+// [3] epilogue (warp 2) wait tfull, [4] epilogue total, [5] producer (warp 6) wait empty, [6] producer total
+__device__ unsigned long long g_tc_timing[8];
+#define PVS1_T0(var) const long long var = clock64()
+#define PVS1_ADD(slot, t0, cond) do { if (cond) atomicAdd(&g_tc_timing[slot], (unsigned long long)(clock64() - (t0))); } while (0)
+#else
+#define PVS1_T0(var)
+#define PVS1_ADD(slot, t0, cond)
+#endif
+
 template <class P>
 struct Layout {
     static constexpr int PARTS = P::PASSES == 3 ? 2 : 1;
@@ -240,7 +252,9 @@ __global__ void __launch_bounds__(Layout<P>::THREADS, 1) tc_kernel(const __grid_
 {
     using L = Layout<P>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment as an OFFSET on the __shared__ array: going through an integer cast would
+    // turn every later access into a generic LD / ST instead of LDS / STS
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::RING_BYTES);
     uint64_t* empty = full + P::STAGES;
     uint64_t* tfull = empty + P::STAGES;
@@ -291,11 +305,15 @@ __global__ void __launch_bounds__(Layout<P>::THREADS, 1) tc_kernel(const __grid_
             uint32_t phase = 0, acc_phase = 0;
             for (int it = 0, t; (t = P::tile_at(prm, it, n_tiles)) >= 0; ++it) {
                 const typename P::Tile tl = P::tile(prm, t);
+                PVS1_T0(t_te);
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
+                PVS1_ADD(1, t_te, true);
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P::BLOCK_N);
                 for (int kb = 0; kb < tl.nkb; ++kb) {
+                    PVS1_T0(t_fu);
                     mbar_wait(&full[stage], phase);
+                    PVS1_ADD(0, t_fu, true);
                     tcgen05_fence_after();
                     const uint32_t sp = smem_u32(smem + stage * L::STAGE_BYTES);
                     const uint32_t a_hi = sp, a_lo = sp + P::A_BYTES;
@@ -359,7 +377,9 @@ __global__ void __launch_bounds__(Layout<P>::THREADS, 1) tc_kernel(const __grid_
             while (t >= 0) {
                 const int stage = (int)(idx % P::STAGES);
                 const uint32_t phase = (uint32_t)((idx / P::STAGES) & 1);
+                PVS1_T0(t_em);
                 mbar_wait(&empty[stage], phase ^ 1);
+                PVS1_ADD(5, t_em, warp == 6 && lane == 0);
                 uint8_t* sp = smem + stage * L::STAGE_BYTES;
                 P::store(prm, tl, kb, cur, sp, sp + P::A_BYTES, sp + L::PARTS * P::A_BYTES,
                          sp + L::PARTS * P::A_BYTES + P::B_BYTES, pw, grp, lane, ps);
@@ -391,10 +411,14 @@ __global__ void __launch_bounds__(Layout<P>::THREADS, 1) tc_kernel(const __grid_
                     if (++stage == P::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
+            PVS1_T0(t_tf);
             mbar_wait(&tfull[acc], acc_phase);
+            PVS1_ADD(3, t_tf, warp == 2 && lane == 0);
             tcgen05_fence_after();
+            PVS1_T0(t_body);
             P::epilogue(prm, tl, tmem_base + (uint32_t)(acc * P::BLOCK_N) + ((uint32_t)(quarter * 32) << 16), quarter,
                         lane, scratch, st);
+            PVS1_ADD(4, t_body, warp == 2 && lane == 0);
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -424,6 +448,17 @@ int launch_tc(const typename P::Params& prm, int n_tiles, cudaStream_t st, int g
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PVS_ERR_CUDA, "tcgen05 kernel launch failed: %s", cudaGetErrorString(e));
+#ifdef PVS_TIMING
+    if (getenv("PVS_TIMING_PRINT")) {
+        cudaStreamSynchronize(st);
+        unsigned long long h[8], z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        cudaMemcpyFromSymbol(h, g_tc_timing, sizeof(h));
+        cudaMemcpyToSymbol(g_tc_timing, z, sizeof(z));
+        const double np = grid;
+        fprintf(stderr, "[tc timing %s] per CTA (kcycles): mma wait_full %.0f wait_tempty %.0f | epi wait_tfull %.0f body %.0f | prod wait_empty %.0f\n",
+                __PRETTY_FUNCTION__, h[0] / np / 1e3, h[1] / np / 1e3, h[3] / np / 1e3, h[4] / np / 1e3, h[5] / np / 1e3);
+    }
+#endif
     return PVS_OK;
 }
 

@@ -31,6 +31,7 @@
 //                tile accumulates onto that instead of overwriting
 // and its callbacks receive the CTA rank and pair index instead of reading blockIdx.
 #pragma once
+#include <stdlib.h>
 #include "pvs_tc.cuh"
 
 namespace pvs {
@@ -114,6 +115,20 @@ __device__ __forceinline__ void umma2_commit(uint64_t* bar)
                  ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 
+#ifdef PVS_TIMING
+// role wait-time counters (cycles, summed over CTAs): [0] MMA wait full, [1] MMA wait tempty,
+// [2] MMA total, [3] epilogue(warp 2) wait tfull, [4] epilogue total, [5] producer(warp 6) wait empty,
+// [6] producer total, [7] epilogue body
+__device__ unsigned long long g_tc2_timing[16];          // [8..15]: policy-defined phases (PVS_TPHASE)
+#define PVS_T0(var) const long long var = clock64()
+#define PVS_TACC(slot, t0) timing_acc[slot] += clock64() - (t0)
+#define PVS_TPHASE(slot, t0, cond) do { if (cond) atomicAdd(&g_tc2_timing[slot], (unsigned long long)(clock64() - (t0))); } while (0)
+#else
+#define PVS_T0(var)
+#define PVS_TACC(slot, t0)
+#define PVS_TPHASE(slot, t0, cond)
+#endif
+
 template <class P>
 struct Layout2 {
     static constexpr int PARTS = P::PASSES == 3 ? 2 : 1;
@@ -142,7 +157,9 @@ tc2_kernel(const __grid_constant__ typename P::Params prm)
 {
     using L = Layout2<P>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment as an OFFSET on the __shared__ array: going through an integer cast would
+    // turn every later access into a generic LD / ST instead of LDS / STS
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* res = smem + L::RING_BYTES;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::RING_BYTES + L::RES_BYTES);
     uint64_t* empty = full + P::STAGES;
@@ -202,15 +219,23 @@ tc2_kernel(const __grid_constant__ typename P::Params prm)
             constexpr uint32_t idesc = make_idesc(P::BF16, false, false, 256, P::BLOCK_N);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
+#ifdef PVS_TIMING
+            long long timing_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+            PVS_T0(t_role);
             if constexpr (P::B_RESIDENT) mbar_wait_cl(bres, 0);
             for (int it = 0, t; (t = P::tile_at(prm, it, pair, n_pairs, n_tiles)) >= 0; ++it) {
                 const typename P::Tile tl = P::tile(prm, t);
                 // ACC_INIT: the buffer must have been initialised (phase n) rather than merely be free
+                PVS_T0(t_te);
                 mbar_wait_cl(&tempty[acc], P::ACC_INIT ? acc_phase : acc_phase ^ 1);
+                PVS_TACC(1, t_te);
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P::BLOCK_N);
                 for (int kb = 0; kb < tl.nkb; ++kb) {
+                    PVS_T0(t_fu);
                     mbar_wait_cl(&full[stage], phase);
+                    PVS_TACC(0, t_fu);
                     tcgen05_fence_after();
                     const uint32_t sp = smem_u32(smem + stage * L::STAGE_BYTES);
                     const uint32_t a_hi = sp, a_lo = sp + P::A_BYTES;
@@ -238,6 +263,10 @@ tc2_kernel(const __grid_constant__ typename P::Params prm)
                 umma2_commit(&tfull[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
+#ifdef PVS_TIMING
+            PVS_TACC(2, t_role);
+            for (int i = 0; i < 3; ++i) atomicAdd(&g_tc2_timing[i], (unsigned long long)timing_acc[i]);
+#endif
         }
     } else if (warp >= 6) {
         if constexpr (P::MANUAL) {
@@ -265,11 +294,17 @@ tc2_kernel(const __grid_constant__ typename P::Params prm)
             };
             seek();
             typename P::Regs cur;
+#ifdef PVS_TIMING
+            long long timing_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+            PVS_T0(t_role);
             if (t >= 0) P::fetch(prm, tl, kb, rank, pw, lane, cur);
             while (t >= 0) {
                 const int stage = (int)(idx % P::STAGES);
                 const uint32_t phase = (uint32_t)((idx / P::STAGES) & 1);
+                PVS_T0(t_em);
                 mbar_wait_cl(&empty[stage], phase ^ 1);
+                PVS_TACC(5, t_em);
                 uint8_t* sp = smem + stage * L::STAGE_BYTES;
                 P::store(prm, tl, kb, cur, sp, sp + P::A_BYTES, pw, lane);
                 fence_proxy_async();
@@ -279,6 +314,10 @@ tc2_kernel(const __grid_constant__ typename P::Params prm)
                 seek();
                 if (t >= 0) P::fetch(prm, tl, kb, rank, pw, lane, cur);
             }
+#ifdef PVS_TIMING
+            PVS_TACC(6, t_role);
+            if (warp == 6 && lane == 0 && rank == 0) for (int i = 5; i < 7; ++i) atomicAdd(&g_tc2_timing[i], (unsigned long long)timing_acc[i]);
+#endif
         }
     } else {
         const int quarter = warp & 3;
@@ -295,13 +334,21 @@ tc2_kernel(const __grid_constant__ typename P::Params prm)
                 if (lane == 0) mbar_arrive_leader(&tempty[a]);
             }
         }
+#ifdef PVS_TIMING
+        long long timing_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+        PVS_T0(t_role);
         for (int it = 0, t; (t = P::tile_at(prm, it, pair, n_pairs, n_tiles)) >= 0; ++it) {
             const typename P::Tile tl = P::tile(prm, t);
             P::epi_begin(prm, tl, st, rank, quarter, lane);
+            PVS_T0(t_tf);
             mbar_wait_cl(&tfull[acc], acc_phase);
+            PVS_TACC(3, t_tf);
             tcgen05_fence_after();
             const uint32_t tacc = tmem_base + (uint32_t)(acc * P::BLOCK_N) + ((uint32_t)(quarter * 32) << 16);
+            PVS_T0(t_body);
             P::epilogue(prm, tl, rank, tacc, quarter, lane, scratch, st);
+            PVS_TACC(7, t_body);
             if constexpr (P::ACC_INIT) {
                 P::acc_init(prm, tacc, lane, scratch);
                 tmem_st_wait();
@@ -311,6 +358,10 @@ tc2_kernel(const __grid_constant__ typename P::Params prm)
             if (lane == 0) mbar_arrive_leader(&tempty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+#ifdef PVS_TIMING
+        PVS_TACC(4, t_role);
+        if (warp == 2 && lane == 0 && rank == 0) { atomicAdd(&g_tc2_timing[3], (unsigned long long)timing_acc[3]); atomicAdd(&g_tc2_timing[4], (unsigned long long)timing_acc[4]); atomicAdd(&g_tc2_timing[7], (unsigned long long)timing_acc[7]); }
+#endif
     }
     tcgen05_fence_before();
     cluster_sync_all();                                     // nobody exits while the peer may still signal it
@@ -335,6 +386,19 @@ int launch_tc2(const typename P::Params& prm, int n_tiles, cudaStream_t st, int 
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PVS_ERR_CUDA, "tcgen05 pair kernel launch failed: %s", cudaGetErrorString(e));
+#ifdef PVS_TIMING
+    if (getenv("PVS_TIMING_PRINT")) {
+        cudaStreamSynchronize(st);
+        unsigned long long h[16], z[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        cudaMemcpyFromSymbol(h, g_tc2_timing, sizeof(h));
+        cudaMemcpyToSymbol(g_tc2_timing, z, sizeof(z));
+        const double np = pairs;
+        fprintf(stderr, "[tc2 timing %s] per pair (kcycles): mma total %.0f wait_full %.0f wait_tempty %.0f | epi total %.0f wait_tfull %.0f body %.0f | prod total %.0f wait_empty %.0f\n",
+                __PRETTY_FUNCTION__, h[2] / np / 1e3, h[0] / np / 1e3, h[1] / np / 1e3, h[4] / np / 1e3, h[3] / np / 1e3, h[7] / np / 1e3, h[6] / np / 1e3, h[5] / np / 1e3);
+        fprintf(stderr, "    phases (kcycles per pair): %.0f %.0f %.0f %.0f %.0f %.0f\n", h[8] / np / 1e3, h[9] / np / 1e3, h[10] / np / 1e3,
+                h[11] / np / 1e3, h[12] / np / 1e3, h[13] / np / 1e3);
+    }
+#endif
     return PVS_OK;
 }
 

@@ -168,7 +168,7 @@ struct StatsParams {
     const float* q;                           // [rows, 256]
     const int64_t* offsets;
     float* S;                                 // [n_images, 256, 128]: [k][ s1 (64) | s2 (64) ], already / T
-    float* s0part;                            // [n_images, 8, 256]: raw column sums of Q per producer warp
+    float* s0part;                            // [n_images, 16, 256]: raw column sums of Q per producer warp
     int64_t n_images;
 };
 
@@ -178,7 +178,7 @@ struct StatsPolicy {
     struct Tile { int nkb; int t; int64_t img, r0; };
     static constexpr bool BF16 = false, A_MN = true, B_MN = true, EPI_READS_STAGES = false, MANUAL = true;
     static constexpr int KT = ST_KT;
-    static constexpr int PASSES = 3, BLOCK_N = FV_K, STAGES = 4, KSTEPS = KT / 8, PGROUPS = 2;
+    static constexpr int PASSES = 3, BLOCK_N = FV_K, STAGES = 4, KSTEPS = KT / 8, PGROUPS = 4;
     static constexpr int A_LBO = KT * 128, B_LBO = KT * 128;          // one [KT rows x 128 B] block per 32 columns
     static constexpr int A_BYTES = (FV_2D / 32) * A_LBO, B_BYTES = (FV_K / 32) * B_LBO, SCRATCH_BYTES = 0;
     static constexpr int TMA_BYTES = 0;
@@ -219,6 +219,7 @@ struct StatsPolicy {
     // eight per-warp partials are added up by fv_finalize.  (Reading the Q tiles back from
     // shared memory for this cost more shared-memory bandwidth than the MMAs had left.)
     struct PState { float4 s0[2]; };
+    static_assert(PGROUPS * 4 == TC_FV_S0_PARTS, "one partial per producer warp");
     __device__ static void store(const Params& p, const Tile& t, int kb, const Regs& g, uint8_t* a_hi, uint8_t* a_lo,
                                  uint8_t* b_hi, uint8_t* b_lo, int pw, int grp, int lane, PState& ps)
     {
@@ -428,51 +429,74 @@ struct PostPairPolicy {
         const int64_t row = (int64_t)t.mb * 256 + rank * 128 + quarter * 32 + lane;
         const bool valid = row < p.rows;
         // The accumulator was pre-loaded with cst (acc_init), so the TMEM columns hold the
-        // complete logits.  pass 1: row maximum (arg-max only when the caller asked for it)
+        // complete logits.  Only one epilogue warp runs per scheduler, so every pass keeps the
+        // TMEM load of the next 32 columns in flight while it works on the current ones and
+        // splits its reductions over four independent chains.
+        // pass 1: row maximum (arg-max only when the caller asked for it)
+        float va[32], vb[32];
         float mx = -INFINITY;
         int mi = 0;
+        const bool tme = quarter == 0 && lane == 0 && rank == 0;
+        (void)tme;
+        PVS_T0(tp1);
         if (p.argmax) {
 #pragma unroll 1
             for (int c = 0; c < FV_K; c += 32) {
-                float v[32];
-                tmem_ld32(tmem + c, v);
+                tmem_ld32(tmem + c, va);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                    if (v[j] > mx) { mx = v[j]; mi = c + j; }     // strict >: lowest index on ties
+                    if (va[j] > mx) { mx = va[j]; mi = c + j; }   // strict >: lowest index on ties
             }
         } else {
+            float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            tmem_ld32(tmem, va);
 #pragma unroll 1
-            for (int c = 0; c < FV_K; c += 32) {
-                float v[32];
-                tmem_ld32(tmem + c, v);
+            for (int c = 0; c < FV_K; c += 64) {
                 tmem_ld_wait();
+                tmem_ld32(tmem + c + 32, vb);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) mx = fmaxf(mx, v[j]);
+                for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], va[j]);
+                tmem_ld_wait();
+                if (c + 64 < FV_K) tmem_ld32(tmem + c + 64, va);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], vb[j]);
             }
+            mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
         }
+        PVS_TPHASE(8, tp1, tme);
+        PVS_T0(tp2);
         const float base = (mx > -INFINITY && mx < INFINITY) ? mx : 0.f;
         // pass 2: e = exp(l - max) = 2^(l log2e - max log2e): one FFMA + one MUFU per logit;
         // e is stashed back into the accumulator columns
         constexpr float LOG2E = 1.4426950408889634f;
         const float nb = -base * LOG2E;
-        float sum = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < FV_K; c += 32) {
-            float v[32];
-            tmem_ld32(tmem + c, v);
-            tmem_ld_wait();
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+        auto exp_chunk = [&](float (&v)[32]) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 float e;
                 asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(v[j], LOG2E, nb)));
                 v[j] = e;
-                sum += e;
+                s4[j & 3] += e;
             }
-            tmem_st32(tmem + c, v);
+        };
+        tmem_ld32(tmem, va);
+#pragma unroll 1
+        for (int c = 0; c < FV_K; c += 64) {
+            tmem_ld_wait();
+            tmem_ld32(tmem + c + 32, vb);                      // (tcgen05.st reads its registers at issue)
+            exp_chunk(va);
+            tmem_st32(tmem + c, va);
+            tmem_ld_wait();
+            if (c + 64 < FV_K) tmem_ld32(tmem + c + 64, va);
+            exp_chunk(vb);
+            tmem_st32(tmem + c + 32, vb);
         }
         tmem_st_wait();
-        const float inv = 1.f / sum;
+        PVS_TPHASE(9, tp2, tme);
+        PVS_T0(tp3);
+        const float inv = 1.f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
         if (valid && p.argmax) p.argmax[row] = mi;
         // pass 3: q = e / sum.  A thread owns a row, so storing straight from registers would
         // scatter 16-byte pieces over 32 rows per instruction; each [32 rows x 32 cols] chunk
@@ -480,11 +504,7 @@ struct PostPairPolicy {
         // row segments (8 lanes per row, 4 rows per instruction).
         float* stg = reinterpret_cast<float*>(scratch + 1024) + quarter * 1024;
         const int64_t wrow0 = (int64_t)t.mb * 256 + rank * 128 + quarter * 32;
-#pragma unroll 1
-        for (int c = 0; c < FV_K; c += 32) {
-            float v[32];
-            tmem_ld32(tmem + c, v);
-            tmem_ld_wait();
+        auto store_chunk = [&](const float (&v)[32], int c) {
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4)
                 *reinterpret_cast<float4*>(stg + lane * 32 + ((j4 ^ (lane & 7)) << 2)) =
@@ -497,7 +517,18 @@ struct PostPairPolicy {
                 if (wrow0 + rr < p.rows) *reinterpret_cast<float4*>(p.q + (wrow0 + rr) * FV_K + c + cc * 4) = q4;
             }
             __syncwarp();
+        };
+        tmem_ld32(tmem, va);
+#pragma unroll 1
+        for (int c = 0; c < FV_K; c += 64) {
+            tmem_ld_wait();
+            tmem_ld32(tmem + c + 32, vb);
+            store_chunk(va, c);
+            tmem_ld_wait();
+            if (c + 64 < FV_K) tmem_ld32(tmem + c + 64, va);
+            store_chunk(vb, c + 32);
         }
+        PVS_TPHASE(10, tp3, tme);
     }
 };
 }  // namespace tc2
@@ -557,7 +588,7 @@ int tc_fv_plan(const pvs_model* g, const pvs_model* pca, int64_t rows, int64_t n
     pl->y = pca ? (float*)take((size_t)rows * FV_D * 4) : nullptr;
     pl->q = (float*)take((size_t)rows * FV_K * 4);
     pl->S = (float*)take((size_t)n_images * FV_K * FV_2D * 4);
-    pl->s0part = (float*)take((size_t)n_images * 8 * FV_K * 4);
+    pl->s0part = (float*)take((size_t)n_images * TC_FV_S0_PARTS * FV_K * 4);
     pl->total = off + 1024;
     return PVS_OK;
 }
@@ -600,7 +631,7 @@ int tc_fv_stats(const TcFvPlan& pl, const float* y, const int64_t* offsets, int6
     StatsParams p{};
     p.y = y; p.q = pl.q; p.offsets = offsets; p.S = pl.S; p.s0part = pl.s0part; p.n_images = n_images;
     // a producer group only writes its partial when it owned a k-block of the image
-    PVS_CUDA(cudaMemsetAsync(pl.s0part, 0, (size_t)n_images * 8 * FV_K * 4, st));
+    PVS_CUDA(cudaMemsetAsync(pl.s0part, 0, (size_t)n_images * TC_FV_S0_PARTS * FV_K * 4, st));
     return launch_tc<StatsPolicy>(p, (int)n_images, st);
 }
 

@@ -50,7 +50,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     tmp = LIB_PATH + ".tmp"
     objdir = os.path.join(os.path.dirname(LIB_PATH), "obj")
     os.makedirs(objdir, exist_ok=True)
-    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + os.environ.get("PVS_NVCC_EXTRA", "").split()   # e.g. -DPVS_TIMING
 
     def compile_one(src: str) -> str:
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")

@@ -79,8 +79,13 @@ class FisherVectorEncoder(ImageEncoderBase):
         return out.astype(self.output_dtype, copy=False)       # flatten=False has the same 2-D shape
 
     def encode_descriptors(self, descriptors, offsets=None, *, out=None, chunk_rows: int = 0,
-                           images_per_call: int = 512):
-        """Bulk entry, see :meth:`VLADEncoder.encode_descriptors`.  Returns float32."""
+                           images_per_call: int = 0):
+        """Bulk entry, see :meth:`VLADEncoder.encode_descriptors`.  Returns float32.
+
+        ``images_per_call`` (device-resident input): images per library call; 0 = four per SM,
+        which keeps the statistics kernel (one image per CTA at a time) evenly loaded."""
+        if images_per_call <= 0:
+            images_per_call = 4 * N.device_info()["sm_count"]
         cluster, pca = self._cluster_handle(), self._pca_handle()
         d_in = pca.d_in if pca else cluster.d
         x, offs, on_device = D.normalise_inputs(descriptors, offsets, d_in)
