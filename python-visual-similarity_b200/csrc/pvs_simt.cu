@@ -257,18 +257,21 @@ __device__ __forceinline__ void add_row(const float* __restrict__ row, int d, in
         for (int v = 0; v < VEC; ++v) acc[j][v] += x[j][v] - cv[j][v];
 }
 
+constexpr int VA_THREADS = 128;      // four warps: registers (up to ~100 with N * VEC = 18) still allow 5 CTAs per SM
 template <int VEC, int N, bool FAST>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(VA_THREADS)
 vlad_aggregate_kernel(const float* __restrict__ y, int d, const int32_t* __restrict__ labels,
                       const int64_t* __restrict__ offsets, const float* __restrict__ centers, int k,
                       int k_per_cta, int t_cap, float power, float ord, float eps, float* __restrict__ out)
 {
     extern __shared__ int sm_i[];
-    int* count = sm_i;                 // [k]   histogram, then fill cursor
-    int* start = sm_i + k;             // [k+1] exclusive scan
-    int* members = start + k + 1;      // [t_cap]
+    constexpr int NW = VA_THREADS / 32;
+    int* count = sm_i;                 // [k]     members per cluster
+    int* start = sm_i + k;             // [k+1]   exclusive scan
+    int* wcur = start + k + 1;         // [NW][k] per-warp histogram, then per-warp fill cursor
+    int* members = wcur + NW * k;      // [t_cap]
     const int64_t img = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = NW;
     const int64_t r0 = offsets[img];
     const int T = (int)(offsets[img + 1] - r0);
     const int kbeg = blockIdx.y * k_per_cta;
@@ -277,9 +280,21 @@ vlad_aggregate_kernel(const float* __restrict__ y, int d, const int32_t* __restr
     const bool sorted = T <= t_cap;
 
     if (sorted) {
-        for (int j = tid; j < k; j += blockDim.x) count[j] = 0;
+        // every warp owns a contiguous range of the image's descriptors; because the ranges
+        // are ordered and each warp places its own range in order, the member lists come
+        // out in descriptor order without any warp waiting for another
+        const int chunk = ((T + NW - 1) / NW + 31) & ~31;
+        const int tb = warp * chunk, te = min(T, tb + chunk);
+        for (int j = tid; j < NW * k; j += VA_THREADS) wcur[j] = 0;
         __syncthreads();
-        for (int t = tid; t < T; t += blockDim.x) atomicAdd(&count[lab[t]], 1);
+        for (int t = tb + lane; t < te; t += 32) atomicAdd(&wcur[warp * k + lab[t]], 1);
+        __syncthreads();
+        for (int j = tid; j < k; j += VA_THREADS) {
+            int tot = 0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) tot += wcur[w * k + j];
+            count[j] = tot;
+        }
         __syncthreads();
         if (warp == 0) {
             int carry = 0;
@@ -288,27 +303,33 @@ vlad_aggregate_kernel(const float* __restrict__ y, int d, const int32_t* __restr
                 int incl = v;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += u; }
-                if (base + lane < k) { start[base + lane] = carry + incl - v; count[base + lane] = 0; }
+                if (base + lane < k) start[base + lane] = carry + incl - v;
                 carry += __shfl_sync(FULL, incl, 31);
             }
             if (lane == 0) start[k] = carry;
+        }
+        __syncthreads();
+        for (int j = tid; j < k; j += VA_THREADS) {            // histogram -> first free slot per (warp, cluster)
+            int run = start[j];
+#pragma unroll
+            for (int w = 0; w < NW; ++w) { const int c = wcur[w * k + j]; wcur[w * k + j] = run; run += c; }
+        }
+        __syncthreads();
+        int* cur = wcur + warp * k;
+        for (int t0 = tb; t0 < te; t0 += 32) {                  // stable placement, 32 descriptors at a time
+            const int t = t0 + lane;
+            const bool valid = t < te;
+            const int l = valid ? lab[t] : -1 - lane;             // invalid lanes match nobody
+            const unsigned m = __match_any_sync(FULL, l);
+            const int rank = __popc(m & ((1u << lane) - 1u));
+            int base = 0;
+            if (valid) base = cur[l];
             __syncwarp();
-            // stable placement: descriptors in order, 32 at a time
-            for (int t0 = 0; t0 < T; t0 += 32) {
-                const int t = t0 + lane;
-                const bool valid = t < T;
-                const int l = valid ? lab[t] : -1 - lane;                 // invalid lanes match nobody
-                const unsigned m = __match_any_sync(FULL, l);
-                const int rank = __popc(m & ((1u << lane) - 1u));
-                int base = 0;
-                if (valid) base = count[l];
-                __syncwarp();
-                if (valid) {
-                    members[start[l] + base + rank] = t;
-                    if (rank == 0) count[l] = base + __popc(m);
-                }
-                __syncwarp();
+            if (valid) {
+                members[base + rank] = t;
+                if (rank == 0) cur[l] = base + __popc(m);
             }
+            __syncwarp();
         }
         __syncthreads();
     }
@@ -326,24 +347,34 @@ vlad_aggregate_kernel(const float* __restrict__ y, int d, const int32_t* __restr
         if (sorted) {
             const int s0 = start[c];
             n_members = start[c + 1] - s0;
-            int i = 0;
-            for (; i + 2 <= n_members; i += 2) {                          // two rows in flight, added in order
-                const float* ra = y + (r0 + members[s0 + i]) * (int64_t)d;
-                const float* rb = y + (r0 + members[s0 + i + 1]) * (int64_t)d;
-                float xa[N][VEC], xb[N][VEC];
+            // up to RIF member rows in flight per warp (more for short rows): one memory round
+            // trip per RIF members, and the rows are still added strictly in order
+            constexpr int RIF = N * VEC <= 4 ? 8 : N * VEC <= 8 ? 4 : 2;
+            for (int i = 0; i < n_members; i += RIF) {
+                float x[RIF][N][VEC];
 #pragma unroll
-                for (int j = 0; j < N; ++j) {
-                    const int e = (lane + 32 * j) * VEC;
+                for (int u = 0; u < RIF; ++u) {
+                    if (i + u < n_members) {                                 // warp-uniform
+                        const float* row = y + (r0 + members[s0 + i + u]) * (int64_t)d;
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v) { xa[j][v] = 0.f; xb[j][v] = 0.f; }
-                    if (e < d) { ld_vec<VEC>(ra + e, xa[j]); ld_vec<VEC>(rb + e, xb[j]); }
+                        for (int j = 0; j < N; ++j) {
+                            const int e = (lane + 32 * j) * VEC;
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) x[u][j][v] = 0.f;
+                            if (e < d) ld_vec<VEC>(row + e, x[u][j]);
+                        }
+                    }
                 }
 #pragma unroll
-                for (int j = 0; j < N; ++j)
+                for (int u = 0; u < RIF; ++u) {
+                    if (i + u < n_members) {
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v) { acc[j][v] += xa[j][v] - cv[j][v]; acc[j][v] += xb[j][v] - cv[j][v]; }
+                        for (int j = 0; j < N; ++j)
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) acc[j][v] += x[u][j][v] - cv[j][v];
+                    }
+                }
             }
-            if (i < n_members) add_row<VEC, N>(y + (r0 + members[s0 + i]) * (int64_t)d, d, lane, cv, acc);
         } else {
             n_members = 0;
             for (int t0 = 0; t0 < T; t0 += 32) {
@@ -385,7 +416,7 @@ vlad_aggregate_kernel(const float* __restrict__ y, int d, const int32_t* __restr
         if constexpr (FAST) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(FULL, nrm, o);
-            den = sqrtf(nrm) + eps;
+            den = 1.f / (sqrtf(nrm) + eps);                                // one reciprocal, then multiplies
         } else {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) nrm = norm_combine(nrm, __shfl_xor_sync(FULL, nrm, o), ord);
@@ -396,7 +427,7 @@ vlad_aggregate_kernel(const float* __restrict__ y, int d, const int32_t* __restr
             const int e = (lane + 32 * j) * VEC;
             float o[VEC];
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) o[v] = acc[j][v] / den;
+            for (int v = 0; v < VEC; ++v) o[v] = FAST ? acc[j][v] * den : acc[j][v] / den;
             if (e < d) st_vec<VEC>(orow + e, o);
         }
     }
@@ -409,10 +440,10 @@ int launch_vlad_agg(dim3 grid, size_t smem, cudaStream_t st, bool fast, const fl
 {
     if (fast) {
         if (smem > 48 * 1024) PVS_CUDA(cudaFuncSetAttribute(vlad_aggregate_kernel<VEC, N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PVS_LAUNCH((vlad_aggregate_kernel<VEC, N, true>), grid, 256, smem, st, y, d, labels, offsets, centers, k, k_per_cta, t_cap, power, ord, eps, out);
+        PVS_LAUNCH((vlad_aggregate_kernel<VEC, N, true>), grid, VA_THREADS, smem, st, y, d, labels, offsets, centers, k, k_per_cta, t_cap, power, ord, eps, out);
     } else {
         if (smem > 48 * 1024) PVS_CUDA(cudaFuncSetAttribute(vlad_aggregate_kernel<VEC, N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PVS_LAUNCH((vlad_aggregate_kernel<VEC, N, false>), grid, 256, smem, st, y, d, labels, offsets, centers, k, k_per_cta, t_cap, power, ord, eps, out);
+        PVS_LAUNCH((vlad_aggregate_kernel<VEC, N, false>), grid, VA_THREADS, smem, st, y, d, labels, offsets, centers, k, k_per_cta, t_cap, power, ord, eps, out);
     }
     return PVS_OK;
 }
@@ -426,8 +457,10 @@ int launch_vlad_aggregate(const float* y, int d, const int32_t* labels, const in
     PVS_CHECK(d <= 2048, PVS_ERR_UNSUPPORTED, "VLAD aggregation supports d <= 2048 (got %d)", d);
     PVS_CHECK(k <= 8192, PVS_ERR_UNSUPPORTED, "VLAD aggregation supports k <= 8192 (got %d)", k);
     // enough CTAs to fill the machine when there are few images (README quick start: 2)
+    // cluster ranges per image: enough CTAs (4 warps each) for ~32 warps per SM even when
+    // there are few images (README quick start: 2)
     int groups = 1;
-    while (groups < 32 && n_images * groups < 2 * 148 && (k / (groups * 2)) >= 8) groups *= 2;
+    while (groups < 32 && n_images * groups * (VA_THREADS / 32) < 148 * 32 && (k / (groups * 2)) >= 8) groups *= 2;
     const int k_per_cta = (int)ceil_div(k, groups);
     dim3 grid((unsigned)n_images, (unsigned)ceil_div(k, k_per_cta));
     // member-list capacity: a few times the mean image size, so ordinary images take the
@@ -435,7 +468,7 @@ int launch_vlad_aggregate(const float* y, int d, const int32_t* labels, const in
     int64_t avg = total_rows / n_images + 1;
     int t_cap = 1024;
     while (t_cap < 4 * avg && t_cap < 32768) t_cap <<= 1;
-    const size_t smem = ((size_t)2 * k + 1 + t_cap) * sizeof(int);
+    const size_t smem = ((size_t)(2 + VA_THREADS / 32) * k + 1 + t_cap) * sizeof(int);
     const bool fast = power == 1.f && norm_order == 2.f;
     const bool a16 = d % 4 == 0 && (((uintptr_t)y | (uintptr_t)centers | (uintptr_t)out) & 15) == 0;
     const bool a8 = d % 2 == 0 && (((uintptr_t)y | (uintptr_t)centers | (uintptr_t)out) & 7) == 0;

@@ -123,6 +123,50 @@ def test_vlad_vgg514_golden(api):
     assert rel_l2(out, g["out"]) <= 1e-4
 
 
+@pytest.mark.parametrize("k,d,images", [(256, 100, 3), (32, 33, 2), (200, 514, 2), (64, 64, 5), (100, 128, 3), (256, 6, 2)])
+def test_vlad_tensor_assignment_odd_shapes_vs_oracle(api, k, d, images):
+    """tcgen05 assignment (3xTF32) on shapes the named configs do not cover: d not a multiple of
+    32 / 4 / 2 (zero-padded k-blocks, 8- and 4-byte row alignment), k < 128 (the second CTA of
+    the pair holds only padding), k not a multiple of 128, ragged images incl. a 1-row one.
+    Labels vs the fp64 oracle (exact except near-ties), encodings vs the oracle, and the
+    tensor path against the CUDA-core path."""
+    rng = np.random.default_rng(k * 1000 + d)
+    centers = rng.standard_normal((k, d)).astype(np.float32)
+    descs = [(centers[rng.integers(0, k, t)] + 0.7 * rng.standard_normal((t, d))).astype(np.float32)
+             for t in ([1, 300, 77, 257, 513][:images])]
+    enc = vlad_encoder(api, centers, d)
+    api.nat.set_path(api.nat.PATH_TENSOR)
+    try:
+        out_tc, lab_tc = enc.encode_descriptors(descs, return_labels=True)
+    finally:
+        api.nat.set_path(api.nat.PATH_AUTO)
+    desc_all = np.vstack(descs)
+    assert_labels(lab_tc, O.kmeans_predict(desc_all, centers), desc_all, centers, max_near_ties=3)
+    assert rel_l2(out_tc, O.vlad_encode(descs, centers)) <= 1e-4
+    api.nat.set_path(api.nat.PATH_SIMT)
+    try:
+        out_cc, lab_cc = enc.encode_descriptors(descs, return_labels=True)
+    finally:
+        api.nat.set_path(api.nat.PATH_AUTO)
+    assert (lab_tc != lab_cc).sum() <= 3
+    if np.array_equal(lab_tc, lab_cc):
+        assert np.array_equal(out_tc, out_cc)      # same aggregation kernel, same order
+
+
+def test_vlad_long_image_takes_the_label_scan_path(api):
+    """An image with more descriptors than the shared-memory member list holds (here forced
+    by a batch whose mean T is small) must give the same block as the sorted path."""
+    rng = np.random.default_rng(5)
+    centers = rng.standard_normal((256, 64)).astype(np.float32)
+    big = (centers[rng.integers(0, 256, 9000)] + 0.5 * rng.standard_normal((9000, 64))).astype(np.float32)
+    small = [big[i * 10:(i + 1) * 10] for i in range(40)]
+    enc = vlad_encoder(api, centers, 64)
+    mixed = enc.encode_descriptors(small + [big])          # mean T ~ 230 -> t_cap 1024 < 9000
+    alone = enc.encode_descriptors([big])                  # t_cap 32768: sorted path
+    assert np.array_equal(mixed[-1], alone[0])
+    assert rel_l2(mixed, O.vlad_encode(small + [big], centers)) <= 1e-4
+
+
 def test_vlad_device_resident_equals_host_path(api):
     g = load_golden("vlad_vgg514")
     enc = vlad_encoder(api, g["centers"], 514)
