@@ -1,0 +1,77 @@
+"""Row-block sharded all-pairs cosine similarity + top-k across N GPUs (BASELINE.json configs[3]
+shape, scaled by --n).  One process per GPU:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port 29533 tools/bench_retrieval_mgpu.py --rows 65536 --dim 32768 --topk 100
+
+Every rank generates the same seeded VLAD-shaped bf16 database (replicated, SURVEY.md 8e
+variant i), scores its own block of query rows against it with the fused tensor-core kernel
+and the ranks all-gather the final (rows / N, k) score and index lists over NCCL -- the only
+collective on the path.  Timing: CUDA events around [top-k kernel + all-gather], barrier on
+both sides, max over ranks.  Rank 0 also checks a few gathered rows against a single-GPU
+pass over the same rows.
+"""
+import argparse, json, os, sys
+import torch, torch.distributed as dist
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "python-visual-similarity_b200"))
+from pyvisim_b200 import retrieval
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--rows", type=int, default=65536)
+ap.add_argument("--dim", type=int, default=32768)
+ap.add_argument("--topk", type=int, default=100)
+ap.add_argument("--reps", type=int, default=2)
+a = ap.parse_args()
+rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+g = torch.Generator(device=dev).manual_seed(0)                # same data on every rank
+x = torch.empty((a.rows, a.dim), dtype=torch.bfloat16, device=dev)
+for r in range(0, a.rows, 4096):
+    m = min(4096, a.rows - r)
+    v = torch.randn((m, a.dim // 128, 128), device=dev, generator=g)
+    v = v / v.norm(dim=2, keepdim=True)
+    v = v * (torch.rand((m, a.dim // 128, 1), device=dev, generator=g) > 0.15)
+    v = v.reshape(m, -1)
+    x[r:r + m] = (v / v.norm(dim=1, keepdim=True).clamp_min(1e-30)).bfloat16()
+lo, hi = retrieval.shard_bounds(a.rows, world, rank)
+
+
+def step():
+    s, i = retrieval.cosine_topk(x[lo:hi], x, a.topk)            # this rank's query rows vs the whole database
+    return retrieval.gather_topk(s, i, a.rows) if world > 1 else (s, i)
+
+
+def barrier():
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+s, i = step()
+barrier()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(a.reps):
+    s, i = step()
+e1.record()
+barrier()
+ms = e0.elapsed_time(e1) / a.reps
+if world > 1:
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+ok = None
+if rank == 0:
+    rows = torch.tensor([0, a.rows // 2, a.rows - 1], device=dev)
+    s1, i1 = retrieval.cosine_topk(x[rows], x, a.topk)
+    ok = bool(torch.equal(i1, i[rows]) and torch.equal(s1, s[rows]))
+    print(json.dumps({"n_gpus": world, "n": a.rows, "d": a.dim, "k": a.topk, "ms": ms, "tflops_total": 2.0 * a.rows * a.rows * a.dim / ms / 1e9,
+                      "queries_per_s": a.rows / ms * 1e3, "gathered_shape": list(s.shape),
+                      "gathered_rows_match_single_gpu_pass": ok, "scaling": "strong (fixed database, query rows split)"}))
+if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
