@@ -159,8 +159,12 @@ def run_extras(dev, pk):
     from pyvisim_b200.features import Descriptors
 
     def timed(fn, reps):
-        fn()
-        torch.cuda.synchronize()
+        # the GPU may have idled (CPU baseline just ran): warm up for ~0.3 s so the clocks are
+        # back up before anything is timed
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < 0.3:
+            fn()
+            torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):

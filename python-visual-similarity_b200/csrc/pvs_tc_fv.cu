@@ -151,7 +151,7 @@ struct PcaPolicy {
 // posterior: logits + softmax -> Q
 // ---------------------------------------------------------------------------------------
 struct PostParams {
-    CUtensorMap w_hi, w_lo;
+    CUtensorMap w_hi, w_lo, q_map;            // q_map: Q [rows, 256] fp32, box 32 cols x 32 rows (TMA store)
     const float* y;
     const float* cst;
     float* q;
@@ -372,8 +372,10 @@ struct PostPairPolicy {
     static constexpr bool BF16 = false, MANUAL = true, B_RESIDENT = true, ACC_INIT = true;
     static constexpr int PASSES = 3, BLOCK_N = FV_K, KSTEPS = 4, NKB_RES = FV_2D / 32, STAGES = 2, PGROUPS = 2;
     static constexpr int A_BYTES = 128 * 128, B_BYTES = (FV_K / 2) * 128, TMA_BYTES = 0;
-    static constexpr int SCRATCH_BYTES = 1024 + 4 * 4096;     // cst + one [32 x 32] fp32 staging tile per epilogue warp
-    __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.w_hi); tma_prefetch_desc(&p.w_lo); }
+    // scratch starts 256 B past a 1024-B boundary (barrier block): 768 B pad, then two 1024-aligned
+    // [32 x 32] fp32 TMA-store staging tiles per epilogue warp, then cst
+    static constexpr int STG_OFF = 768, CST_OFF = STG_OFF + 4 * 2 * 4096, SCRATCH_BYTES = CST_OFF + 1024;
+    __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.w_hi); tma_prefetch_desc(&p.w_lo); tma_prefetch_desc(&p.q_map); }
     __device__ static int num_tiles(const Params& p) { return p.m_blocks; }
     __device__ static int tile_at(const Params&, int it, int pair, int n_pairs, int n)
     {
@@ -402,7 +404,7 @@ struct PostPairPolicy {
     }
     __device__ static void epi_init(const Params& p, uint8_t* scratch, int tid)
     {
-        float* c = reinterpret_cast<float*>(scratch);
+        float* c = reinterpret_cast<float*>(scratch + CST_OFF);
         c[tid] = p.cst[tid];
         c[tid + 128] = p.cst[tid + 128];
         epi_barrier();
@@ -410,7 +412,7 @@ struct PostPairPolicy {
     // every lane (descriptor row) of an accumulator buffer starts from the per-component constant
     __device__ static void acc_init(const Params&, uint32_t tmem, int, uint8_t* scratch)
     {
-        const float4* cst4 = reinterpret_cast<const float4*>(scratch);
+        const float4* cst4 = reinterpret_cast<const float4*>(scratch + CST_OFF);
 #pragma unroll 1
         for (int c = 0; c < FV_K; c += 32) {
             float v[32];
@@ -499,35 +501,39 @@ struct PostPairPolicy {
         const float inv = 1.f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
         if (valid && p.argmax) p.argmax[row] = mi;
         // pass 3: q = e / sum.  A thread owns a row, so storing straight from registers would
-        // scatter 16-byte pieces over 32 rows per instruction; each [32 rows x 32 cols] chunk
-        // goes through a swizzled shared-memory tile instead and leaves as full 128-byte
-        // row segments (8 lanes per row, 4 rows per instruction).
-        float* stg = reinterpret_cast<float*>(scratch + 1024) + quarter * 1024;
-        const int64_t wrow0 = (int64_t)t.mb * 256 + rank * 128 + quarter * 32;
-        auto store_chunk = [&](const float (&v)[32], int c) {
+        // scatter 16-byte pieces over 32 rows per instruction.  Each [32 rows x 32 cols] chunk is
+        // written to a 128-byte-swizzled shared-memory tile instead and leaves through a TMA
+        // store (rows past the end of the batch are clipped by the tensor map); two tiles per
+        // warp, so the stores of one chunk overlap the TMA read of the previous one.
+        uint8_t* stg = scratch + STG_OFF + quarter * (2 * 4096);
+        const int wrow0 = (int)((int64_t)t.mb * 256 + rank * 128 + quarter * 32);
+        auto store_chunk = [&](const float (&v)[32], int c, int buf) {
+            if (lane == 0) tma_store_wait_read<1>();             // the group that last used this tile has read it
+            __syncwarp();
+            float* tile = reinterpret_cast<float*>(stg + buf * 4096);
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4)
-                *reinterpret_cast<float4*>(stg + lane * 32 + ((j4 ^ (lane & 7)) << 2)) =
+                *reinterpret_cast<float4*>(tile + lane * 32 + ((j4 ^ (lane & 7)) << 2)) =
                     make_float4(v[4 * j4] * inv, v[4 * j4 + 1] * inv, v[4 * j4 + 2] * inv, v[4 * j4 + 3] * inv);
+            fence_proxy_async();
             __syncwarp();
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                const int rr = it * 4 + (lane >> 3), cc = lane & 7;
-                const float4 q4 = *reinterpret_cast<const float4*>(stg + rr * 32 + ((cc ^ (rr & 7)) << 2));
-                if (wrow0 + rr < p.rows) *reinterpret_cast<float4*>(p.q + (wrow0 + rr) * FV_K + c + cc * 4) = q4;
+            if (lane == 0) {
+                tma_store_2d(&p.q_map, tile, c, wrow0);
+                tma_store_commit();
             }
-            __syncwarp();
         };
         tmem_ld32(tmem, va);
 #pragma unroll 1
         for (int c = 0; c < FV_K; c += 64) {
             tmem_ld_wait();
             tmem_ld32(tmem + c + 32, vb);
-            store_chunk(va, c);
+            store_chunk(va, c, 0);
             tmem_ld_wait();
             if (c + 64 < FV_K) tmem_ld32(tmem + c + 64, va);
-            store_chunk(vb, c + 32);
+            store_chunk(vb, c + 32, 1);
         }
+        if (lane == 0) tma_store_wait_read<0>();                 // tiles are free again (and valid until read)
+        __syncwarp();
         PVS_TPHASE(10, tp3, tme);
     }
 };
@@ -576,7 +582,7 @@ bool tc_fv_supported(const pvs_model* g, const pvs_model* pca, int64_t rows, int
 {
     if (!tc_available() || !g->tc0 || g->k != FV_K || g->d != FV_D) return false;
     if (pca && !pca->tc0) return false;
-    return rows / 128 + 2 < 2147483647LL && n_images < 2147483647LL;
+    return rows < 2147483000LL && n_images < 2147483647LL;      // TMA coordinates are 32-bit
 }
 
 int tc_fv_plan(const pvs_model* g, const pvs_model* pca, int64_t rows, int64_t n_images, void* ws, TcFvPlan* pl)
@@ -620,6 +626,7 @@ int tc_fv_posterior(const TcFvPlan& pl, const pvs_model* g, const float* y, int6
     int rc;
     if ((rc = make_tmap_2d(&p.w_hi, g->tc0, false, FV_K, FV_2D, FV_2D, 32, FV_K / 2))) return rc;
     if ((rc = make_tmap_2d(&p.w_lo, g->tc1, false, FV_K, FV_2D, FV_2D, 32, FV_K / 2))) return rc;
+    if ((rc = make_tmap_2d(&p.q_map, pl.q, false, rows, FV_K, FV_K, 32, 32))) return rc;
     p.y = y; p.cst = g->cst; p.q = pl.q; p.argmax = argmax; p.rows = rows;
     p.m_blocks = (int)ceil_div(rows, 256);                    // CTA pairs: 256-row tiles, W resident
     return tc2::launch_tc2<tc2::PostPairPolicy>(p, p.m_blocks, st);

@@ -172,6 +172,18 @@ class Model:
             pass
 
 
+_sm_count_cache: dict = {}
+
+
+def sm_count() -> int:
+    """SM count of the current device (cached: the property query costs ~1 ms)."""
+    import torch
+    dev = torch.cuda.current_device()
+    if dev not in _sm_count_cache:
+        _sm_count_cache[dev] = device_info()["sm_count"]
+    return _sm_count_cache[dev]
+
+
 def device_info() -> dict:
     sm, major, minor, mem = _i32(), _i32(), _i32(), _sz()
     check(lib().pvs_device_info(C.byref(sm), C.byref(major), C.byref(minor), C.byref(mem)))

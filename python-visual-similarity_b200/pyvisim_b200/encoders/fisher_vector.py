@@ -85,7 +85,7 @@ class FisherVectorEncoder(ImageEncoderBase):
         ``images_per_call`` (device-resident input): images per library call; 0 = four per SM,
         which keeps the statistics kernel (one image per CTA at a time) evenly loaded."""
         if images_per_call <= 0:
-            images_per_call = 4 * N.device_info()["sm_count"]
+            images_per_call = 4 * N.sm_count()
         cluster, pca = self._cluster_handle(), self._pca_handle()
         d_in = pca.d_in if pca else cluster.d
         x, offs, on_device = D.normalise_inputs(descriptors, offsets, d_in)
