@@ -57,6 +57,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
     }
 }
 
+// one lane of a converged warp; ptxas then knows the guarded region is single-threaded and
+// issues UTCHMMA / UTMALDG directly (a plain `lane == 0` test makes it wrap every such
+// instruction in an ELECT loop, ~20 extra instructions per MMA)
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m)
 {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -311,7 +321,7 @@ __global__ void __launch_bounds__(Layout<P>::THREADS, 1) tc_kernel(const __grid_
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // the whole warp walks the pipeline; one elected lane issues the MMAs and commits
             constexpr uint32_t idesc = make_idesc(P::BF16, P::A_MN, P::B_MN, 128, P::BLOCK_N);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
@@ -319,17 +329,18 @@ __global__ void __launch_bounds__(Layout<P>::THREADS, 1) tc_kernel(const __grid_
                 const typename P::Tile tl = P::tile(prm, t);
                 PVS1_T0(t_te);
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
-                PVS1_ADD(1, t_te, true);
+                PVS1_ADD(1, t_te, lane == 0);
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P::BLOCK_N);
                 for (int kb = 0; kb < tl.nkb; ++kb) {
                     PVS1_T0(t_fu);
                     mbar_wait(&full[stage], phase);
-                    PVS1_ADD(0, t_fu, true);
+                    PVS1_ADD(0, t_fu, lane == 0);
                     tcgen05_fence_after();
                     const uint32_t sp = smem_u32(smem + stage * L::STAGE_BYTES);
                     const uint32_t a_hi = sp, a_lo = sp + P::A_BYTES;
                     const uint32_t b_hi = sp + L::PARTS * P::A_BYTES, b_lo = b_hi + P::B_BYTES;
+                    if (elect_one()) {
 #pragma unroll
                     for (int ks = 0; ks < P::KSTEPS; ++ks) {
                         const uint32_t a_off = P::A_MN ? ks * 1024 : ks * 32;
@@ -352,9 +363,12 @@ __global__ void __launch_bounds__(Layout<P>::THREADS, 1) tc_kernel(const __grid_
                         }
                     }
                     umma_commit(&empty[stage]);          // smem slot free once these MMAs retire
+                    }
+                    __syncwarp();
                     if (++stage == P::STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull[acc]);                // accumulator complete
+                if (elect_one()) umma_commit(&tfull[acc]);    // accumulator complete
+                __syncwarp();
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }

@@ -215,7 +215,7 @@ tc2_kernel(const __grid_constant__ typename P::Params prm)
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
+        if (rank == 0) {   // the whole warp walks the pipeline; one elected lane issues the MMAs and commits
             constexpr uint32_t idesc = make_idesc(P::BF16, false, false, 256, P::BLOCK_N);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
@@ -242,6 +242,7 @@ tc2_kernel(const __grid_constant__ typename P::Params prm)
                     const uint32_t b_hi = P::B_RESIDENT ? smem_u32(res) + (uint32_t)(kb * L::PARTS * P::B_BYTES)
                                                         : sp + L::PARTS * P::A_BYTES;
                     const uint32_t b_lo = b_hi + P::B_BYTES;
+                    if (elect_one()) {
 #pragma unroll
                     for (int ks = 0; ks < P::KSTEPS; ++ks) {
                         const uint64_t da_hi = make_smem_desc(a_hi + ks * 32, 16, 1024, LAYOUT_SW128);
@@ -258,14 +259,17 @@ tc2_kernel(const __grid_constant__ typename P::Params prm)
                         }
                     }
                     umma2_commit(&empty[stage]);
+                    }
+                    __syncwarp();
                     if (++stage == P::STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma2_commit(&tfull[acc]);
+                if (elect_one()) umma2_commit(&tfull[acc]);
+                __syncwarp();
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
 #ifdef PVS_TIMING
             PVS_TACC(2, t_role);
-            for (int i = 0; i < 3; ++i) atomicAdd(&g_tc2_timing[i], (unsigned long long)timing_acc[i]);
+            if (lane == 0) for (int i = 0; i < 3; ++i) atomicAdd(&g_tc2_timing[i], (unsigned long long)timing_acc[i]);
 #endif
         }
     } else if (warp >= 6) {

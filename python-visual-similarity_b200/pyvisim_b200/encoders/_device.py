@@ -51,12 +51,16 @@ def check_offsets(offs: np.ndarray, rows: int) -> None:
 
 
 def run_device(encode_fn, ws_fn, cluster: N.Model, pca: Optional[N.Model], x, offs_host: np.ndarray,
-               out_dim: int, params, images_per_call: int, want_rows_i32: bool):
+               out_dim: int, params, images_per_call: int, want_rows_i32: bool, out=None):
     """Device-resident path: loop over image chunks so the workspace stays bounded."""
     import torch
     n_images = offs_host.size - 1
     dev = x.device
-    out = torch.empty((n_images, out_dim), dtype=torch.float32, device=dev)
+    if out is None:
+        out = torch.empty((n_images, out_dim), dtype=torch.float32, device=dev)
+    elif (not isinstance(out, torch.Tensor) or out.device != dev or out.dtype != torch.float32
+          or tuple(out.shape) != (n_images, out_dim) or not out.is_contiguous()):
+        raise ValueError(f"out must be a contiguous float32 tensor of shape {(n_images, out_dim)} on {dev}")
     rows_i32 = torch.empty((x.shape[0],), dtype=torch.int32, device=dev) if want_rows_i32 else None
     offs_dev = torch.as_tensor(offs_host, device=dev)
     stream = torch.cuda.current_stream(dev).cuda_stream

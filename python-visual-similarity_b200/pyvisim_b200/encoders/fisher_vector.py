@@ -95,7 +95,7 @@ class FisherVectorEncoder(ImageEncoderBase):
         params = (float(self.power_norm_weight), float(self.norm_order), float(self.epsilon))
         if on_device:
             res, _ = D.run_device(N.lib().pvs_fv_encode, N.lib().pvs_fv_workspace_bytes, cluster, pca, x, offs, dim,
-                                  params, images_per_call, False)
+                                  params, images_per_call, False, out=out)
             return res
         if out is None:
             out = np.empty((n, dim), dtype=np.float32)

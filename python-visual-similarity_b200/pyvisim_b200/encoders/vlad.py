@@ -88,7 +88,7 @@ class VLADEncoder(ImageEncoderBase):
         params = (float(self.power_norm_weight), float(self.norm_order), float(self.epsilon))
         if on_device:
             res, labels = D.run_device(N.lib().pvs_vlad_encode, N.lib().pvs_vlad_workspace_bytes, cluster, pca, x,
-                                       offs, dim, params, images_per_call, return_labels)
+                                       offs, dim, params, images_per_call, return_labels, out=out)
             return (res, labels) if return_labels else res
         if out is None:
             out = np.empty((n, dim), dtype=np.float32)
