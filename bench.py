@@ -310,9 +310,9 @@ def run_ours(args):
                        "tc_fv_stats": 2 * T * K * 2 * D}
     bytes_per_image = {"gmm_softmax": 2 * T * K * 4, "fv_finalize": K * (2 * D + 1) * 4 + out_dim * 4 * 3}
     # DRAM bytes per image of each kernel from the committed `ncu --set full` capture
-    # (profiles/ncu_fv_pair_r01.txt: dram read + write per launch of 512 images)
-    ncu_dram_bytes_per_image = {"tc_fv_project": (0.524403e9 + 230.873e6) / 512, "tc_fv_posterior": (0.262483e9 + 991.868e6) / 512,
-                                "tc_fv_stats": (1.310766e9 + 63.2998e6) / 512}
+    # (profiles/ncu_fv_r01b.txt: dram read + write per launch of 592 images)
+    ncu_dram_bytes_per_image = {"tc_fv_project": (0.606374e9 + 0.268744e9) / 592, "tc_fv_posterior": (0.303465e9 + 1.153728e9) / 592,
+                                "tc_fv_stats": (1.515914e9 + 0.070594e9) / 592}
     roofline = None
     if dominant[0]:
         name, (ms, n) = dominant

@@ -362,6 +362,7 @@ tc2_kernel(const __grid_constant__ typename P::Params prm)
             if (lane == 0) mbar_arrive_leader(&tempty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        tma_store_wait_read<0>();                            // TMA stores of the last tile have read their smem tiles
 #ifdef PVS_TIMING
         PVS_TACC(4, t_role);
         if (warp == 2 && lane == 0 && rank == 0) { atomicAdd(&g_tc2_timing[3], (unsigned long long)timing_acc[3]); atomicAdd(&g_tc2_timing[4], (unsigned long long)timing_acc[4]); atomicAdd(&g_tc2_timing[7], (unsigned long long)timing_acc[7]); }

@@ -79,7 +79,7 @@ __device__ __forceinline__ void store_kmajor_32rows(const KRegs& r, uint8_t* hi,
 // project: Y = X C^T + b
 // ---------------------------------------------------------------------------------------
 struct PcaParams {
-    CUtensorMap c_hi, c_lo;
+    CUtensorMap c_hi, c_lo, y_map;            // y_map: Y [rows, 64] fp32, box 32 cols x 32 rows (TMA store, pair kernel)
     const float* x;
     const float* bias;
     float* y;
@@ -309,8 +309,11 @@ struct PcaPairPolicy {
     struct Tile { int nkb, mb; };
     static constexpr bool BF16 = false, MANUAL = true, B_RESIDENT = true, ACC_INIT = false;
     static constexpr int PASSES = 3, BLOCK_N = FV_D, KSTEPS = 4, NKB_RES = 4, STAGES = 4, PGROUPS = 4;
-    static constexpr int A_BYTES = 128 * 128, B_BYTES = (FV_D / 2) * 128, SCRATCH_BYTES = 256, TMA_BYTES = 0;
-    __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.c_hi); tma_prefetch_desc(&p.c_lo); }
+    static constexpr int A_BYTES = 128 * 128, B_BYTES = (FV_D / 2) * 128, TMA_BYTES = 0;
+    // scratch starts 256 B past a 1024-B boundary: pad, two 1024-aligned [32 x 32] fp32 TMA-store tiles per
+    // epilogue warp (the two 32-column halves of its rows), then the bias
+    static constexpr int STG_OFF = 768, BIAS_OFF = STG_OFF + 4 * 2 * 4096, SCRATCH_BYTES = BIAS_OFF + 256;
+    __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.c_hi); tma_prefetch_desc(&p.c_lo); tma_prefetch_desc(&p.y_map); }
     __device__ static int num_tiles(const Params& p) { return p.m_blocks; }
     __device__ static int tile_at(const Params&, int it, int pair, int n_pairs, int n)
     {
@@ -337,7 +340,7 @@ struct PcaPairPolicy {
     }
     __device__ static void epi_init(const Params& p, uint8_t* scratch, int tid)
     {
-        float* b = reinterpret_cast<float*>(scratch);
+        float* b = reinterpret_cast<float*>(scratch + BIAS_OFF);
         if (tid < FV_D) b[tid] = p.bias[tid];
         epi_barrier();
     }
@@ -345,21 +348,32 @@ struct PcaPairPolicy {
     __device__ static void epilogue(const Params& p, const Tile& t, int rank, uint32_t tmem, int quarter, int lane,
                                     uint8_t* scratch, EpiState&)
     {
-        const float* bias = reinterpret_cast<const float*>(scratch);
-        const int64_t row = (int64_t)t.mb * 256 + rank * 128 + quarter * 32 + lane;
-        const bool valid = row < p.rows;
-        float4* o = reinterpret_cast<float4*>(p.y + row * FV_D);
+        const float* bias = reinterpret_cast<const float*>(scratch + BIAS_OFF);
+        const int wrow0 = (int)((int64_t)t.mb * 256 + rank * 128 + quarter * 32);
+        uint8_t* stg = scratch + STG_OFF + quarter * (2 * 4096);
+        // a thread owns a row; the [32 rows x 32 cols] halves go through 128-byte-swizzled shared
+        // tiles and leave as TMA stores (full 128-byte row segments, rows past the end clipped)
+        if (lane == 0) tma_store_wait_read<0>();                 // the previous tile's stores have read their tiles
+        __syncwarp();
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             float v[32];
             tmem_ld32(tmem + half * 32, v);
             tmem_ld_wait();
-            if (valid) {
+            float* tile = reinterpret_cast<float*>(stg + half * 4096);
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    o[(half * 32 + j) >> 2] = make_float4(v[j] + bias[half * 32 + j], v[j + 1] + bias[half * 32 + j + 1],
-                                                          v[j + 2] + bias[half * 32 + j + 2], v[j + 3] + bias[half * 32 + j + 3]);
+            for (int j4 = 0; j4 < 8; ++j4) {
+                const int j = half * 32 + 4 * j4;
+                *reinterpret_cast<float4*>(tile + lane * 32 + ((j4 ^ (lane & 7)) << 2)) =
+                    make_float4(v[4 * j4] + bias[j], v[4 * j4 + 1] + bias[j + 1], v[4 * j4 + 2] + bias[j + 2], v[4 * j4 + 3] + bias[j + 3]);
             }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            tma_store_2d(&p.y_map, stg, 0, wrow0);
+            tma_store_2d(&p.y_map, stg + 4096, 32, wrow0);
+            tma_store_commit();
         }
     }
 };
@@ -612,6 +626,7 @@ int tc_fv_project(const TcFvPlan& pl, const pvs_model* pca, const float* desc, i
     if (pca->d_in == 128) {                                   // CTA pairs, C resident (32 rows per CTA)
         if ((rc = make_tmap_2d(&p.c_hi, pca->tc0, false, pca->d, pca->d_in, pca->d_in, 32, FV_D / 2))) return rc;
         if ((rc = make_tmap_2d(&p.c_lo, pca->tc1, false, pca->d, pca->d_in, pca->d_in, 32, FV_D / 2))) return rc;
+        if ((rc = make_tmap_2d(&p.y_map, pl.y, false, rows, FV_D, FV_D, 32, 32))) return rc;
         p.m_blocks = (int)ceil_div(rows, 256);
         return tc2::launch_tc2<tc2::PcaPairPolicy>(p, p.m_blocks, st);
     }

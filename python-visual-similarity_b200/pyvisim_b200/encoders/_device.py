@@ -50,9 +50,24 @@ def check_offsets(offs: np.ndarray, rows: int) -> None:
         raise ValueError("offsets must be non-decreasing int64 with offsets[0] == 0 and offsets[-1] == rows")
 
 
+_side_streams: dict = {}
+
+
+def _streams_for(dev, n: int):
+    """Two (cached) side streams per device: consecutive image chunks alternate between them, so
+    the ramp-down of one chunk's kernels overlaps the ramp-up of the next chunk's."""
+    import torch
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), n)
+    if key not in _side_streams:
+        _side_streams[key] = [torch.cuda.Stream(dev) for _ in range(n)]
+    return _side_streams[key]
+
+
 def run_device(encode_fn, ws_fn, cluster: N.Model, pca: Optional[N.Model], x, offs_host: np.ndarray,
-               out_dim: int, params, images_per_call: int, want_rows_i32: bool, out=None):
-    """Device-resident path: loop over image chunks so the workspace stays bounded."""
+               out_dim: int, params, images_per_call: int, want_rows_i32: bool, out=None, n_streams: int = 2):
+    """Device-resident path: loop over image chunks so the workspace stays bounded.  Chunks are
+    independent; with more than one chunk they are issued round-robin on ``n_streams`` side
+    streams (one workspace each) that fork from and join back into the caller's stream."""
     import torch
     n_images = offs_host.size - 1
     dev = x.device
@@ -63,22 +78,31 @@ def run_device(encode_fn, ws_fn, cluster: N.Model, pca: Optional[N.Model], x, of
         raise ValueError(f"out must be a contiguous float32 tensor of shape {(n_images, out_dim)} on {dev}")
     rows_i32 = torch.empty((x.shape[0],), dtype=torch.int32, device=dev) if want_rows_i32 else None
     offs_dev = torch.as_tensor(offs_host, device=dev)
-    stream = torch.cuda.current_stream(dev).cuda_stream
-    lib = N.lib()
+    caller = torch.cuda.current_stream(dev)
+    n_chunks = (n_images + images_per_call - 1) // images_per_call
+    streams = [caller] if (n_chunks <= 1 or n_streams <= 1) else _streams_for(dev, n_streams)
+    for s in streams:
+        if s is not caller:
+            s.wait_stream(caller)                       # inputs / offsets / out are ready on the caller's stream
     pca_h = pca.handle if pca else None
-    ws = None
+    ws = [None] * len(streams)
     power, order, eps = params
     with torch.cuda.device(dev):
-        for i0 in range(0, n_images, images_per_call):
-            i1 = min(n_images, i0 + images_per_call)
-            r0, r1 = int(offs_host[i0]), int(offs_host[i1])
-            need = ws_fn(cluster.handle, pca_h, r1 - r0, i1 - i0)
-            if ws is None or ws.numel() < need:
-                ws = torch.empty((need,), dtype=torch.uint8, device=dev)
-            local = offs_dev[i0:i1 + 1] - r0 if i0 else offs_dev[:i1 + 1]
-            N.check(encode_fn(cluster.handle, pca_h, x[r0:r1].data_ptr() if r1 > r0 else x.data_ptr(),
-                              local.data_ptr(), i1 - i0, r1 - r0, power, order, eps, out[i0:i1].data_ptr(),
-                              rows_i32[r0:].data_ptr() if (rows_i32 is not None and r1 > r0) else None,
-                              ws.data_ptr(), ws.numel(), stream))
-            del local
+        for c, i0 in enumerate(range(0, n_images, images_per_call)):
+            si = c % len(streams)
+            with torch.cuda.stream(streams[si]):
+                i1 = min(n_images, i0 + images_per_call)
+                r0, r1 = int(offs_host[i0]), int(offs_host[i1])
+                need = ws_fn(cluster.handle, pca_h, r1 - r0, i1 - i0)
+                if ws[si] is None or ws[si].numel() < need:
+                    ws[si] = torch.empty((need,), dtype=torch.uint8, device=dev)
+                local = offs_dev[i0:i1 + 1] - r0 if i0 else offs_dev[:i1 + 1]
+                N.check(encode_fn(cluster.handle, pca_h, x[r0:r1].data_ptr() if r1 > r0 else x.data_ptr(),
+                                  local.data_ptr(), i1 - i0, r1 - r0, power, order, eps, out[i0:i1].data_ptr(),
+                                  rows_i32[r0:].data_ptr() if (rows_i32 is not None and r1 > r0) else None,
+                                  ws[si].data_ptr(), ws[si].numel(), streams[si].cuda_stream))
+                del local
+    for s in streams:
+        if s is not caller:
+            caller.wait_stream(s)
     return out, rows_i32
