@@ -251,14 +251,15 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step():
-        return enc.encode_descriptors(x, offsets, images_per_call=args.images_per_call)
+    res = torch.empty((n_img, out_dim), dtype=torch.float32, device=dev)      # caller-owned output
+
+    def step(n_streams=2):
+        return enc.encode_descriptors(x, offsets, images_per_call=args.images_per_call, out=res, n_streams=n_streams)
 
     for _ in range(args.warmup):
         out = step()
     barrier()
     N.lib().pvs_launch_count_reset()
-    N.profile_enable(not args.no_profile)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
         barrier()
@@ -269,8 +270,21 @@ def run_ours(args):
         barrier()
     total_ms = ev0.elapsed_time(ev1)
     launches = int(N.lib().pvs_launch_count())
-    stages = N.profile_read()
-    N.profile_enable(False)
+    # per-kernel durations: the timed steps alternate image chunks between two streams, so kernels
+    # of neighbouring chunks overlap there; the stage times (and the roofline entry computed from
+    # them) come from extra steps issued on ONE stream, CUDA events around every launch
+    stages = {}
+    prof_steps = 0
+    if not args.no_profile:
+        prof_steps = max(1, min(args.steps, 2))
+        step(n_streams=1)
+        barrier()
+        N.profile_enable(True)
+        for _ in range(prof_steps):
+            step(n_streams=1)
+        barrier()
+        stages = N.profile_read()
+        N.profile_enable(False)
     if world > 1:
         t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -317,7 +331,7 @@ def run_ours(args):
     if dominant[0]:
         name, (ms, n) = dominant
         per_launch_ms = ms / n
-        imgs_per_launch = n_img * args.steps / n
+        imgs_per_launch = n_img * prof_steps / n
         if name in flops_per_image:
             ach = flops_per_image[name] * imgs_per_launch / (per_launch_ms / 1e3) / 1e12
             peak = pk["bf16_tflops_sustained"]
@@ -333,7 +347,8 @@ def run_ours(args):
             roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                         "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": f"hbm copy, {pk['source']}"}
         roofline["kernel_ms_per_launch"] = per_launch_ms
-        roofline["kernel_share_of_step"] = ms / total_ms
+        roofline["kernel_share_of_step"] = ms / sum(v[0] for v in stages.values())
+        roofline["timing"] = f"{prof_steps} extra single-stream step(s), CUDA events around each launch"
     # whole-path HBM roofline (algorithmic bytes per image: descriptors in + encoding out)
     alg_bytes = T * d_in * 4 + out_dim * 4
     path_gbs = alg_bytes * n_img / (ms_per_step / 1e3) / 1e9
@@ -362,7 +377,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "images_per_gpu": n_img, "descriptors_per_image": T, "d_in": d_in,
                        "k": K, "d": D, "weights": "bundled gmm_k256_sift_pca + pca_k256_sift_f2",
-                       "l2": "inputs (8.4 GB/GPU) larger than L2, no flush", "parallelism": f"dp{world} (images sharded, no collective)",
+                       "l2": "inputs (8.4 GB/GPU) larger than L2, no flush", "parallelism": f"dp{world} (images sharded, no collective)", "streams": "image chunks alternate between 2 CUDA streams per GPU",
                        "images_per_call": args.images_per_call or "4 per SM (592)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(e_rows * d_in * 4 + (e2e_images + 1) * 8),
                     "d2h_bytes_per_step": int(e2e_images * out_dim * 4), "images": e2e_images,
@@ -371,7 +386,7 @@ def run_ours(args):
             "roofline": roofline,
             "path_hbm": {"algorithmic_bytes_per_image": alg_bytes, "achieved_gbs": path_gbs,
                          "frac_of_hbm_peak": path_gbs / pk["hbm_gbs"]},
-            "stages_ms": {k: round(v[0] / args.steps, 4) for k, v in stages.items()},
+            "stages_ms": {k: round(v[0] / max(prof_steps, 1), 4) for k, v in stages.items()},
             "cpu_baseline": cpu,
             "extra": extra,
             "clocks": clocks.summary(),

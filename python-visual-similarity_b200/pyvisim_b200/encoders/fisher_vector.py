@@ -79,11 +79,13 @@ class FisherVectorEncoder(ImageEncoderBase):
         return out.astype(self.output_dtype, copy=False)       # flatten=False has the same 2-D shape
 
     def encode_descriptors(self, descriptors, offsets=None, *, out=None, chunk_rows: int = 0,
-                           images_per_call: int = 0):
+                           images_per_call: int = 0, n_streams: int = 2):
         """Bulk entry, see :meth:`VLADEncoder.encode_descriptors`.  Returns float32.
 
         ``images_per_call`` (device-resident input): images per library call; 0 = four per SM,
-        which keeps the statistics kernel (one image per CTA at a time) evenly loaded."""
+        which keeps the statistics kernel (one image per CTA at a time) evenly loaded.
+        ``n_streams``: consecutive chunks alternate between this many side streams (see
+        ``_device.run_device``); 1 = everything on the caller's stream."""
         if images_per_call <= 0:
             images_per_call = 4 * N.sm_count()
         cluster, pca = self._cluster_handle(), self._pca_handle()
@@ -95,7 +97,7 @@ class FisherVectorEncoder(ImageEncoderBase):
         params = (float(self.power_norm_weight), float(self.norm_order), float(self.epsilon))
         if on_device:
             res, _ = D.run_device(N.lib().pvs_fv_encode, N.lib().pvs_fv_workspace_bytes, cluster, pca, x, offs, dim,
-                                  params, images_per_call, False, out=out)
+                                  params, images_per_call, False, out=out, n_streams=n_streams)
             return res
         if out is None:
             out = np.empty((n, dim), dtype=np.float32)

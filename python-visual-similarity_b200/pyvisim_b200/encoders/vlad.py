@@ -71,7 +71,7 @@ class VLADEncoder(ImageEncoderBase):
         return out if self.flatten else out.reshape(len(descs) * k, d)
 
     def encode_descriptors(self, descriptors, offsets=None, *, return_labels: bool = False, out=None,
-                           chunk_rows: int = 0, images_per_call: int = 4096):
+                           chunk_rows: int = 0, images_per_call: int = 4096, n_streams: int = 2):
         """Bulk entry: descriptors of many images at once.
 
         ``descriptors``: list of ``(T_i, D_in)`` arrays, or a packed ``(sum T, D_in)`` NumPy
@@ -88,7 +88,7 @@ class VLADEncoder(ImageEncoderBase):
         params = (float(self.power_norm_weight), float(self.norm_order), float(self.epsilon))
         if on_device:
             res, labels = D.run_device(N.lib().pvs_vlad_encode, N.lib().pvs_vlad_workspace_bytes, cluster, pca, x,
-                                       offs, dim, params, images_per_call, return_labels, out=out)
+                                       offs, dim, params, images_per_call, return_labels, out=out, n_streams=n_streams)
             return (res, labels) if return_labels else res
         if out is None:
             out = np.empty((n, dim), dtype=np.float32)
