@@ -194,6 +194,44 @@ def run_extras(dev, pk):
         out[name] = {"images_per_s": n / ms * 1e3, "images": n, "descriptors_per_image": T, "d": D, "k": 256,
                      "frac_of_hbm_peak": alg * n / ms / 1e6 / pk["hbm_gbs"], "weights": "random-init K-Means (no file bundled)"}
         del x, enc, res
+    # BASELINE.json configs[0]: README quick start, similarity_score of two images (~2k RootSIFT-128
+    # descriptors each) through the drop-in API with host arrays; wall-clock latency per call
+    rng = np.random.default_rng(0)
+
+    def rootsift_like(t):
+        a = np.abs(rng.standard_normal((t, 128))).astype(np.float32)
+        a /= a.sum(axis=1, keepdims=True) + 1e-7
+        return np.sqrt(a)
+
+    d1, d2 = rootsift_like(2000), rootsift_like(1900)
+    cen = np.vstack([d1, d2])[rng.choice(3900, 256, replace=False)]
+    enc = VLADEncoder(feature_extractor=Descriptors(128), kmeans_model=kmeans_from_centers(cen))
+    for _ in range(5):
+        score = enc.similarity_score([d1], [d2])
+    lat = []
+    for _ in range(30):
+        t0 = time.perf_counter()
+        score = enc.similarity_score([d1], [d2])
+        lat.append(time.perf_counter() - t0)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pvs_oracle as O
+    t0 = time.perf_counter()
+    ref = O.similarity_score(O.vlad_encode([d1], cen), O.vlad_encode([d2], cen))
+    cpu_s = time.perf_counter() - t0
+    _, lab = enc.encode_descriptors([d1, d2], return_labels=True)
+    xs = np.vstack([d1, d2])
+    gold = O.kmeans_predict(xs, cen)
+    bad = np.flatnonzero(lab != gold)
+    gaps = []
+    if bad.size:
+        sc = O.kmeans_scores(xs[bad], cen)
+        gaps = (np.abs(sc[np.arange(bad.size), lab[bad]] - sc[np.arange(bad.size), gold[bad]]) / np.abs(sc).max(axis=1)).tolist()
+    out["quickstart_vlad_similarity_score"] = {"latency_ms_median": 1e3 * float(np.median(lat)), "latency_ms_min": 1e3 * float(np.min(lat)),
+                                               "cpu_oracle_ms": 1e3 * cpu_s, "score": float(np.asarray(score).ravel()[0]),
+                                               "abs_diff_vs_oracle": float(abs(np.asarray(score).ravel()[0] - np.asarray(ref).ravel()[0])),
+                                               "label_flips_vs_fp32_oracle": int(bad.size), "rel_score_gap_of_flips": gaps,
+                                               "descriptors": [2000, 1900]}
+    del enc
     n, d, k = 16384, 32768, 100
     v = torch.empty((n, d), dtype=torch.bfloat16, device=dev)
     for r in range(0, n, 4096):                           # VLAD-shaped rows: 256 unit blocks of 128, ~15 % empty

@@ -481,10 +481,11 @@ extern "C" int pvs_cosine_matrix(const float* x, int64_t n, const float* y, int6
     if (n == 0 || m == 0) return PVS_OK;
     PVS_CHECK(x && y && s, PVS_ERR_BAD_ARG, "pvs_cosine_matrix: NULL buffer");
     PVS_CHECK(d < 2147483647LL && m < 2147483647LL, PVS_ERR_BAD_SHAPE, "pvs_cosine_matrix: dimension too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n * m <= 1024) return launch_cosine_small(x, n, y, m, d, s, st);     // e.g. similarity_score of two images
     const size_t need = pvs_cosine_matrix_workspace_bytes(n, m, d);
     PVS_CHECK(workspace && workspace_bytes >= need, PVS_ERR_WORKSPACE, "pvs_cosine_matrix: workspace %zu < %zu",
               workspace_bytes, need);
-    cudaStream_t st = (cudaStream_t)stream;
     char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     float* xn = (float*)ws;
     float* yn = (float*)(ws + align_up((size_t)n * d * 4, 256));

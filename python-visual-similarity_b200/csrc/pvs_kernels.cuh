@@ -35,6 +35,8 @@ int launch_fv_finalize(const float* S, int ld, const float* s0part, int parts, c
 // ---- similarity / top-k --------------------------------------------------------------------
 int launch_l2_normalize(const float* x, int64_t n, int64_t d, void* out, int out_dtype, cudaStream_t st);
 int launch_bf16_to_f32(const void* x, int64_t n, float* out, cudaStream_t st);
+// s[n, m] = cosine of raw rows, for small n * m (one CTA per pair, no workspace)
+int launch_cosine_small(const float* x, int64_t n, const float* y, int64_t m, int64_t d, float* s, cudaStream_t st);
 // per-row top-k of a dense score block S [rows, n_db] (row stride lds)
 int launch_topk_rows(const float* S, int64_t lds, int64_t rows, int64_t n_db, int k, int64_t idx_offset,
                      float* scores_out, int64_t* idx_out, cudaStream_t st);

@@ -739,6 +739,49 @@ __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ x, int64_t 
 }
 }  // namespace
 
+namespace {
+// Small outputs (similarity_score of a few images): one CTA per (i, j) pair streams both rows
+// once and reduces dot, |x|^2, |y|^2 together -- the tiled contraction above would put the
+// whole K = d reduction of a 1 x 1 output on a single CTA.  Zero rows give 0, as sklearn's
+// normalize leaves them zero.
+__global__ void __launch_bounds__(256)
+cosine_small_kernel(const float* __restrict__ x, const float* __restrict__ y, int m, int64_t d, float* __restrict__ s)
+{
+    __shared__ float red[3][8];
+    const int i = blockIdx.x / m, j = blockIdx.x - i * m;
+    const float* px = x + (int64_t)i * d;
+    const float* py = y + (int64_t)j * d;
+    float dot = 0.f, xx = 0.f, yy = 0.f;
+    for (int64_t t = threadIdx.x; t < d; t += blockDim.x) {
+        const float a = px[t], b = py[t];
+        dot = fmaf(a, b, dot);
+        xx = fmaf(a, a, xx);
+        yy = fmaf(b, b, yy);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        dot += __shfl_xor_sync(FULL, dot, o);
+        xx += __shfl_xor_sync(FULL, xx, o);
+        yy += __shfl_xor_sync(FULL, yy, o);
+    }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = dot; red[1][threadIdx.x >> 5] = xx; red[2][threadIdx.x >> 5] = yy; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, b = 0.f, c = 0.f;
+        for (int w = 0; w < 8; ++w) { a += red[0][w]; b += red[1][w]; c += red[2][w]; }
+        const float nx = sqrtf(b), ny = sqrtf(c);
+        s[blockIdx.x] = (nx == 0.f || ny == 0.f) ? 0.f : (a / nx) / ny;
+    }
+}
+}  // namespace
+
+int launch_cosine_small(const float* x, int64_t n, const float* y, int64_t m, int64_t d, float* s, cudaStream_t st)
+{
+    if (n <= 0 || m <= 0) return PVS_OK;
+    PVS_LAUNCH(cosine_small_kernel, (unsigned)(n * m), 256, 0, st, x, y, (int)m, d, s);
+    return PVS_OK;
+}
+
 int launch_l2_normalize(const float* x, int64_t n, int64_t d, void* out, int out_dtype, cudaStream_t st)
 {
     if (n <= 0) return PVS_OK;
