@@ -45,7 +45,8 @@ typedef enum pvs_status {
     PVS_ERR_BAD_SHAPE = -2,   /* dimension mismatch between model / pca / descriptors  */
     PVS_ERR_CUDA = -3,        /* CUDA runtime error (message has the cudaError string) */
     PVS_ERR_WORKSPACE = -4,   /* workspace too small                                   */
-    PVS_ERR_UNSUPPORTED = -5  /* e.g. norm_order <= 0                                  */
+    PVS_ERR_UNSUPPORTED = -5, /* e.g. norm_order <= 0                                  */
+    PVS_ERR_NCCL = -6         /* NCCL error (message has ncclGetErrorString)           */
 } pvs_status;
 
 typedef enum pvs_model_kind { PVS_MODEL_KMEANS = 1, PVS_MODEL_GMM_DIAG = 2, PVS_MODEL_PCA = 3 } pvs_model_kind;
@@ -59,6 +60,7 @@ typedef enum pvs_path {
 } pvs_path;
 
 typedef struct pvs_model pvs_model; /* opaque; device-resident, immutable after create */
+typedef struct pvs_comm pvs_comm;   /* opaque; one NCCL communicator of this process          */
 
 /* ---- library ------------------------------------------------------------------------ */
 int pvs_version(void);
@@ -150,6 +152,24 @@ int pvs_cosine_topk(const void* q_dev, const void* db_dev, int dtype, int64_t n_
  * [n_q, k] list with the same ordering rule -- used when the DATABASE is sharded. */
 int pvs_topk_merge(const float* scores_dev, const int64_t* idx_dev, int parts, int64_t n_q, int k,
                    float* scores_out_dev, int64_t* idx_out_dev, void* stream);
+
+/* ---- C1: the one collective of the path -----------------------------------
+ * Row-block sharded retrieval: rank r scores query rows shard(r) against the database, so its
+ * top-k lists (eval.py:40-43 per query) are final for those rows; the lists of all ranks are
+ * assembled with an NCCL all-gather.  NCCL is loaded at run time (the copy already in the
+ * process, e.g. PyTorch's, is preferred; pvs_nccl_load(path) names another one).
+ *   pvs_comm_unique_id : rank 0 creates the 128-byte id and ships it to the other ranks by
+ *                        any means (torch.distributed broadcast in the Python wrapper)
+ *   pvs_comm_create    : ncclCommInitRank on the current device (collective call)
+ *   pvs_allgather_topk : scores fp32 / indices int64 [rows_per_rank, k] of every rank ->
+ *                        [world * rows_per_rank, k] on every rank, rank-major, on `stream`;
+ *                        rows_per_rank is the same on all ranks (the caller pads). */
+int pvs_nccl_load(const char* library_path);
+int pvs_comm_unique_id(void* id_out_128);
+int pvs_comm_create(const void* id_128, int world, int rank, pvs_comm** out);
+int pvs_comm_destroy(pvs_comm* comm);
+int pvs_allgather_topk(pvs_comm* comm, const float* scores_dev, const int64_t* idx_dev, int64_t rows_per_rank,
+                       int k, float* scores_all_dev, int64_t* idx_all_dev, void* stream);
 
 /* ---- f1: label logic on top-k lists  (eval.py:82-98, 126-145) ------------------------- */
 /* hits_out[q] = any(db_labels[idx[q, :k]] == query_labels[q]);  ap_out[q] = average precision

@@ -65,7 +65,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     from concurrent.futures import ThreadPoolExecutor
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
         objs = list(pool.map(compile_one, sources()))
-    cmd = [nvcc, "-shared", "-Xcompiler", "-fPIC", "-o", tmp, *objs]
+    cmd = [nvcc, "-shared", "-Xcompiler", "-fPIC", "-o", tmp, *objs, "-ldl"]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError(f"nvcc link failed ({proc.returncode}):\n{proc.stdout}\n{proc.stderr}")

@@ -68,6 +68,11 @@ EXPORTS = {
     "pvs_cosine_topk": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _i32, _i64, _vp, _vp, _vp, _sz, _vp]),
     "pvs_topk_merge": (_i32, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp]),
     "pvs_topk_label_metrics": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "pvs_nccl_load": (_i32, [C.c_char_p]),
+    "pvs_comm_unique_id": (_i32, [_vp]),
+    "pvs_comm_create": (_i32, [_vp, _i32, _i32, _pp]),
+    "pvs_comm_destroy": (_i32, [_vp]),
+    "pvs_allgather_topk": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "pvs_vlad_encode_host": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _vp, _vp, _i64]),
     "pvs_fv_encode_host": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _vp, _i64]),
     "pvs_cosine_matrix_host": (_i32, [_vp, _i64, _vp, _i64, _i64, _vp]),

@@ -20,7 +20,60 @@ import numpy as np
 from . import _native as N
 
 __all__ = ["l2_normalize", "cosine_topk", "all_pairs_topk", "shard_bounds", "merge_topk",
-           "gather_topk", "label_metrics"]
+           "gather_topk", "label_metrics", "NativeComm"]
+
+
+class NativeComm:
+    """NCCL communicator owned by ``libpvs_b200`` (``pvs_comm_*`` / ``pvs_allgather_topk``).
+
+    Created collectively by all ranks of an initialised ``torch.distributed`` group: rank 0
+    makes the 128-byte NCCL unique id, the group broadcasts it, every rank calls
+    ``ncclCommInitRank`` on its current CUDA device.  ``gather_topk(..., comm=NativeComm())``
+    then runs the all-gather of the top-k lists through the C ABI instead of
+    ``torch.distributed``."""
+
+    def __init__(self, group=None):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("torch.distributed must be initialised to exchange the NCCL id")
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        lib = N.lib()
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            buf = (C.c_ubyte * 128)()
+            N.check(lib.pvs_comm_unique_id(C.addressof(buf)))
+            uid = torch.tensor(list(buf), dtype=torch.uint8)
+        on_cuda = dist.get_backend(group) == "nccl"
+        t = uid.cuda() if on_cuda else uid
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        raw = bytes(t.cpu().tolist())
+        self._handle = C.c_void_p()
+        N.check(lib.pvs_comm_create(raw, self.world, self.rank, C.byref(self._handle)))
+
+    def allgather_topk(self, scores, idx):
+        """[rows, k] fp32 / int64 CUDA tensors (same rows on every rank) -> [world*rows, k]."""
+        import torch
+        rows, k = scores.shape
+        s_all = torch.empty((self.world * rows, k), dtype=torch.float32, device=scores.device)
+        i_all = torch.empty((self.world * rows, k), dtype=torch.int64, device=scores.device)
+        with torch.cuda.device(scores.device):
+            N.check(N.lib().pvs_allgather_topk(self._handle, scores.contiguous().data_ptr(), idx.contiguous().data_ptr(),
+                                               rows, k, s_all.data_ptr(), i_all.data_ptr(),
+                                               torch.cuda.current_stream(scores.device).cuda_stream))
+        return s_all, i_all
+
+    def close(self):
+        if getattr(self, "_handle", None):
+            N.lib().pvs_comm_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def shard_bounds(n: int, world: int, rank: int) -> tuple[int, int]:
@@ -82,9 +135,10 @@ def merge_topk(scores, idx, k: int):
     return so, io
 
 
-def gather_topk(scores, idx, n_total: int, group=None):
+def gather_topk(scores, idx, n_total: int, group=None, comm: "Optional[NativeComm]" = None):
     """All-gather the per-rank ``(rows_r, k)`` lists into ``(n_total, k)`` on every rank.
-    Works on CUDA (NCCL) and CPU (gloo) tensors; row counts may differ by one between ranks."""
+    Works on CUDA (NCCL) and CPU (gloo) tensors; row counts may differ by one between ranks.
+    With ``comm`` (a :class:`NativeComm`) the exchange goes through ``pvs_allgather_topk``."""
     import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
@@ -101,10 +155,13 @@ def gather_topk(scores, idx, n_total: int, group=None):
         p[: t.shape[0]] = t
         return p
 
-    s_all = torch.empty((world * pad, k), dtype=scores.dtype, device=scores.device)
-    i_all = torch.empty((world * pad, k), dtype=idx.dtype, device=idx.device)
-    dist.all_gather_into_tensor(s_all, padded(scores), group=group)
-    dist.all_gather_into_tensor(i_all, padded(idx), group=group)
+    if comm is not None:
+        s_all, i_all = comm.allgather_topk(padded(scores), padded(idx))
+    else:
+        s_all = torch.empty((world * pad, k), dtype=scores.dtype, device=scores.device)
+        i_all = torch.empty((world * pad, k), dtype=idx.dtype, device=idx.device)
+        dist.all_gather_into_tensor(s_all, padded(scores), group=group)
+        dist.all_gather_into_tensor(i_all, padded(idx), group=group)
     if all(hi - lo == pad for lo, hi in sizes):
         return s_all, i_all
     keep = torch.cat([torch.arange(r * pad, r * pad + (hi - lo)) for r, (lo, hi) in enumerate(sizes)]).to(scores.device)

@@ -163,3 +163,12 @@ def test_gather_topk_world_size_2_gloo(tmp_path):
     outs = [p.communicate(timeout=180)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all("ok" in o for o in outs)
+
+
+def test_allgather_topk_argument_checks_without_a_communicator():
+    """C1 export: a NULL communicator is a bad argument (no NCCL, no device needed)."""
+    from pyvisim_b200 import _native as N
+    lib = N.lib()
+    rc = lib.pvs_allgather_topk(None, None, None, 4, 3, None, None, None)
+    assert rc == -1 and b"communicator" in lib.pvs_last_error()
+    assert lib.pvs_comm_destroy(None) == 0

@@ -22,6 +22,7 @@ ap.add_argument("--rows", type=int, default=65536)
 ap.add_argument("--dim", type=int, default=32768)
 ap.add_argument("--topk", type=int, default=100)
 ap.add_argument("--reps", type=int, default=2)
+ap.add_argument("--native-comm", action="store_true", help="all-gather through pvs_allgather_topk (library-owned NCCL communicator)")
 a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -38,11 +39,12 @@ for r in range(0, a.rows, 4096):
     v = v.reshape(m, -1)
     x[r:r + m] = (v / v.norm(dim=1, keepdim=True).clamp_min(1e-30)).bfloat16()
 lo, hi = retrieval.shard_bounds(a.rows, world, rank)
+comm = retrieval.NativeComm() if (a.native_comm and world > 1) else None
 
 
 def step():
     s, i = retrieval.cosine_topk(x[lo:hi], x, a.topk)            # this rank's query rows vs the whole database
-    return retrieval.gather_topk(s, i, a.rows) if world > 1 else (s, i)
+    return retrieval.gather_topk(s, i, a.rows, comm=comm) if world > 1 else (s, i)
 
 
 def barrier():
@@ -71,7 +73,7 @@ if rank == 0:
     ok = bool(torch.equal(i1, i[rows]) and torch.equal(s1, s[rows]))
     print(json.dumps({"n_gpus": world, "n": a.rows, "d": a.dim, "k": a.topk, "ms": ms, "tflops_total": 2.0 * a.rows * a.rows * a.dim / ms / 1e9,
                       "queries_per_s": a.rows / ms * 1e3, "gathered_shape": list(s.shape),
-                      "gathered_rows_match_single_gpu_pass": ok, "scaling": "strong (fixed database, query rows split)"}))
+                      "gathered_rows_match_single_gpu_pass": ok, "collective": "pvs_allgather_topk" if comm else "torch.distributed all_gather_into_tensor", "scaling": "strong (fixed database, query rows split)"}))
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()
