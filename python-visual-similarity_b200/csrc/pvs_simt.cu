@@ -612,26 +612,42 @@ fv_finalize_kernel(const float* __restrict__ S, int ld, const float* __restrict_
     }
     __syncthreads();
     float den = 0.f;
+    // element e = j * d + dd.  When d divides the block size a thread keeps dd fixed and only
+    // steps j, so the index needs no division (d = 64 / 128 in every bundled model);
+    // otherwise e is strided and split with one integer division.
+    const bool fixed_dd = (nt % d) == 0;
+    const int dd_f = tid % d, j_f = tid / d, j_step = nt / d;
+    const int n_it = fixed_dd ? (k - j_f + j_step - 1) / j_step : (kd - tid + nt - 1) / nt;
+    auto fast_root = [](float x) {                       // sign(x) sqrt|x| without the IEEE sqrt sequence
+        const float a = fabsf(x);
+        return a > 0.f ? copysignf(a * rsqrtf(a), x) : x;  // keeps +-0 and propagates NaN
+    };
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
         float part = 0.f;
-        for (int e0 = tid; e0 < kd; e0 += 4 * nt) {
+        const float inv_den = pass ? 1.f / den : 0.f;
+        for (int it0 = 0; it0 < n_it; it0 += 4) {
             float s1[4], s2[4], m[4], v[4], gm[4], gs[4], s0[4];
+            int ee[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int e = e0 + u * nt;
-                if (e < kd) {
-                    const int j = e / d, dd = e - j * d;
-                    s1[u] = Simg[(int64_t)j * ld + dd];
-                    s2[u] = Simg[(int64_t)j * ld + d + dd];
-                    m[u] = mu[e]; v[u] = var[e]; gm[u] = g_mu[e]; gs[u] = g_sig[e];
+                const int it = it0 + u;
+                int j, dd;
+                if (fixed_dd) { j = j_f + it * j_step; dd = dd_f; }
+                else { const int e = tid + it * nt; j = e / d; dd = e - j * d; }
+                ee[u] = it < n_it ? j * d + dd : -1;
+                if (ee[u] >= 0) {
+                    const float* Sj = Simg + (unsigned)(j * ld);
+                    s1[u] = Sj[dd];
+                    s2[u] = Sj[d + dd];
+                    m[u] = mu[ee[u]]; v[u] = var[ee[u]]; gm[u] = g_mu[ee[u]]; gs[u] = g_sig[ee[u]];
                     s0[u] = s0s[j];
                 }
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int e = e0 + u * nt;
-                if (e < kd) {
+                const int e = ee[u];
+                if (e >= 0) {
                     const float dm = (s1[u] - s0[u] * m[u]) * gm[u];
                     const float ds = (-s2[u] - s0[u] * m[u] * m[u] + s0[u] * v[u] + 2.f * s1[u] * m[u]) * gs[u];
                     if (pass == 0) {
@@ -641,8 +657,8 @@ fv_finalize_kernel(const float* __restrict__ S, int ld, const float* __restrict_
                             part = norm_combine(part, norm_term(signed_pow(ds, power), ord), ord);
                         }
                     } else if (FAST) {
-                        o[k + e] = copysignf(sqrtf(fabsf(dm)), dm) / den;
-                        o[k + kd + e] = copysignf(sqrtf(fabsf(ds)), ds) / den;
+                        o[k + e] = fast_root(dm) * inv_den;
+                        o[k + kd + e] = fast_root(ds) * inv_den;
                     } else {
                         o[k + e] = signed_pow(dm, power) / den;
                         o[k + kd + e] = signed_pow(ds, power) / den;
@@ -653,7 +669,7 @@ fv_finalize_kernel(const float* __restrict__ S, int ld, const float* __restrict_
         for (int j = tid; j < k; j += nt) {
             const float dp = (s0s[j] - pi[j]) * g_pi[j];
             if (pass == 0) part = FAST ? part + fabsf(dp) : norm_combine(part, norm_term(signed_pow(dp, power), ord), ord);
-            else o[j] = (FAST ? copysignf(sqrtf(fabsf(dp)), dp) : signed_pow(dp, power)) / den;
+            else o[j] = FAST ? fast_root(dp) * inv_den : signed_pow(dp, power) / den;
         }
         if (pass == 0) {
 #pragma unroll
