@@ -267,6 +267,9 @@ struct Layout {
     static_assert(!(P::BF16 && (P::A_MN || P::B_MN)), "MN-major operands are implemented for tf32 only");
     static_assert(P::A_BYTES % 1024 == 0 && P::B_BYTES % 1024 == 0, "operand tiles must keep 1024-B alignment");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
+    // every stage must be refilled by one producer group only: a group that ran two uses ahead of
+    // another one on the same stage would pass the parity wait of the empty barrier too early
+    static_assert(!P::MANUAL || P::STAGES % P::PGROUPS == 0, "PGROUPS must divide STAGES");
 };
 
 template <class P>
@@ -392,7 +395,8 @@ __global__ void __launch_bounds__(Layout<P>::THREADS, 1) tc_kernel(const __grid_
                         if (t >= 0) tl = P::tile(prm, t);
                         continue;
                     }
-                    if ((int)(idx % P::PGROUPS) == grp) return;
+                    if ((int)(idx % P::PGROUPS) == grp) return;   // a stage is always refilled by the same group
+                                                                  // (PGROUPS divides STAGES): parity waits stay unambiguous
                     ++kb; ++idx;
                 }
             };

@@ -147,7 +147,9 @@ struct Layout2 {
     static_assert(P::BLOCK_N % 16 == 0 && P::BLOCK_N <= 256, "pair MMA needs N % 16 == 0, N <= 256");
     static_assert(P::A_BYTES % 1024 == 0 && P::B_BYTES % 1024 == 0, "operand tiles must keep 1024-B alignment");
     static_assert(P::STAGES + 8 <= 30, "barrier block too small");
-    static_assert(!P::MANUAL || (P::PGROUPS >= 1 && P::PGROUPS <= P::STAGES), "one stage per producer group at least");
+    // every stage must be refilled by one producer group only: a group that ran two uses ahead of
+    // another one on the same stage would pass the parity wait of the empty barrier too early
+    static_assert(!P::MANUAL || (P::PGROUPS >= 1 && P::STAGES % P::PGROUPS == 0), "PGROUPS must divide STAGES");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
 };
 

@@ -255,7 +255,10 @@ struct StatsPolicy {
             *reinterpret_cast<float4*>(a_lo + 2 * A_LBO + off) = l;
         }
         if (kb + PGROUPS >= t.nkb) {                       // this group's last k-block of the image
-            float4* dst = reinterpret_cast<float4*>(p.s0part + ((t.img * (PGROUPS * 4) + grp * 4 + pw) * FV_K));
+            // slot by the k-block's position in the image, not by the group: which rows meet in a
+            // partial sum then does not depend on the tiles this CTA handled before (same bits for
+            // any chunking of the batch)
+            float4* dst = reinterpret_cast<float4*>(p.s0part + ((t.img * (PGROUPS * 4) + (kb % PGROUPS) * 4 + pw) * FV_K));
             dst[lane] = ps.s0[0];
             dst[lane + 32] = ps.s0[1];
             ps.s0[0] = ps.s0[1] = make_float4(0.f, 0.f, 0.f, 0.f);
