@@ -203,8 +203,10 @@ tc2_kernel(const __grid_constant__ typename P::Params prm)
             if constexpr (P::TMA_BYTES > 0) {
                 int stage = 0;
                 uint32_t phase = 0;
-                for (int it = 0, t; (t = P::tile_at(prm, it, pair, n_pairs, n_tiles)) >= 0; ++it) {
+                int it = 0;
+                for (int t; (t = P::tile_at(prm, it, pair, n_pairs, n_tiles)) >= 0; ++it) {
                     const typename P::Tile tl = P::tile(prm, t);
+                    if constexpr (P::TILE_SYNC) P::tile_sync(prm, it, rank, n_pairs);   // keep the pairs in step (L2 reuse)
                     for (int kb = 0; kb < tl.nkb; ++kb) {
                         mbar_wait_cl(&empty[stage], phase ^ 1);
                         if (rank == 0) mbar_expect_tx(&full[stage], 2u * (uint32_t)P::TMA_BYTES);
@@ -214,6 +216,7 @@ tc2_kernel(const __grid_constant__ typename P::Params prm)
                         if (++stage == P::STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
+                if constexpr (P::TILE_SYNC) P::tile_sync_done(prm, it, rank);
             }
         }
     } else if (warp == 1) {

@@ -310,7 +310,7 @@ struct PcaPairPolicy {
     using Params = PcaParams;
     using EpiState = NoEpiState;
     struct Tile { int nkb, mb; };
-    static constexpr bool BF16 = false, MANUAL = true, B_RESIDENT = true, ACC_INIT = false;
+    static constexpr bool BF16 = false, MANUAL = true, B_RESIDENT = true, ACC_INIT = false, TILE_SYNC = false;
     static constexpr int PASSES = 3, BLOCK_N = FV_D, KSTEPS = 4, NKB_RES = 4, STAGES = 4, PGROUPS = 4;
     static constexpr int A_BYTES = 128 * 128, B_BYTES = (FV_D / 2) * 128, TMA_BYTES = 0;
     // scratch starts 256 B past a 1024-B boundary: pad, two 1024-aligned [32 x 32] fp32 TMA-store tiles per
@@ -386,7 +386,7 @@ struct PostPairPolicy {
     using Params = PostParams;
     using EpiState = NoEpiState;
     struct Tile { int nkb, mb; };
-    static constexpr bool BF16 = false, MANUAL = true, B_RESIDENT = true, ACC_INIT = true;
+    static constexpr bool BF16 = false, MANUAL = true, B_RESIDENT = true, ACC_INIT = true, TILE_SYNC = false;
     static constexpr int PASSES = 3, BLOCK_N = FV_K, KSTEPS = 4, NKB_RES = FV_2D / 32, STAGES = 2, PGROUPS = 2;
     static constexpr int A_BYTES = 128 * 128, B_BYTES = (FV_K / 2) * 128, TMA_BYTES = 0;
     // scratch starts 256 B past a 1024-B boundary (barrier block): 768 B pad, then two 1024-aligned

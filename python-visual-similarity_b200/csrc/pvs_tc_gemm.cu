@@ -152,7 +152,7 @@ struct GemmPair {
     using Params = GemmParams;
     using EpiState = NoState;
     struct Tile { int nkb, mb, nb; };
-    static constexpr bool BF16 = BF16_, MANUAL = false, B_RESIDENT = RES_, ACC_INIT = false;
+    static constexpr bool BF16 = BF16_, MANUAL = false, B_RESIDENT = RES_, ACC_INIT = false, TILE_SYNC = false;
     static constexpr int PASSES = PASSES_, BLOCK_N = BLOCK_N_, KSTEPS = 4, NKB_RES = 4, PGROUPS = 1;
     static constexpr int BK = BF16 ? 64 : 32;
     static constexpr int A_BYTES = 128 * 128, B_BYTES = (BLOCK_N / 2) * 128, SCRATCH_BYTES = 0;

@@ -38,6 +38,8 @@ struct SimParams {
     int64_t* part_idx;             // [stripes, n_q, k]
     int64_t n_q, n_db, idx_offset;
     int k, cap, nkb, q_blocks, db_blocks, stripes, tiles_per_unit, n_units;
+    unsigned* sync_ctr;            // zeroed before launch: arrivals of the pairs' tile steps (drift limiter)
+    int sync_steps;                // tile steps of the busiest pair
 };
 
 __device__ __forceinline__ unsigned long long sim_key(float s, unsigned idx)
@@ -81,7 +83,7 @@ struct SimPolicy {
     using Params = SimParams;
     using EpiState = SimState;
     struct Tile { int nkb, qb, dbb, stripe; bool first, last; };
-    static constexpr bool BF16 = true, MANUAL = false, B_RESIDENT = false, ACC_INIT = false;
+    static constexpr bool BF16 = true, MANUAL = false, B_RESIDENT = false, ACC_INIT = false, TILE_SYNC = true;
     static constexpr int CAP = CAP_, PASSES = 1, BLOCK_N = 256, KSTEPS = 4, NKB_RES = 0, PGROUPS = 1;
     static constexpr int A_BYTES = 128 * 128, B_BYTES = 128 * 128, TMA_BYTES = A_BYTES + B_BYTES;
     static constexpr int SCRATCH_BYTES = CAP <= 512 ? 0 : 4 * CAP * 8;
@@ -112,6 +114,30 @@ struct SimPolicy {
     {
         tma_load_2d_pair(a, &p.q_map, bar, kb * 64, t.qb * 256 + rank * 128);
         tma_load_2d_pair(b, &p.db_map, bar, kb * 64, t.dbb * 256 + rank * 128);
+    }
+    // Drift limiter.  The pairs that run at the same time share query / database blocks through
+    // L2 only while they walk the feature dimension of the same tile step together; nothing else
+    // keeps them together over units of 100+ tiles, and a pair that falls behind finds its
+    // operands evicted.  The leader's TMA thread therefore starts tile step s only after every
+    // pair has reached step s (one atomic + a short spin per ~200 us tile).  All CTAs of the
+    // grid are co-resident (grid <= SM count), so the spin cannot deadlock; it is a performance
+    // hint only and times out harmlessly.
+    __device__ static void tile_sync(const Params& p, int it, int rank, int n_pairs)
+    {
+        if (rank != 0 || !p.sync_ctr) return;
+        atomicAdd(p.sync_ctr, 1u);
+        const unsigned want = (unsigned)n_pairs * (unsigned)(it + 1);
+        const long long t0 = clock64();
+        while (*(volatile unsigned*)p.sync_ctr < want) {
+            __nanosleep(200);
+            if (clock64() - t0 > 4000000LL) break;             // ~2 ms: give up on stragglers, never hang
+        }
+    }
+    // a pair with fewer tile steps than the busiest one donates its missing arrivals on exit
+    __device__ static void tile_sync_done(const Params& p, int steps_done, int rank)
+    {
+        if (rank != 0 || !p.sync_ctr) return;
+        if (steps_done < p.sync_steps) atomicAdd(p.sync_ctr, (unsigned)(p.sync_steps - steps_done));
     }
     __device__ static void epi_init(const Params&, uint8_t*, int) {}
     __device__ static void epi_begin(const Params&, const Tile& t, EpiState& st, int, int, int)
@@ -257,7 +283,7 @@ struct SimPolicy {
 
 using namespace tc2;
 
-struct SimPlan { int q_blocks, db_blocks, stripes, tiles_per_unit, n_units, pairs, cap; size_t bufs, ps, pi, total; };
+struct SimPlan { int q_blocks, db_blocks, stripes, tiles_per_unit, n_units, pairs, cap; size_t bufs, ps, pi, ctr, total; };
 
 static int sim_cap(int k)
 {
@@ -293,6 +319,7 @@ static SimPlan sim_plan(int64_t n_q, int64_t n_db, int k)
     pl.bufs = off; off += align_up((size_t)pl.pairs * 2 * 128 * pl.cap * 8, 1024);
     pl.ps = off;   off += align_up((size_t)pl.stripes * n_q * k * 4, 1024);
     pl.pi = off;   off += align_up((size_t)pl.stripes * n_q * k * 8, 1024);
+    pl.ctr = off;  off += 1024;
     pl.total = off + 1024;
     return pl;
 }
@@ -325,6 +352,9 @@ int tc_sim_topk(const void* q, const void* db, int64_t n_q, int64_t n_db, int64_
     p.q_blocks = pl.q_blocks; p.db_blocks = pl.db_blocks; p.stripes = pl.stripes;
     p.tiles_per_unit = pl.tiles_per_unit; p.n_units = pl.n_units;
     const int n_tiles = pl.n_units * pl.tiles_per_unit;
+    p.sync_ctr = getenv("PVS_SIM_NOSYNC") ? nullptr : (unsigned*)(base + pl.ctr);
+    p.sync_steps = (int)ceil_div(pl.n_units, pl.pairs) * pl.tiles_per_unit;
+    PVS_CUDA(cudaMemsetAsync(base + pl.ctr, 0, 1024, st));
     switch (pl.cap) {
         case 512: rc = launch_tc2<SimPolicy<512>>(p, n_tiles, st, pl.pairs); break;
         case 1024: rc = launch_tc2<SimPolicy<1024>>(p, n_tiles, st, pl.pairs); break;

@@ -85,7 +85,7 @@ struct AssignPolicy {
     using Params = AssignParams;
     using EpiState = AssignState;
     struct Tile { int nkb, mb; };
-    static constexpr bool BF16 = false, MANUAL = true, B_RESIDENT = RES_, ACC_INIT = false;
+    static constexpr bool BF16 = false, MANUAL = true, B_RESIDENT = RES_, ACC_INIT = false, TILE_SYNC = false;
     static constexpr int PASSES = 3, BLOCK_N = 256, KSTEPS = 4, NKB_RES = NKB_, STAGES = 3, PGROUPS = 3;
     static constexpr int A_BYTES = 128 * 128, B_BYTES = 128 * 128, SCRATCH_BYTES = 1024;
     static constexpr int TMA_BYTES = RES_ ? 0 : 2 * B_BYTES;
