@@ -126,11 +126,16 @@ struct SimPolicy {
     {
         if (rank != 0 || !p.sync_ctr) return;
         atomicAdd(p.sync_ctr, 1u);
+        volatile unsigned* ctr = p.sync_ctr;
+        if (ctr[1]) return;                                    // a pair timed out before: run unsynchronised
         const unsigned want = (unsigned)n_pairs * (unsigned)(it + 1);
         const long long t0 = clock64();
-        while (*(volatile unsigned*)p.sync_ctr < want) {
+        while (ctr[0] < want) {
             __nanosleep(200);
-            if (clock64() - t0 > 4000000LL) break;             // ~2 ms: give up on stragglers, never hang
+            if (clock64() - t0 > 4000000LL) {                  // ~2 ms: not all pairs are resident (another kernel
+                ctr[1] = 1u;                                   // holds SMs); never hang, and stop waiting for good
+                break;
+            }
         }
     }
     // a pair with fewer tile steps than the busiest one donates its missing arrivals on exit
