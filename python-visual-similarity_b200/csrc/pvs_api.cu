@@ -1,6 +1,7 @@
 // pvs_api.cu -- the C ABI declared in include/pvs_b200.h: model handles, stage
 // orchestration on caller-provided device buffers, and the host-buffer entry points.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <mutex>
 
@@ -44,11 +45,11 @@ constexpr int64_t ASSIGN_CHUNK_ROWS = 1 << 18;
 // ---- optional per-stage device timing (CUDA events on the launching stream) -------------
 enum Stage { ST_PCA = 0, ST_KM_SCORES, ST_KM_ARGMIN, ST_VLAD_AGG, ST_GMM_LOGITS, ST_GMM_SOFTMAX, ST_FV_STATS,
              ST_FV_FINALIZE, ST_L2NORM, ST_SIM_GEMM, ST_TOPK_SELECT, ST_TC_VLAD_ASSIGN, ST_TC_FV_POSTERIOR,
-             ST_TC_FV_STATS, ST_TC_SIM_TOPK, ST_TC_FV_PREP, ST_TC_FV_PROJECT, ST_COUNT };
+             ST_TC_FV_STATS, ST_TC_SIM_TOPK, ST_TC_FV_PREP, ST_TC_FV_PROJECT, ST_TC_GEMM_PCA, ST_TC_GEMM_LOGITS, ST_COUNT };
 static const char* kStageNames[ST_COUNT] = {
     "pca_project", "kmeans_scores", "kmeans_argmin", "vlad_aggregate", "gmm_logits", "gmm_softmax", "fv_stats",
     "fv_finalize", "l2_normalize", "sim_gemm", "topk_select", "tc_vlad_assign", "tc_fv_posterior", "tc_fv_stats",
-    "tc_sim_topk", "tc_fv_prep", "tc_fv_project"};
+    "tc_sim_topk", "tc_fv_prep", "tc_fv_project", "tc_gemm_pca", "tc_gemm_logits"};
 struct StageRec { int stage; cudaEvent_t a, b; };
 static std::mutex g_prof_mu;
 static std::atomic<int> g_prof_on{0};
@@ -220,6 +221,7 @@ extern "C" int pvs_gmm_create(const double* w, const double* mu, const double* c
     m->g_mu = m->g_pi + k;
     m->g_sig = m->g_mu + kd;
     if (int s = tc_prepare_model(m)) { pvs_model_destroy(m); return s; }
+    if (int s = tc_prepare_generic(m)) { pvs_model_destroy(m); return s; }
     *out = m;
     return PVS_OK;
 }
@@ -242,6 +244,7 @@ extern "C" int pvs_pca_create(const float* comp, const float* mean, int d_out, i
     m->comp = (const float*)m->block;
     m->bias = m->comp + (size_t)d_out * d_in;
     if (int s = tc_prepare_model(m)) { pvs_model_destroy(m); return s; }
+    if (int s = tc_prepare_generic(m)) { pvs_model_destroy(m); return s; }
     *out = m;
     return PVS_OK;
 }
@@ -251,6 +254,7 @@ extern "C" int pvs_model_destroy(pvs_model* m)
     if (!m) return PVS_OK;
     if (m->block) cudaFree(m->block);
     if (m->tc0) cudaFree((void*)m->tc0);
+    if (m->tcg0) cudaFree((void*)m->tcg0);
     delete m;
     return PVS_OK;
 }
@@ -283,6 +287,14 @@ extern "C" int pvs_pca_project(const pvs_model* pca, const float* x, int64_t row
 {
     PVS_CHECK(pca && pca->kind == PVS_MODEL_PCA, PVS_ERR_BAD_ARG, "pvs_pca_project: not a PCA model");
     PVS_CHECK(rows >= 0 && (rows == 0 || (x && y)), PVS_ERR_BAD_ARG, "pvs_pca_project: bad buffers");
+    // The tensor core truncates when it accumulates (error grows linearly with the number of MMA
+    // steps); for the 514-long VGG16 projection that alone costs 5.6e-5 of the 1e-4 parity budget
+    // of the Fisher vector (measured on the golden case), so long contractions stay on the
+    // round-to-nearest CUDA-core kernel.
+    if (g_path.load() != PVS_PATH_SIMT && pca->tcg0 && pca->d_in <= 256 && tc_gemm_nt_supported(rows, pca->d))
+        return PVS_STAGE(ST_TC_GEMM_PCA, (cudaStream_t)stream,
+                         tc_gemm_nt(x, pca->d_in, pca->d_in, false, pca->tcg0, pca->tcg1, pca->tcg_ld, pca->d, y, pca->d, rows,
+                                    1.f, pca->bias, (cudaStream_t)stream));
     return PVS_STAGE(ST_PCA, (cudaStream_t)stream,
                      launch_gemm_nt(x, pca->d_in, pca->comp, pca->d_in, y, pca->d, rows, pca->d, pca->d_in, 0, 1.f,
                                     pca->bias, (cudaStream_t)stream));
@@ -319,7 +331,10 @@ extern "C" int pvs_gmm_posterior(const pvs_model* g, const float* y, int64_t row
     PVS_CHECK(g && g->kind == PVS_MODEL_GMM_DIAG, PVS_ERR_BAD_ARG, "pvs_gmm_posterior: not a GMM model");
     PVS_CHECK(rows >= 0 && (rows == 0 || (y && q)), PVS_ERR_BAD_ARG, "pvs_gmm_posterior: bad buffers");
     cudaStream_t st = (cudaStream_t)stream;
-    if (int rc = PVS_STAGE(ST_GMM_LOGITS, st, launch_gemm_nt(y, g->d, g->wcat, 2 * g->d, q, g->k, rows, g->k, g->d, 1, 1.f, g->cst, st))) return rc;
+    if (g_path.load() != PVS_PATH_SIMT && g->tcg0 && tc_gemm_nt_supported(rows, g->k)) {
+        if (int rc = PVS_STAGE(ST_TC_GEMM_LOGITS, st, tc_gemm_nt(y, g->d, g->d, true, g->tcg0, g->tcg1, g->tcg_ld, g->k, q, g->k, rows,
+                                                                 1.f, g->cst, st))) return rc;
+    } else if (int rc = PVS_STAGE(ST_GMM_LOGITS, st, launch_gemm_nt(y, g->d, g->wcat, 2 * g->d, q, g->k, rows, g->k, g->d, 1, 1.f, g->cst, st))) return rc;
     return PVS_STAGE(ST_GMM_SOFTMAX, st, launch_row_softmax(q, rows, g->k, nullptr, st));
 }
 
@@ -452,8 +467,11 @@ extern "C" int pvs_fv_encode(const pvs_model* g, const pvs_model* pca, const flo
     }
     float* q = (float*)(ws + w.q);
     float* S = (float*)(ws + w.s);
-    if (int rc = PVS_STAGE(ST_GMM_LOGITS, st, launch_gemm_nt(y, g->d, g->wcat, 2 * g->d, q, g->k, total_rows, g->k, g->d, 1,
-                                                             1.f, g->cst, st))) return rc;
+    if (g_path.load() != PVS_PATH_SIMT && g->tcg0 && tc_gemm_nt_supported(total_rows, g->k)) {
+        if (int rc = PVS_STAGE(ST_TC_GEMM_LOGITS, st, tc_gemm_nt(y, g->d, g->d, true, g->tcg0, g->tcg1, g->tcg_ld, g->k, q, g->k,
+                                                                 total_rows, 1.f, g->cst, st))) return rc;
+    } else if (int rc = PVS_STAGE(ST_GMM_LOGITS, st, launch_gemm_nt(y, g->d, g->wcat, 2 * g->d, q, g->k, total_rows, g->k, g->d, 1,
+                                                                    1.f, g->cst, st))) return rc;
     if (int rc = PVS_STAGE(ST_GMM_SOFTMAX, st, launch_row_softmax(q, total_rows, g->k, argmax_out, st))) return rc;
     if (int rc = PVS_STAGE(ST_FV_STATS, st, launch_fv_stats(q, y, g->d, g->k, offsets, n_images, S, st))) return rc;
     return PVS_STAGE(ST_FV_FINALIZE, st, launch_fv_finalize(S, 2 * g->d + 1, nullptr, 0, offsets, g, n_images, power,

@@ -82,4 +82,8 @@ struct pvs_model {
     const float* tc0 = nullptr;
     const float* tc1 = nullptr;
     int tc_ld = 0;
+    // generic tensor path (pvs_tc_gemmnt.cu): zero-padded hi / lo copies of comp (PCA) or wcat (GMM)
+    const float* tcg0 = nullptr;
+    const float* tcg1 = nullptr;
+    int tcg_ld = 0;
 };

@@ -71,6 +71,12 @@ int tc_fv_project(const TcFvPlan& pl, const pvs_model* pca, const float* desc, i
 int tc_fv_posterior(const TcFvPlan& pl, const pvs_model* g, const float* y, int64_t rows, int32_t* argmax, cudaStream_t st);
 int tc_fv_stats(const TcFvPlan& pl, const float* y, const int64_t* offsets, int64_t n_images, cudaStream_t st);
 
+// generic fp32-accurate contraction on tensor cores (pvs_tc_gemmnt.cu), any shape
+int tc_prepare_generic(pvs_model* m);
+bool tc_gemm_nt_supported(int64_t m, int n);
+int tc_gemm_nt(const float* a, int64_t lda, int a_cols, bool square_cat, const float* b_hi, const float* b_lo, int b_ld,
+               int n, float* c, int64_t ldc, int64_t m, float alpha, const float* bias, cudaStream_t st);
+
 // similarity + fused top-k on bf16 tensor cores (pvs_tc_sim.cu)
 bool tc_sim_supported(int dtype, int64_t n_q, int64_t n_db, int64_t d, int k);
 size_t tc_sim_workspace_bytes(int64_t n_q, int64_t n_db, int k);
