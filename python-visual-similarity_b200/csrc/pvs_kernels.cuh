@@ -77,6 +77,10 @@ bool tc_gemm_nt_supported(int64_t m, int n);
 int tc_gemm_nt(const float* a, int64_t lda, int a_cols, bool square_cat, const float* b_hi, const float* b_lo, int b_ld,
                int n, float* c, int64_t ldc, int64_t m, float alpha, const float* bias, cudaStream_t st);
 
+bool tc_fv_stats_generic_supported(const pvs_model* g, int64_t n_images);
+int tc_fv_stats_generic(const float* q, const float* y, int d, const int64_t* offsets, int64_t n_images, float* S,
+                        float* s0part, cudaStream_t st);
+
 // similarity + fused top-k on bf16 tensor cores (pvs_tc_sim.cu)
 bool tc_sim_supported(int dtype, int64_t n_q, int64_t n_db, int64_t d, int k);
 size_t tc_sim_workspace_bytes(int64_t n_q, int64_t n_db, int k);

@@ -289,6 +289,131 @@ struct StatsPolicy {
 
 
 // ---------------------------------------------------------------------------------------
+// stats, any feature dimension D (K = 256): the [2D x K] statistics are cut into 128-row M
+// tiles of the augmented operand [y*y | y]; tile = (image, M tile).  The M tiles of an image
+// run on neighbouring CTAs at the same time, so its posteriors are read from HBM once and
+// served to the other tiles from L2.  Zeroth-order partials come from the M tile 0 producers.
+// (VGG16-PCA: D = 257 -> 5 M tiles; RootSIFT without PCA: D = 128 -> 2.)
+// ---------------------------------------------------------------------------------------
+struct StatsGenParams {
+    const float* y;                           // [rows, d]
+    const float* q;                           // [rows, 256]
+    const int64_t* offsets;
+    float* S;                                 // [n_images, 256, 2d]: [k][ s1 (d) | s2 (d) ], already / T
+    float* s0part;                            // [n_images, 16, 256]
+    int64_t n_images;
+    int d, n_mt;
+};
+
+struct StatsGenPolicy {
+    using Params = StatsGenParams;
+    using EpiState = NoEpiState;
+    struct Tile { int nkb; int t; int mt; int64_t img, r0; };
+    static constexpr bool BF16 = false, A_MN = true, B_MN = true, EPI_READS_STAGES = false, MANUAL = true;
+    static constexpr int KT = ST_KT;
+    static constexpr int PASSES = 3, BLOCK_N = FV_K, STAGES = 4, KSTEPS = KT / 8, PGROUPS = 4;
+    static constexpr int A_LBO = KT * 128, B_LBO = KT * 128;
+    static constexpr int A_BYTES = 4 * A_LBO, B_BYTES = (FV_K / 32) * B_LBO, SCRATCH_BYTES = 0, TMA_BYTES = 0;
+    static constexpr int RPW = KT / 4;
+    static_assert(PGROUPS * 4 == TC_FV_S0_PARTS, "one partial per producer warp");
+    __device__ static void prefetch(const Params&) {}
+    __device__ static int num_tiles(const Params& p) { return (int)(p.n_images * p.n_mt); }
+    __device__ static int tile_at(const Params&, int it, int n) { return strided_tile(it, n); }
+    __device__ static Tile tile(const Params& p, int i)
+    {
+        const int64_t img = i / p.n_mt;
+        const int64_t r0 = p.offsets[img];
+        const int t = (int)(p.offsets[img + 1] - r0);
+        return {(t + KT - 1) / KT, t, i - (int)img * p.n_mt, img, r0};
+    }
+    __device__ static void load(const Params&, const Tile&, int, uint8_t*, uint8_t*, uint8_t*, uint8_t*, uint64_t*) {}
+    struct Regs { float4 q[RPW * 2]; float4 y[RPW]; };
+    struct PState { float4 s0[2]; };
+    // augmented column a of a descriptor row: [0, d) -> y[a]^2, [d, 2d) -> y[a - d], beyond -> 0
+    __device__ static float aug(const Params& p, const float* yrow, int a)
+    {
+        if (a < p.d) { const float v = __ldg(yrow + a); return v * v; }
+        return a < 2 * p.d ? __ldg(yrow + a - p.d) : 0.f;
+    }
+    __device__ static void fetch(const Params& p, const Tile& t, int kb, int pw, int lane, Regs& g)
+    {
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int a0 = t.mt * 128 + lane * 4;                  // this lane's four augmented columns
+#pragma unroll
+        for (int rr = 0; rr < RPW; ++rr) {
+            const int tt = kb * KT + pw * RPW + rr;
+            const bool valid = tt < t.t;
+            const float* qrow = p.q + (t.r0 + tt) * FV_K;
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) g.q[rr * 2 + h2] = valid ? ldg4(qrow + (lane + 32 * h2) * 4) : z;
+            g.y[rr] = z;
+            if (valid) {
+                const float* yrow = p.y + (t.r0 + tt) * (int64_t)p.d;
+                g.y[rr] = make_float4(aug(p, yrow, a0), aug(p, yrow, a0 + 1), aug(p, yrow, a0 + 2), aug(p, yrow, a0 + 3));
+            }
+        }
+    }
+    __device__ static void store(const Params& p, const Tile& t, int kb, const Regs& g, uint8_t* a_hi, uint8_t* a_lo,
+                                 uint8_t* b_hi, uint8_t* b_lo, int pw, int grp, int lane, PState& ps)
+    {
+#pragma unroll
+        for (int rr = 0; rr < RPW; ++rr) {
+            const int r = pw * RPW + rr;
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+                const int c4 = lane + 32 * h2;
+                const float4 qv = g.q[rr * 2 + h2];
+                ps.s0[h2].x += qv.x; ps.s0[h2].y += qv.y; ps.s0[h2].z += qv.z; ps.s0[h2].w += qv.w;
+                float4 h, l;
+                split4(qv, h, l);
+                const uint32_t off = (uint32_t)((c4 >> 3) * B_LBO) + sw32_off(r, c4 & 7);
+                *reinterpret_cast<float4*>(b_hi + off) = h;
+                *reinterpret_cast<float4*>(b_lo + off) = l;
+            }
+            float4 h, l;
+            split4(g.y[rr], h, l);
+            const uint32_t off = (uint32_t)((lane >> 3) * A_LBO) + sw32_off(r, lane & 7);
+            *reinterpret_cast<float4*>(a_hi + off) = h;
+            *reinterpret_cast<float4*>(a_lo + off) = l;
+        }
+        if (kb + PGROUPS >= t.nkb) {                       // this group's last k-block of the tile
+            if (t.mt == 0) {
+                float4* dst = reinterpret_cast<float4*>(p.s0part + ((t.img * (PGROUPS * 4) + (kb % PGROUPS) * 4 + pw) * FV_K));
+                dst[lane] = ps.s0[0];
+                dst[lane + 32] = ps.s0[1];
+            }
+            ps.s0[0] = ps.s0[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        (void)grp;
+    }
+    __device__ static void epi_init(const Params&, uint8_t*, int) {}
+    __device__ static void epi_begin(const Params&, const Tile&, EpiState&, int, int) {}
+    __device__ static void epilogue(const Params& p, const Tile& t, uint32_t tmem, int quarter, int lane, uint8_t*,
+                                    EpiState&)
+    {
+        const int a = t.mt * 128 + quarter * 32 + lane;    // augmented column owned by this thread
+        const int ld = 2 * p.d;
+        const int col = a < p.d ? p.d + a : a - p.d;       // [ s1 | s2 ] layout
+        const bool live = a < ld;
+        float* Simg = p.S + t.img * (int64_t)FV_K * ld;
+        const float inv_t = 1.f / (float)t.t;              // T == 0 -> NaN, like the reference
+        const bool empty = t.nkb == 0;
+        const float nanv = __int_as_float(0x7fc00000);
+#pragma unroll 1
+        for (int c = 0; c < FV_K; c += 32) {
+            float v[32];
+            __syncwarp();
+            tmem_ld32(tmem + c, v);
+            tmem_ld_wait();
+            if (live) {
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) Simg[(int64_t)(c + jj) * ld + col] = empty ? nanv : v[jj] * inv_t;
+            }
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------
 // CTA-pair versions of project and posterior (pvs_tc2.cuh): the weight operand is resident
 // in shared memory (half per CTA) instead of being re-streamed from L2 for every tile, and
 // three producer groups keep three operand stages in flight.
@@ -658,6 +783,24 @@ int tc_fv_stats(const TcFvPlan& pl, const float* y, const int64_t* offsets, int6
     // a producer group only writes its partial when it owned a k-block of the image
     PVS_CUDA(cudaMemsetAsync(pl.s0part, 0, (size_t)n_images * TC_FV_S0_PARTS * FV_K * 4, st));
     return launch_tc<StatsPolicy>(p, (int)n_images, st);
+}
+
+// statistics for any D (K = 256) on tensor cores; S rows have pitch 2d, s0 comes as partials
+bool tc_fv_stats_generic_supported(const pvs_model* g, int64_t n_images)
+{
+    return tc_available() && g->k == FV_K && g->d >= 1 && n_images * ((2 * g->d + 127) / 128) < 2147483000LL;
+}
+
+int tc_fv_stats_generic(const float* q, const float* y, int d, const int64_t* offsets, int64_t n_images, float* S,
+                        float* s0part, cudaStream_t st)
+{
+    if (n_images <= 0) return PVS_OK;
+    PVS_CHECK((((uintptr_t)q) & 15) == 0, PVS_ERR_BAD_ARG, "posterior buffer must be 16-byte aligned");
+    StatsGenParams p{};
+    p.y = y; p.q = q; p.offsets = offsets; p.S = S; p.s0part = s0part; p.n_images = n_images;
+    p.d = d; p.n_mt = (2 * d + 127) / 128;
+    PVS_CUDA(cudaMemsetAsync(s0part, 0, (size_t)n_images * TC_FV_S0_PARTS * FV_K * 4, st));
+    return launch_tc<StatsGenPolicy>(p, (int)(n_images * p.n_mt), st);
 }
 
 }  // namespace pvs
