@@ -413,7 +413,7 @@ static FvWs fv_ws(const pvs_model* g, const pvs_model* pca, int64_t rows, int64_
 
 static bool fv_use_tc(const pvs_model* g, const pvs_model* pca, int64_t rows, int64_t n_images)
 {
-    return g_path.load() != PVS_PATH_SIMT && tc_fv_supported(g, pca, rows, n_images);
+    return g_path.load() != PVS_PATH_SIMT && tc_fv_supported(g, pca, rows, n_images) && !getenv("PVS_FV_FORCE_GENERIC");
 }
 
 extern "C" size_t pvs_fv_workspace_bytes(const pvs_model* g, const pvs_model* pca, int64_t total_rows, int64_t n_images)

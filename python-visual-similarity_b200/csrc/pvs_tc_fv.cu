@@ -511,7 +511,7 @@ struct PostPairPolicy {
     using Params = PostParams;
     using EpiState = NoEpiState;
     struct Tile { int nkb, mb; };
-    static constexpr bool BF16 = false, MANUAL = true, B_RESIDENT = true, ACC_INIT = true, TILE_SYNC = false;
+    static constexpr bool BF16 = false, MANUAL = true, B_RESIDENT = true, ACC_INIT = false, TILE_SYNC = false;
     static constexpr int PASSES = 3, BLOCK_N = FV_K, KSTEPS = 4, NKB_RES = FV_2D / 32, STAGES = 2, PGROUPS = 2;
     static constexpr int A_BYTES = 128 * 128, B_BYTES = (FV_K / 2) * 128, TMA_BYTES = 0;
     // scratch starts 256 B past a 1024-B boundary (barrier block): 768 B pad, then two 1024-aligned
@@ -534,15 +534,36 @@ struct PostPairPolicy {
     }
     __device__ static void load(const Params&, const Tile&, int, int, uint8_t*, uint8_t*, uint8_t*, uint8_t*, uint64_t*) {}
     // operand columns [0,64) are y*y, [64,128) are y
-    using Regs = KRegs;
+    // Operand row = interleaved (y_d^2, y_d) pairs (the weight copy is interleaved to match): the
+    // quadratic and the linear term of a dimension are accumulated next to each other, so the
+    // running sum in TMEM stays at the scale of the final logit -- the tensor core truncates when
+    // it accumulates and that error is proportional to the running sum (3x lower FV error than
+    // the [y*y | y] order, tools/probe_fv_err.py).  K-block kb holds dimensions [16 kb, 16 kb + 16).
+    struct Regs { float2 v[8]; };
     __device__ static void fetch(const Params& p, const Tile& t, int kb, int rank, int pw, int lane, Regs& r)
     {
-        fetch_kmajor_32rows(p.y, FV_D, (int64_t)t.mb * 256 + rank * 128, p.rows, (kb & 1) * 32, pw, lane, r);
+        const int64_t row0 = (int64_t)t.mb * 256 + rank * 128 + pw * 32;
+        const int c = lane & 7;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int64_t gr = row0 + i * 4 + (lane >> 3);
+            r.v[i] = make_float2(0.f, 0.f);
+            if (gr < p.rows) r.v[i] = __ldg(reinterpret_cast<const float2*>(p.y + gr * FV_D + kb * 16 + c * 2));
+        }
     }
-    __device__ static void store(const Params&, const Tile&, int kb, const Regs& r, uint8_t* a_hi, uint8_t* a_lo, int pw, int lane)
+    __device__ static void store(const Params&, const Tile&, int, const Regs& r, uint8_t* a_hi, uint8_t* a_lo, int pw, int lane)
     {
-        if (kb < 2) store_kmajor_32rows<true>(r, a_hi, a_lo, pw, lane);
-        else store_kmajor_32rows<false>(r, a_hi, a_lo, pw, lane);
+        const int c = lane & 7;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int row = pw * 32 + i * 4 + (lane >> 3);
+            const float2 y = r.v[i];
+            float4 h, l;
+            tc::split4(make_float4(y.x * y.x, y.x, y.y * y.y, y.y), h, l);
+            const uint32_t off = tc::sw128_off(row, c);
+            *reinterpret_cast<float4*>(a_hi + off) = h;
+            *reinterpret_cast<float4*>(a_lo + off) = l;
+        }
     }
     __device__ static void epi_init(const Params& p, uint8_t* scratch, int tid)
     {
@@ -551,35 +572,27 @@ struct PostPairPolicy {
         c[tid + 128] = p.cst[tid + 128];
         epi_barrier();
     }
-    // every lane (descriptor row) of an accumulator buffer starts from the per-component constant
-    __device__ static void acc_init(const Params&, uint32_t tmem, int, uint8_t* scratch)
-    {
-        const float4* cst4 = reinterpret_cast<const float4*>(scratch + CST_OFF);
-#pragma unroll 1
-        for (int c = 0; c < FV_K; c += 32) {
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float4 t = cst4[(c >> 2) + j];
-                v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
-            }
-            tmem_st32(tmem + c, v);
-        }
-    }
     __device__ static void epi_begin(const Params&, const Tile&, EpiState&, int, int, int) {}
     __device__ static void epilogue(const Params& p, const Tile& t, int rank, uint32_t tmem, int quarter, int lane,
                                     uint8_t* scratch, EpiState&)
     {
         const int64_t row = (int64_t)t.mb * 256 + rank * 128 + quarter * 32 + lane;
         const bool valid = row < p.rows;
-        // The accumulator was pre-loaded with cst (acc_init), so the TMEM columns hold the
-        // complete logits.  Only one epilogue warp runs per scheduler, so every pass keeps the
+        // The per-component constant is added here in fp32 rather than pre-loaded into the
+        // accumulator: the tensor core truncates when it accumulates, relative to the running
+        // sum, and starting that sum at |cst| ~ 10^2 cost a factor 3.6 in FV accuracy.
+        // Only one epilogue warp runs per scheduler, so every pass keeps the
         // TMEM load of the next 32 columns in flight while it works on the current ones and
         // splits its reductions over four independent chains.
         // pass 1: row maximum (arg-max only when the caller asked for it)
         float va[32], vb[32];
         float mx = -INFINITY;
         int mi = 0;
+        const float* cstv = reinterpret_cast<const float*>(scratch + CST_OFF);
+        auto addc = [&](float (&v)[32], int c) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += cstv[c + j];
+        };
         const bool tme = quarter == 0 && lane == 0 && rank == 0;
         (void)tme;
         PVS_T0(tp1);
@@ -588,6 +601,7 @@ struct PostPairPolicy {
             for (int c = 0; c < FV_K; c += 32) {
                 tmem_ld32(tmem + c, va);
                 tmem_ld_wait();
+                addc(va, c);
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
                     if (va[j] > mx) { mx = va[j]; mi = c + j; }   // strict >: lowest index on ties
@@ -599,10 +613,12 @@ struct PostPairPolicy {
             for (int c = 0; c < FV_K; c += 64) {
                 tmem_ld_wait();
                 tmem_ld32(tmem + c + 32, vb);
+                addc(va, c);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], va[j]);
                 tmem_ld_wait();
                 if (c + 64 < FV_K) tmem_ld32(tmem + c + 64, va);
+                addc(vb, c + 32);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], vb[j]);
             }
@@ -630,10 +646,12 @@ struct PostPairPolicy {
         for (int c = 0; c < FV_K; c += 64) {
             tmem_ld_wait();
             tmem_ld32(tmem + c + 32, vb);                      // (tcgen05.st reads its registers at issue)
+            addc(va, c);
             exp_chunk(va);
             tmem_st32(tmem + c, va);
             tmem_ld_wait();
             if (c + 64 < FV_K) tmem_ld32(tmem + c + 64, va);
+            addc(vb, c + 32);
             exp_chunk(vb);
             tmem_st32(tmem + c + 32, vb);
         }
@@ -767,8 +785,10 @@ int tc_fv_posterior(const TcFvPlan& pl, const pvs_model* g, const float* y, int6
     PVS_CHECK(((uintptr_t)y & 15) == 0, PVS_ERR_BAD_ARG, "descriptor buffer must be 16-byte aligned");
     PostParams p{};
     int rc;
-    if ((rc = make_tmap_2d(&p.w_hi, g->tc0, false, FV_K, FV_2D, FV_2D, 32, FV_K / 2))) return rc;
-    if ((rc = make_tmap_2d(&p.w_lo, g->tc1, false, FV_K, FV_2D, FV_2D, 32, FV_K / 2))) return rc;
+    // the interleaved (-P/2, mu P) hi / lo copies of pvs_tc_gemmnt.cu (row pitch 2D = 128 here)
+    PVS_CHECK(g->tcg0 && g->tcg_ld == FV_2D, PVS_ERR_BAD_ARG, "GMM model lacks the interleaved weight copy");
+    if ((rc = make_tmap_2d(&p.w_hi, g->tcg0, false, FV_K, FV_2D, FV_2D, 32, FV_K / 2))) return rc;
+    if ((rc = make_tmap_2d(&p.w_lo, g->tcg1, false, FV_K, FV_2D, FV_2D, 32, FV_K / 2))) return rc;
     if ((rc = make_tmap_2d(&p.q_map, pl.q, false, rows, FV_K, FV_K, 32, 32))) return rc;
     p.y = y; p.cst = g->cst; p.q = pl.q; p.argmax = argmax; p.rows = rows;
     p.m_blocks = (int)ceil_div(rows, 256);                    // CTA pairs: 256-row tiles, W resident
