@@ -210,6 +210,22 @@ extern "C" int pvs_gmm_create(const double* w, const double* mu, const double* c
     }
     pvs_model* m = new pvs_model();
     m->kind = PVS_MODEL_GMM_DIAG; m->k = k; m->d = d; m->d_in = d;
+    {   // power-of-two operand scale of the fp16x2 path: |mu| + 6 sigma <= 128 * 2^h_exp, and the scaled
+        // weights must sit well inside fp16's range (degenerate variances, e.g. sklearn's reg_covar
+        // floor, rule the model out -> it stays on 3xTF32)
+        double r = 0.0;
+        for (size_t e = 0; e < kd; ++e) r = fmax(r, fabs(mu[e]) + 6.0 * sqrt(cov[e]));
+        if (r > 0.0 && isfinite(r)) {
+            const int ex = (int)ceil(log2(r)) - 7;
+            double wmax = 0.0;
+            for (size_t e = 0; e < kd; ++e) {
+                const double P = pc[e] * pc[e];
+                wmax = fmax(wmax, fmax(0.5 * P * ldexp(1.0, 2 * ex), fabs(mu[e]) * P * ldexp(1.0, ex)));
+            }
+            m->h_exp = ex;
+            m->h_ok = ex > -40 && ex < 40 && wmax < 16384.0;
+        }
+    }
     if (int s = upload_block(m, h)) { delete m; return s; }
     const float* b = (const float*)m->block;
     m->wcat = b;
@@ -255,6 +271,7 @@ extern "C" int pvs_model_destroy(pvs_model* m)
     if (m->block) cudaFree(m->block);
     if (m->tc0) cudaFree((void*)m->tc0);
     if (m->tcg0) cudaFree((void*)m->tcg0);
+    if (m->th0) cudaFree((void*)m->th0);
     delete m;
     return PVS_OK;
 }
@@ -446,10 +463,11 @@ extern "C" int pvs_fv_encode(const pvs_model* g, const pvs_model* pca, const flo
         char* ws = (char*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
         tc_fv_plan(g, pca, total_rows, n_images, ws, &pl);
         const float* y = pca ? pl.y : desc;
+        if (int rc = tc_fv_begin(pl, n_images, st)) return rc;
         if (pca)
-            if (int rc = PVS_STAGE(ST_TC_FV_PROJECT, st, tc_fv_project(pl, pca, desc, total_rows, st))) return rc;
+            if (int rc = PVS_STAGE(ST_TC_FV_PROJECT, st, tc_fv_project(pl, g, pca, desc, total_rows, st))) return rc;
         if (int rc = PVS_STAGE(ST_TC_FV_POSTERIOR, st, tc_fv_posterior(pl, g, y, total_rows, argmax_out, st))) return rc;
-        if (int rc = PVS_STAGE(ST_TC_FV_STATS, st, tc_fv_stats(pl, y, offsets, n_images, st))) return rc;
+        if (int rc = PVS_STAGE(ST_TC_FV_STATS, st, tc_fv_stats(pl, g, y, offsets, n_images, st))) return rc;
         return PVS_STAGE(ST_FV_FINALIZE, st, launch_fv_finalize(pl.S, 2 * g->d, pl.s0part, TC_FV_S0_PARTS, offsets, g, n_images, power,
                                                                  norm_order, eps, out, st));
     }

@@ -86,4 +86,10 @@ struct pvs_model {
     const float* tcg0 = nullptr;
     const float* tcg1 = nullptr;
     int tcg_ld = 0;
+    // fp16x2 tensor path (GMM, K = 256 / D = 64): y is scaled by 2^-h_exp so that |mu| + 6 sigma <= 128,
+    // th0 / th1 = fp16 hi / lo parts of the interleaved weights (-P/2 * 4^h_exp, mu P * 2^h_exp) [k, 2d]
+    bool h_ok = false;
+    int h_exp = 0;
+    const void* th0 = nullptr;
+    const void* th1 = nullptr;
 };

@@ -62,14 +62,19 @@ struct TcFvPlan {
     float* q;                    // [rows, 256] posteriors
     float* S;                    // [n_images, 256, 128] first/second-order sums / T
     float* s0part;               // [n_images, TC_FV_S0_PARTS, 256] raw zeroth-order partial sums
+    int* flag;                   // right behind s0part (one memset clears both): raised by the projection when
+                                 // some |y| leaves the fp16x2 operand range -> the 3xTF32 kernels do the work
+    bool fp16x2;                 // this call may use the fp16x2 kernels (eligible model, PCA present)
     int n_tiles;                 // 128-row tiles
+    int64_t rows;
     size_t total;
 };
 bool tc_fv_supported(const pvs_model* g, const pvs_model* pca, int64_t rows, int64_t n_images);
 int tc_fv_plan(const pvs_model* g, const pvs_model* pca, int64_t rows, int64_t n_images, void* ws, TcFvPlan* plan);
-int tc_fv_project(const TcFvPlan& pl, const pvs_model* pca, const float* desc, int64_t rows, cudaStream_t st);
+int tc_fv_begin(const TcFvPlan& pl, int64_t n_images, cudaStream_t st);   // clears s0part + flag
+int tc_fv_project(const TcFvPlan& pl, const pvs_model* g, const pvs_model* pca, const float* desc, int64_t rows, cudaStream_t st);
 int tc_fv_posterior(const TcFvPlan& pl, const pvs_model* g, const float* y, int64_t rows, int32_t* argmax, cudaStream_t st);
-int tc_fv_stats(const TcFvPlan& pl, const float* y, const int64_t* offsets, int64_t n_images, cudaStream_t st);
+int tc_fv_stats(const TcFvPlan& pl, const pvs_model* g, const float* y, const int64_t* offsets, int64_t n_images, cudaStream_t st);
 
 // generic fp32-accurate contraction on tensor cores (pvs_tc_gemmnt.cu), any shape
 int tc_prepare_generic(pvs_model* m);

@@ -196,11 +196,36 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
     return d;
 }
 // Instruction descriptor: fp32 accumulate, A/B format tf32 (2) or bf16 (1), majors, N>>3, M>>4
-__host__ __device__ constexpr uint32_t make_idesc(bool bf16, bool a_mn, bool b_mn, int m, int n)
+__host__ __device__ constexpr uint32_t make_idesc(bool bf16, bool a_mn, bool b_mn, int m, int n, bool f16 = false)
 {
-    return (1u << 4) | ((bf16 ? 1u : 2u) << 7) | ((bf16 ? 1u : 2u) << 10) | ((a_mn ? 1u : 0u) << 15) |
+    const uint32_t fmt = f16 ? 0u : bf16 ? 1u : 2u;          // kind::f16: 0 = fp16, 1 = bf16; kind::tf32: 2 = tf32
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((a_mn ? 1u : 0u) << 15) |
            ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+
+// Optional policy members (detected, so existing policies need not declare them):
+//   static constexpr bool F16 = true   operands are fp16 (kind::f16, format 0); with PASSES == 3 this is the
+//                                      "fp16x2" split x = hi + lo, hi*lo + lo*hi + hi*hi: 22 mantissa bits like
+//                                      3xTF32 at twice the tensor rate and half the shared-memory bytes, for
+//                                      operands that were scaled into fp16's range by an exact power of two
+//   static bool enabled(const Params&) uniform early exit: the kernel returns at once when this is false
+//                                      (two precision variants are launched back to back and a device-side
+//                                      flag decides which one does the work -- no host synchronisation)
+template <class P, class = void> struct policy_f16 { static constexpr bool value = false; };
+template <class P> struct policy_f16<P, decltype((void)P::F16)> { static constexpr bool value = P::F16; };
+//   static constexpr int STAGE_EXTRA   policy-owned bytes at the end of every stage (e.g. a TMA-filled staging tile
+//                                      plus the policy's own mbarrier), with
+//   static void init_stage(uint8_t*)   called once per stage (pointer to the extra region) before the barriers
+//                                      are published
+template <class P, class = void> struct policy_extra { static constexpr int value = 0; };
+template <class P> struct policy_extra<P, decltype((void)P::STAGE_EXTRA)> { static constexpr int value = P::STAGE_EXTRA; };
+//   static constexpr bool TMA_OWN_BARRIER = true   the policy's load() completes its TMA bytes on its own mbarrier
+//                                      (in the extra region) instead of full[s]; the MANUAL warps wait for
+//                                      it inside store(), post-process the tiles and only then arrive on full[s]
+template <class P, class = void> struct policy_own_tx { static constexpr bool value = false; };
+template <class P> struct policy_own_tx<P, decltype((void)P::TMA_OWN_BARRIER)> { static constexpr bool value = P::TMA_OWN_BARRIER; };
+template <class P, class = void> struct policy_gated { static constexpr bool value = false; };
+template <class P> struct policy_gated<P, decltype((void)&P::enabled)> { static constexpr bool value = true; };
 
 // ---------------------------------------------------------------------------------------
 // host: TMA tensor maps (driver entry point resolved at run time, no libcuda link)
@@ -252,19 +277,24 @@ __device__ unsigned long long g_tc_timing[8];
 template <class P>
 struct Layout {
     static constexpr int PARTS = P::PASSES == 3 ? 2 : 1;
-    static constexpr int STAGE_BYTES = PARTS * (P::A_BYTES + P::B_BYTES);
+    static constexpr int EXTRA = policy_extra<P>::value;
+    static constexpr int STAGE_BYTES = PARTS * (P::A_BYTES + P::B_BYTES) + EXTRA;
     static constexpr int RING_BYTES = P::STAGES * STAGE_BYTES;
     static constexpr int BAR_BYTES = 256;
     static constexpr int SMEM_BYTES = 1024 /*alignment slack*/ + RING_BYTES + BAR_BYTES + P::SCRATCH_BYTES;
+    static_assert(EXTRA % 1024 == 0, "stages must keep 1024-B alignment");
+    static_assert(2 * P::STAGES + 4 <= 30, "barrier block too small");
     static constexpr int TMEM_COLS = 2 * P::BLOCK_N <= 32 ? 32 : 2 * P::BLOCK_N <= 64 ? 64 : 2 * P::BLOCK_N <= 128 ? 128
                                      : 2 * P::BLOCK_N <= 256 ? 256 : 512;
     // threads: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue,
     // warps 6-9 (only with P::MANUAL) operand producers that load fp32 from global memory,
     // split it into tf32 hi/lo parts and store the swizzled tiles themselves
     static constexpr int THREADS = P::MANUAL ? 192 + 128 * P::PGROUPS : 192;
-    static constexpr uint32_t FULL_COUNT = (P::TMA_BYTES > 0 ? 1 : 0) + (P::MANUAL ? 4 : 0);
+    static constexpr bool OWN_TX = policy_own_tx<P>::value;
+    static constexpr uint32_t FULL_COUNT = (P::TMA_BYTES > 0 && !OWN_TX ? 1 : 0) + (P::MANUAL ? 4 : 0);
     static_assert(2 * P::BLOCK_N <= 512, "accumulator does not fit TMEM twice");
-    static_assert(!(P::BF16 && (P::A_MN || P::B_MN)), "MN-major operands are implemented for tf32 only");
+    static constexpr bool F16 = policy_f16<P>::value;
+    static_assert(!(P::BF16 && (P::A_MN || P::B_MN)), "MN-major operands are implemented for tf32 and fp16 only");
     static_assert(P::A_BYTES % 1024 == 0 && P::B_BYTES % 1024 == 0, "operand tiles must keep 1024-B alignment");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
     // every stage must be refilled by one producer group only: a group that ran two uses ahead of
@@ -276,6 +306,9 @@ template <class P>
 __global__ void __launch_bounds__(Layout<P>::THREADS, 1) tc_kernel(const __grid_constant__ typename P::Params prm)
 {
     using L = Layout<P>;
+    if constexpr (policy_gated<P>::value) {
+        if (!P::enabled(prm)) return;                        // uniform over the grid
+    }
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment as an OFFSET on the __shared__ array: going through an integer cast would
     // turn every later access into a generic LD / ST instead of LDS / STS
@@ -292,6 +325,7 @@ __global__ void __launch_bounds__(Layout<P>::THREADS, 1) tc_kernel(const __grid_
         for (int s = 0; s < P::STAGES; ++s) {
             mbar_init(&full[s], L::FULL_COUNT);
             mbar_init(&empty[s], 1 + (P::EPI_READS_STAGES ? 4 : 0));
+            if constexpr (L::EXTRA > 0) P::init_stage(smem + s * L::STAGE_BYTES + L::PARTS * (P::A_BYTES + P::B_BYTES));
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull[a], 1);
@@ -315,7 +349,7 @@ __global__ void __launch_bounds__(Layout<P>::THREADS, 1) tc_kernel(const __grid_
                 const typename P::Tile tl = P::tile(prm, t);
                 for (int kb = 0; kb < tl.nkb; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_expect_tx(&full[stage], P::TMA_BYTES);
+                    if constexpr (!L::OWN_TX) mbar_expect_tx(&full[stage], P::TMA_BYTES);
                     uint8_t* sp = smem + stage * L::STAGE_BYTES;
                     P::load(prm, tl, kb, sp, sp + P::A_BYTES, sp + L::PARTS * P::A_BYTES,
                             sp + L::PARTS * P::A_BYTES + P::B_BYTES, &full[stage]);
@@ -325,7 +359,9 @@ __global__ void __launch_bounds__(Layout<P>::THREADS, 1) tc_kernel(const __grid_
         }
     } else if (warp == 1) {
         {   // the whole warp walks the pipeline; one elected lane issues the MMAs and commits
-            constexpr uint32_t idesc = make_idesc(P::BF16, P::A_MN, P::B_MN, 128, P::BLOCK_N);
+            constexpr bool F16 = L::F16;
+            constexpr bool H = P::BF16 || F16;               // kind::f16
+            constexpr uint32_t idesc = make_idesc(P::BF16, P::A_MN, P::B_MN, 128, P::BLOCK_N, F16);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             for (int it = 0, t; (t = P::tile_at(prm, it, n_tiles)) >= 0; ++it) {
@@ -346,23 +382,28 @@ __global__ void __launch_bounds__(Layout<P>::THREADS, 1) tc_kernel(const __grid_
                     if (elect_one()) {
 #pragma unroll
                     for (int ks = 0; ks < P::KSTEPS; ++ks) {
-                        const uint32_t a_off = P::A_MN ? ks * 1024 : ks * 32;
-                        const uint32_t b_off = P::B_MN ? ks * 1024 : ks * 32;
+                        // one k-step: tf32 K = 8, 16-bit K = 16.  K-major: 32 B along the 128-B row either way.
+                        // MN-major: K rows of 128 B; tf32 uses 4-row atoms (512 B, SWIZZLE_128B_BASE32B), 16-bit
+                        // types 8-row atoms (1024 B, SWIZZLE_128B) -- a k-step spans two atoms in both cases.
+                        constexpr uint32_t mn_step = F16 ? 2048 : 1024, mn_sbo = F16 ? 1024 : 512;
+                        constexpr uint32_t mn_layout = F16 ? LAYOUT_SW128 : LAYOUT_SW128_BASE32B;
+                        const uint32_t a_off = P::A_MN ? ks * mn_step : ks * 32;
+                        const uint32_t b_off = P::B_MN ? ks * mn_step : ks * 32;
                         const uint32_t a_l = P::A_MN ? P::A_LBO : 16, b_l = P::B_MN ? P::B_LBO : 16;
-                        const uint32_t a_s = P::A_MN ? 512 : 1024, b_s = P::B_MN ? 512 : 1024;
-                        const uint32_t a_t = P::A_MN ? LAYOUT_SW128_BASE32B : LAYOUT_SW128;
-                        const uint32_t b_t = P::B_MN ? LAYOUT_SW128_BASE32B : LAYOUT_SW128;
+                        const uint32_t a_s = P::A_MN ? mn_sbo : 1024, b_s = P::B_MN ? mn_sbo : 1024;
+                        const uint32_t a_t = P::A_MN ? mn_layout : LAYOUT_SW128;
+                        const uint32_t b_t = P::B_MN ? mn_layout : LAYOUT_SW128;
                         const uint64_t da_hi = make_smem_desc(a_hi + a_off, a_l, a_s, a_t);
                         const uint64_t db_hi = make_smem_desc(b_hi + b_off, b_l, b_s, b_t);
                         const uint32_t first = (kb > 0 || ks > 0) ? 1u : 0u;
                         if constexpr (P::PASSES == 3) {
                             const uint64_t da_lo = make_smem_desc(a_lo + a_off, a_l, a_s, a_t);
                             const uint64_t db_lo = make_smem_desc(b_lo + b_off, b_l, b_s, b_t);
-                            umma<P::BF16>(d_tmem, da_hi, db_lo, idesc, first);
-                            umma<P::BF16>(d_tmem, da_lo, db_hi, idesc, 1u);
-                            umma<P::BF16>(d_tmem, da_hi, db_hi, idesc, 1u);
+                            umma<H>(d_tmem, da_hi, db_lo, idesc, first);
+                            umma<H>(d_tmem, da_lo, db_hi, idesc, 1u);
+                            umma<H>(d_tmem, da_hi, db_hi, idesc, 1u);
                         } else {
-                            umma<P::BF16>(d_tmem, da_hi, db_hi, idesc, first);
+                            umma<H>(d_tmem, da_hi, db_hi, idesc, first);
                         }
                     }
                     umma_commit(&empty[stage]);          // smem slot free once these MMAs retire

@@ -158,6 +158,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Layout2<P>::THREADS,
 tc2_kernel(const __grid_constant__ typename P::Params prm)
 {
     using L = Layout2<P>;
+    if constexpr (policy_gated<P>::value) {
+        if (!P::enabled(prm)) return;                        // uniform over the grid (both CTAs of every pair)
+    }
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment as an OFFSET on the __shared__ array: going through an integer cast would
     // turn every later access into a generic LD / ST instead of LDS / STS
@@ -221,7 +224,8 @@ tc2_kernel(const __grid_constant__ typename P::Params prm)
         }
     } else if (warp == 1) {
         if (rank == 0) {   // the whole warp walks the pipeline; one elected lane issues the MMAs and commits
-            constexpr uint32_t idesc = make_idesc(P::BF16, false, false, 256, P::BLOCK_N);
+            constexpr bool H = P::BF16 || policy_f16<P>::value;   // kind::f16
+            constexpr uint32_t idesc = make_idesc(P::BF16, false, false, 256, P::BLOCK_N, policy_f16<P>::value);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
 #ifdef PVS_TIMING
@@ -256,11 +260,11 @@ tc2_kernel(const __grid_constant__ typename P::Params prm)
                         if constexpr (P::PASSES == 3) {
                             const uint64_t da_lo = make_smem_desc(a_lo + ks * 32, 16, 1024, LAYOUT_SW128);
                             const uint64_t db_lo = make_smem_desc(b_lo + ks * 32, 16, 1024, LAYOUT_SW128);
-                            umma2<P::BF16>(d_tmem, da_hi, db_lo, idesc, first);
-                            umma2<P::BF16>(d_tmem, da_lo, db_hi, idesc, 1u);
-                            umma2<P::BF16>(d_tmem, da_hi, db_hi, idesc, 1u);
+                            umma2<H>(d_tmem, da_hi, db_lo, idesc, first);
+                            umma2<H>(d_tmem, da_lo, db_hi, idesc, 1u);
+                            umma2<H>(d_tmem, da_hi, db_hi, idesc, 1u);
                         } else {
-                            umma2<P::BF16>(d_tmem, da_hi, db_hi, idesc, first);
+                            umma2<H>(d_tmem, da_hi, db_hi, idesc, first);
                         }
                     }
                     umma2_commit(&empty[stage]);

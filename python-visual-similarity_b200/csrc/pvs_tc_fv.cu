@@ -21,6 +21,7 @@
 #include "pvs_tc.cuh"
 #include "pvs_tc2.cuh"
 #include "pvs_kernels.cuh"
+#include <cuda_fp16.h>
 
 namespace pvs {
 namespace tc {
@@ -85,6 +86,8 @@ struct PcaParams {
     float* y;
     int64_t rows;
     int m_blocks, nkb, d_in;
+    int* flag;                                // raised when some |y| > lim (fp16x2 operand range), may be NULL
+    float lim;
 };
 struct NoEpiState {};
 
@@ -131,6 +134,7 @@ struct PcaPolicy {
         const int64_t row = (int64_t)t.mb * 128 + quarter * 32 + lane;
         const bool valid = row < p.rows;
         float4* o = reinterpret_cast<float4*>(p.y + row * FV_D);
+        float amax = 0.f;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             float v[32];
@@ -139,11 +143,13 @@ struct PcaPolicy {
             tmem_ld_wait();
             if (valid) {
 #pragma unroll
+                for (int j = 0; j < 32; ++j) { v[j] += bias[half * 32 + j]; amax = fmaxf(amax, fabsf(v[j])); }
+#pragma unroll
                 for (int j = 0; j < 32; j += 4)
-                    o[(half * 32 + j) >> 2] = make_float4(v[j] + bias[half * 32 + j], v[j + 1] + bias[half * 32 + j + 1],
-                                                          v[j + 2] + bias[half * 32 + j + 2], v[j + 3] + bias[half * 32 + j + 3]);
+                    o[(half * 32 + j) >> 2] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             }
         }
+        if (p.flag && amax > p.lim) *p.flag = 1;               // fp16x2 range guard (inf raises it, NaN just propagates)
     }
 };
 
@@ -152,12 +158,18 @@ struct PcaPolicy {
 // ---------------------------------------------------------------------------------------
 struct PostParams {
     CUtensorMap w_hi, w_lo, q_map;            // q_map: Q [rows, 256] fp32, box 32 cols x 32 rows (TMA store)
+    CUtensorMap qh_map, ql_map;               // fp16x2 variant, planes == 1: Q * 2^14 as fp16 hi / lo planes [rows, 256],
+                                              // box 64 cols x 32 rows -- the operand format of the statistics kernel
     const float* y;
     const float* cst;
     float* q;
     int32_t* argmax;
     int64_t rows;
     int m_blocks;
+    const int* flag;                          // fp16x2 range flag (NULL: no gating): the fp16x2 variant runs when it is 0,
+                                              // the 3xTF32 variant when it is not
+    float sc_y;                               // 2^-e (fp16x2 variant)
+    int planes;                               // fp16x2 variant: write the fp16 planes instead of fp32 Q
 };
 
 // ---------------------------------------------------------------------------------------
@@ -284,6 +296,191 @@ struct StatsPolicy {
 #pragma unroll
             for (int jj = 0; jj < 32; ++jj) Simg[(int64_t)(c + jj) * FV_2D + n] = empty ? nanv : v[jj] * inv_t;
         }
+    }
+};
+
+
+// ---------------------------------------------------------------------------------------
+// stats, fp16x2 operands: the same contraction with both operands scaled into fp16's range by
+// exact powers of two (Q by 2^14; y by 2^-e, e from the mixture model so that |mu| + 6 sigma
+// <= 128 * 2^e, hence y'^2 <= 2^14) and split x = hi + lo into two fp16 parts.  Three
+// kind::f16 MMAs (hi*lo + lo*hi + hi*hi) keep 22 mantissa bits -- the class of 3xTF32 -- at
+// twice the tensor rate and half the shared-memory bytes per stage, which moves this kernel
+// from the tensor pipe to the HBM roofline (it has to read Q: 1 KB per descriptor).  Gated
+// by a device flag the projection kernel raises when some |y| would leave the fp16 range; the
+// 3xTF32 kernel is launched right behind with the opposite gate.
+// ---------------------------------------------------------------------------------------
+struct Stats16Params {
+    CUtensorMap qh_map, ql_map;               // Q * 2^14 as fp16 hi / lo planes [rows, 256], box 64 cols x 16 rows
+    CUtensorMap y_map;                        // Y [rows, 64] fp32, box 32 cols x 16 rows
+    StatsParams b;
+    const int* flag;                          // != 0: operands out of fp16 range -> this kernel does nothing
+    float sc_y, un1, un2;                     // 2^-e, 2^(e-14), 2^(2e-14)
+};
+
+__device__ __forceinline__ uint32_t pack_h2(__half2 v) { return *reinterpret_cast<uint32_t*>(&v); }
+// eight fp32 values -> 16-byte chunks of fp16 hi and lo parts (x = hi + lo + O(2^-22 |x|))
+__device__ __forceinline__ void split8_h(const float (&x)[8], uint4& hi, uint4& lo)
+{
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __half2 hh = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+        const float2 back = __half22float2(hh);
+        h[i] = pack_h2(hh);
+        l[i] = pack_h2(__floats2half2_rn(x[2 * i] - back.x, x[2 * i + 1] - back.y));
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// The posterior kernel leaves Q already scaled and split (two fp16 planes), so the Q operand of a
+// stage is eight TMA boxes straight into the swizzled MN-major tiles -- no registers, no conversion,
+// as many stages in flight as shared memory holds.  Y (256 B per descriptor) arrives by TMA as fp32
+// in a staging tile of the stage; four converter warps scale / square / split it into the A tiles,
+// zero the Q rows past the end of the image in the image's last stage, and publish the stage.  The
+// epilogue warps read the Q tiles of every stage for the zeroth-order sums while the MMAs run.
+struct Stats16Policy {
+    using Params = Stats16Params;
+    struct EpiState { float2 s0; };
+    struct Tile { int nkb; int t; int64_t img, r0; };
+    static constexpr bool BF16 = false, F16 = true, A_MN = true, B_MN = true, EPI_READS_STAGES = true, MANUAL = true;
+    static constexpr bool TMA_OWN_BARRIER = true;
+    static constexpr int KT = 16;             // descriptors per stage = one K=16 step
+    static constexpr int PASSES = 3, BLOCK_N = FV_K, STAGES = 7, KSTEPS = 1, PGROUPS = 1;
+    static constexpr int A_LBO = KT * 128, B_LBO = KT * 128;          // one [KT rows x 128 B] block per 64 columns
+    static constexpr int A_BYTES = (FV_2D / 64) * A_LBO, B_BYTES = (FV_K / 64) * B_LBO, SCRATCH_BYTES = 0;
+    static constexpr int Y_STAGE = KT * FV_D * 4;                     // two [16 x 32] fp32 boxes
+    static constexpr int STAGE_EXTRA = Y_STAGE + 1024;                // + the policy's mbarrier
+    static constexpr int TMA_BYTES = 2 * B_BYTES + Y_STAGE;
+    __device__ static bool enabled(const Params& p) { return *p.flag == 0; }
+    __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.qh_map); tma_prefetch_desc(&p.ql_map); tma_prefetch_desc(&p.y_map); }
+    __device__ static void init_stage(uint8_t* extra) { mbar_init(reinterpret_cast<uint64_t*>(extra + Y_STAGE), 1); }
+    __device__ static int num_tiles(const Params& p) { return (int)p.b.n_images; }
+    __device__ static int tile_at(const Params&, int it, int n) { return strided_tile(it, n); }
+    __device__ static Tile tile(const Params& p, int i)
+    {
+        const int64_t r0 = p.b.offsets[i];
+        const int t = (int)(p.b.offsets[i + 1] - r0);
+        return {(t + KT - 1) / KT, t, (int64_t)i, r0};
+    }
+    __device__ static void load(const Params& p, const Tile& t, int kb, uint8_t*, uint8_t*, uint8_t* b_hi, uint8_t* b_lo, uint64_t*)
+    {
+        uint8_t* extra = b_lo + B_BYTES;
+        uint64_t* bar = reinterpret_cast<uint64_t*>(extra + Y_STAGE);
+        const int row = (int)(t.r0 + (int64_t)kb * KT);
+        mbar_expect_tx(bar, TMA_BYTES);
+#pragma unroll
+        for (int cb = 0; cb < FV_K / 64; ++cb) {
+            tma_load_2d(b_hi + cb * B_LBO, &p.qh_map, bar, cb * 64, row);
+            tma_load_2d(b_lo + cb * B_LBO, &p.ql_map, bar, cb * 64, row);
+        }
+        tma_load_2d(extra, &p.y_map, bar, 0, row);
+        tma_load_2d(extra + Y_STAGE / 2, &p.y_map, bar, 32, row);
+    }
+    struct Regs {};
+    __device__ static void fetch(const Params&, const Tile&, int, int, int, Regs&) {}
+    struct PState { uint32_t uses; };          // stages published so far by this warp (PGROUPS == 1: all of them)
+    __device__ static void store(const Params& p, const Tile& t, int kb, const Regs&, uint8_t* a_hi, uint8_t* a_lo,
+                                 uint8_t* b_hi, uint8_t* b_lo, int pw, int, int lane, PState& ps)
+    {
+        uint8_t* extra = b_lo + B_BYTES;
+        mbar_wait(reinterpret_cast<uint64_t*>(extra + Y_STAGE), (ps.uses / STAGES) & 1u);
+        ++ps.uses;
+        const int valid = t.t - kb * KT;                   // rows of this stage that belong to the image
+        // a lane owns 8 dims of one row: row r = 4 pw + lane / 8, dims [8 (lane % 8), +8)
+        const int r = pw * 4 + (lane >> 3);
+        const int blk = (lane & 7) >> 2, c0 = (lane & 3) * 2;
+        const uint8_t* src = extra + blk * (Y_STAGE / 2);
+        float4 y0 = *reinterpret_cast<const float4*>(src + sw128_off(r, c0));
+        float4 y1 = *reinterpret_cast<const float4*>(src + sw128_off(r, c0 + 1));
+        if (r >= valid) y0 = y1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float v[8] = {y0.x * p.sc_y, y0.y * p.sc_y, y0.z * p.sc_y, y0.w * p.sc_y,
+                            y1.x * p.sc_y, y1.y * p.sc_y, y1.z * p.sc_y, y1.w * p.sc_y};
+        float sq[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sq[i] = v[i] * v[i];
+        uint4 h, l;
+        const uint32_t off = sw128_off(r, lane & 7);       // y'^2 -> column block 0, y' -> block 1
+        split8_h(sq, h, l);
+        *reinterpret_cast<uint4*>(a_hi + off) = h;
+        *reinterpret_cast<uint4*>(a_lo + off) = l;
+        split8_h(v, h, l);
+        *reinterpret_cast<uint4*>(a_hi + A_LBO + off) = h;
+        *reinterpret_cast<uint4*>(a_lo + A_LBO + off) = l;
+        if (valid < KT) {
+            // last stage of the image: the Q boxes also brought rows of the next image (or zeros past the
+            // end of the batch); clear them so that neither the MMA (0 x NaN) nor the zeroth-order sums see them
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+            for (int i = pw * 32 + lane; i < (KT - valid) * 64; i += 128) {
+                const int rr = valid + (i >> 6), part = (i >> 5) & 1, cb = (i >> 3) & 3, ch = i & 7;
+                *reinterpret_cast<uint4*>((part ? b_lo : b_hi) + cb * B_LBO + rr * 128 + (ch << 4)) = z;
+            }
+        }
+    }
+    __device__ static void epi_init(const Params&, uint8_t*, int) {}
+    __device__ static void epi_begin(const Params&, const Tile&, EpiState& st, int, int) { st.s0 = make_float2(0.f, 0.f); }
+    // zeroth-order sums: thread (quarter, lane) owns components 2e, 2e + 1 (e = 32 quarter + lane) = one
+    // 4-byte word of every row in column block `quarter`; a warp reads one 128-B row per instruction
+    __device__ static void consume(const Params&, const Tile&, int, uint8_t*, uint8_t*, uint8_t* b_hi, uint8_t* b_lo,
+                                   EpiState& st, int quarter, int lane)
+    {
+        const uint32_t base = (uint32_t)(quarter * B_LBO + (lane & 3) * 4);
+        const int ch = lane >> 2;
+        float2 acc = st.s0;
+#pragma unroll
+        for (int r = 0; r < KT; ++r) {
+            const uint32_t off = base + (uint32_t)(r * 128 + ((ch ^ (r & 7)) << 4));
+            const float2 h = __half22float2(*reinterpret_cast<const __half2*>(b_hi + off));
+            const float2 l = __half22float2(*reinterpret_cast<const __half2*>(b_lo + off));
+            acc.x += h.x + l.x;
+            acc.y += h.y + l.y;
+        }
+        st.s0 = acc;
+    }
+    __device__ static void epilogue(const Params& p, const Tile& t, uint32_t tmem, int quarter, int lane, uint8_t*,
+                                    EpiState& st)
+    {
+        const int e = quarter * 32 + lane;                 // operand row: [0,64) = y'^2, [64,128) = y'
+        const int n = e < FV_D ? FV_D + e : e - FV_D;      // column in the [ s1 | s2 ] layout
+        float* Simg = p.b.S + t.img * (int64_t)FV_K * FV_2D;
+        const float scale = (e < FV_D ? p.un2 : p.un1) / (float)t.t;   // undo the operand scales; T == 0 -> NaN below
+        const bool empty = t.nkb == 0;
+        const float nanv = __int_as_float(0x7fc00000);
+        // raw zeroth-order sums go into partial slot 0 (the other slots stay zero, fv_finalize adds them up and divides by T)
+        reinterpret_cast<float2*>(p.b.s0part + t.img * (int64_t)(TC_FV_S0_PARTS * FV_K))[e] =
+            make_float2(st.s0.x * (1.f / 16384.f), st.s0.y * (1.f / 16384.f));
+#pragma unroll 1
+        for (int c = 0; c < FV_K; c += 32) {
+            float v[32];
+            __syncwarp();
+            tmem_ld32(tmem + c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) Simg[(int64_t)(c + jj) * FV_2D + n] = empty ? nanv : v[jj] * scale;
+        }
+    }
+};
+// the 3xTF32 kernel behind the opposite gate
+struct StatsGatedPolicy : StatsPolicy {
+    using Params = Stats16Params;
+    __device__ static bool enabled(const Params& p) { return *p.flag != 0; }
+    __device__ static int num_tiles(const Params& p) { return StatsPolicy::num_tiles(p.b); }
+    __device__ static int tile_at(const Params&, int it, int n) { return strided_tile(it, n); }
+    __device__ static Tile tile(const Params& p, int i) { return StatsPolicy::tile(p.b, i); }
+    __device__ static void prefetch(const Params&) {}
+    __device__ static void load(const Params&, const Tile&, int, uint8_t*, uint8_t*, uint8_t*, uint8_t*, uint64_t*) {}
+    __device__ static void fetch(const Params& p, const Tile& t, int kb, int pw, int lane, Regs& g) { StatsPolicy::fetch(p.b, t, kb, pw, lane, g); }
+    __device__ static void store(const Params& p, const Tile& t, int kb, const Regs& g, uint8_t* a_hi, uint8_t* a_lo,
+                                 uint8_t* b_hi, uint8_t* b_lo, int pw, int grp, int lane, PState& ps)
+    {
+        StatsPolicy::store(p.b, t, kb, g, a_hi, a_lo, b_hi, b_lo, pw, grp, lane, ps);
+    }
+    __device__ static void epi_init(const Params&, uint8_t*, int) {}
+    __device__ static void epi_begin(const Params&, const Tile&, EpiState&, int, int) {}
+    __device__ static void epilogue(const Params& p, const Tile& t, uint32_t tmem, int quarter, int lane, uint8_t* sc, EpiState& st)
+    {
+        StatsPolicy::epilogue(p.b, t, tmem, quarter, lane, sc, st);
     }
 };
 
@@ -483,6 +680,7 @@ struct PcaPairPolicy {
         // tiles and leave as TMA stores (full 128-byte row segments, rows past the end clipped)
         if (lane == 0) tma_store_wait_read<0>();                 // the previous tile's stores have read their tiles
         __syncwarp();
+        float amax = 0.f;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             float v[32];
@@ -490,12 +688,15 @@ struct PcaPairPolicy {
             tmem_ld_wait();
             float* tile = reinterpret_cast<float*>(stg + half * 4096);
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-                const int j = half * 32 + 4 * j4;
+            for (int j = 0; j < 32; ++j) { v[j] += bias[half * 32 + j]; amax = fmaxf(amax, fabsf(v[j])); }
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4)
                 *reinterpret_cast<float4*>(tile + lane * 32 + ((j4 ^ (lane & 7)) << 2)) =
-                    make_float4(v[4 * j4] + bias[j], v[4 * j4 + 1] + bias[j + 1], v[4 * j4 + 2] + bias[j + 2], v[4 * j4 + 3] + bias[j + 3]);
-            }
+                    make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
         }
+        // fp16x2 range guard (rows past the end hold the bias only); inf raises it, NaN is dropped by fmaxf and
+        // simply propagates through either precision variant
+        if (p.flag && amax > p.lim) *p.flag = 1;
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
@@ -507,29 +708,41 @@ struct PcaPairPolicy {
 };
 
 // logits + softmax -> Q: pair tile [256 rows x 256 components], W = [-P/2 | mu P] resident
-struct PostPairPolicy {
+// H = false: 3xTF32 operands (tf32 hi / lo).  H = true: fp16x2 -- y scaled by 2^-e and the weights by
+// 4^e / 2^e (exact), both split into fp16 hi + lo: the same 22-bit products at twice the tensor rate;
+// a k-block is then 32 dimensions (64 interleaved fp16 columns) and the resident weights take half the space.
+template <bool H>
+struct PostPairT {
     using Params = PostParams;
     using EpiState = NoEpiState;
     struct Tile { int nkb, mb; };
-    static constexpr bool BF16 = false, MANUAL = true, B_RESIDENT = true, ACC_INIT = false, TILE_SYNC = false;
-    static constexpr int PASSES = 3, BLOCK_N = FV_K, KSTEPS = 4, NKB_RES = FV_2D / 32, STAGES = 2, PGROUPS = 2;
+    static constexpr bool BF16 = false, F16 = H, MANUAL = true, B_RESIDENT = true, ACC_INIT = false, TILE_SYNC = false;
+    static constexpr int KCOLS = H ? 64 : 32;                         // operand columns per 128-B row = per k-block
+    static constexpr int PASSES = 3, BLOCK_N = FV_K, KSTEPS = 4, NKB_RES = FV_2D / KCOLS, STAGES = 2, PGROUPS = 2;
     static constexpr int A_BYTES = 128 * 128, B_BYTES = (FV_K / 2) * 128, TMA_BYTES = 0;
-    // scratch starts 256 B past a 1024-B boundary (barrier block): 768 B pad, then two 1024-aligned
-    // [32 x 32] fp32 TMA-store staging tiles per epilogue warp, then cst
-    static constexpr int STG_OFF = 768, CST_OFF = STG_OFF + 4 * 2 * 4096, SCRATCH_BYTES = CST_OFF + 1024;
-    __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.w_hi); tma_prefetch_desc(&p.w_lo); tma_prefetch_desc(&p.q_map); }
+    // scratch starts 256 B past a 1024-B boundary (barrier block): 768 B pad, then 1024-aligned 4-KB
+    // TMA-store staging tiles per epilogue warp (two [32 x 32] fp32 tiles, or two (hi, lo) pairs of
+    // [32 x 64] fp16 tiles), then cst
+    static constexpr int STG_TILES = H ? 4 : 2;
+    static constexpr int STG_OFF = 768, CST_OFF = STG_OFF + 4 * STG_TILES * 4096, SCRATCH_BYTES = CST_OFF + 1024;
+    __device__ static bool enabled(const Params& p) { return !p.flag || (*p.flag == 0) == H; }
+    __device__ static void prefetch(const Params& p)
+    {
+        tma_prefetch_desc(&p.w_hi); tma_prefetch_desc(&p.w_lo); tma_prefetch_desc(&p.q_map);
+        if (H) { tma_prefetch_desc(&p.qh_map); tma_prefetch_desc(&p.ql_map); }
+    }
     __device__ static int num_tiles(const Params& p) { return p.m_blocks; }
     __device__ static int tile_at(const Params&, int it, int pair, int n_pairs, int n)
     {
         const long long t = (long long)pair + (long long)it * n_pairs;
         return t < n ? (int)t : -1;
     }
-    __device__ static Tile tile(const Params&, int i) { return {FV_2D / 32, i}; }
+    __device__ static Tile tile(const Params&, int i) { return {NKB_RES, i}; }
     __device__ static void load_resident(const Params& p, int rank, uint8_t* res, uint64_t* bar)
     {
         for (int kb = 0; kb < NKB_RES; ++kb) {
-            tma_load_2d_pair(res + (2 * kb) * B_BYTES, &p.w_hi, bar, kb * 32, rank * (FV_K / 2));
-            tma_load_2d_pair(res + (2 * kb + 1) * B_BYTES, &p.w_lo, bar, kb * 32, rank * (FV_K / 2));
+            tma_load_2d_pair(res + (2 * kb) * B_BYTES, &p.w_hi, bar, kb * KCOLS, rank * (FV_K / 2));
+            tma_load_2d_pair(res + (2 * kb + 1) * B_BYTES, &p.w_lo, bar, kb * KCOLS, rank * (FV_K / 2));
         }
     }
     __device__ static void load(const Params&, const Tile&, int, int, uint8_t*, uint8_t*, uint8_t*, uint8_t*, uint64_t*) {}
@@ -539,7 +752,8 @@ struct PostPairPolicy {
     // running sum in TMEM stays at the scale of the final logit -- the tensor core truncates when
     // it accumulates and that error is proportional to the running sum (3x lower FV error than
     // the [y*y | y] order, tools/probe_fv_err.py).  K-block kb holds dimensions [16 kb, 16 kb + 16).
-    struct Regs { float2 v[8]; };
+    // a lane fills one 16-byte chunk of the operand row: two dimensions (tf32) or four (fp16)
+    struct Regs { float4 v[8]; };
     __device__ static void fetch(const Params& p, const Tile& t, int kb, int rank, int pw, int lane, Regs& r)
     {
         const int64_t row0 = (int64_t)t.mb * 256 + rank * 128 + pw * 32;
@@ -547,22 +761,37 @@ struct PostPairPolicy {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int64_t gr = row0 + i * 4 + (lane >> 3);
-            r.v[i] = make_float2(0.f, 0.f);
-            if (gr < p.rows) r.v[i] = __ldg(reinterpret_cast<const float2*>(p.y + gr * FV_D + kb * 16 + c * 2));
+            r.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gr < p.rows) {
+                if constexpr (H) r.v[i] = tc::ldg4(p.y + gr * FV_D + kb * 32 + c * 4);
+                else {
+                    const float2 y2 = __ldg(reinterpret_cast<const float2*>(p.y + gr * FV_D + kb * 16 + c * 2));
+                    r.v[i].x = y2.x; r.v[i].y = y2.y;
+                }
+            }
         }
     }
-    __device__ static void store(const Params&, const Tile&, int, const Regs& r, uint8_t* a_hi, uint8_t* a_lo, int pw, int lane)
+    __device__ static void store(const Params& p, const Tile&, int, const Regs& r, uint8_t* a_hi, uint8_t* a_lo, int pw, int lane)
     {
         const int c = lane & 7;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int row = pw * 32 + i * 4 + (lane >> 3);
-            const float2 y = r.v[i];
-            float4 h, l;
-            tc::split4(make_float4(y.x * y.x, y.x, y.y * y.y, y.y), h, l);
             const uint32_t off = tc::sw128_off(row, c);
-            *reinterpret_cast<float4*>(a_hi + off) = h;
-            *reinterpret_cast<float4*>(a_lo + off) = l;
+            if constexpr (H) {
+                const float a = r.v[i].x * p.sc_y, b = r.v[i].y * p.sc_y, cc = r.v[i].z * p.sc_y, d = r.v[i].w * p.sc_y;
+                const float x[8] = {a * a, a, b * b, b, cc * cc, cc, d * d, d};
+                uint4 h, l;
+                tc::split8_h(x, h, l);
+                *reinterpret_cast<uint4*>(a_hi + off) = h;
+                *reinterpret_cast<uint4*>(a_lo + off) = l;
+            } else {
+                const float4 y = r.v[i];
+                float4 h, l;
+                tc::split4(make_float4(y.x * y.x, y.x, y.y * y.y, y.y), h, l);
+                *reinterpret_cast<float4*>(a_hi + off) = h;
+                *reinterpret_cast<float4*>(a_lo + off) = l;
+            }
         }
     }
     __device__ static void epi_init(const Params& p, uint8_t* scratch, int tid)
@@ -665,8 +894,53 @@ struct PostPairPolicy {
         // written to a 128-byte-swizzled shared-memory tile instead and leaves through a TMA
         // store (rows past the end of the batch are clipped by the tensor map); two tiles per
         // warp, so the stores of one chunk overlap the TMA read of the previous one.
-        uint8_t* stg = scratch + STG_OFF + quarter * (2 * 4096);
+        uint8_t* stg = scratch + STG_OFF + quarter * (STG_TILES * 4096);
         const int wrow0 = (int)((int64_t)t.mb * 256 + rank * 128 + quarter * 32);
+        if (H && p.planes) {
+            // Q * 2^14 split into fp16 hi + lo: what the statistics kernel's TMA loads expect.  A thread owns a
+            // row; 64 components = one 128-byte row of the hi tile and one of the lo tile.
+            const float sc = inv * 16384.f;
+            int buf = 0;
+            tmem_ld32(tmem, va);
+#pragma unroll 1
+            for (int c = 0; c < FV_K; c += 64) {
+                tmem_ld_wait();
+                tmem_ld32(tmem + c + 32, vb);
+                if (lane == 0) tma_store_wait_read<1>();         // the group that last used this tile pair has read it
+                __syncwarp();
+                uint8_t* th = stg + buf * 8192;
+                uint8_t* tl = th + 4096;
+                auto put = [&](const float (&v)[32], int j0) {
+#pragma unroll
+                    for (int j8 = 0; j8 < 4; ++j8) {
+                        float x[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) x[u] = v[8 * j8 + u] * sc;
+                        uint4 h, l;
+                        tc::split8_h(x, h, l);
+                        const uint32_t off = (uint32_t)(lane * 128 + (((j0 + j8) ^ (lane & 7)) << 4));
+                        *reinterpret_cast<uint4*>(th + off) = h;
+                        *reinterpret_cast<uint4*>(tl + off) = l;
+                    }
+                };
+                put(va, 0);
+                tmem_ld_wait();
+                if (c + 64 < FV_K) tmem_ld32(tmem + c + 64, va);
+                put(vb, 4);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&p.qh_map, th, c, wrow0);
+                    tma_store_2d(&p.ql_map, tl, c, wrow0);
+                    tma_store_commit();
+                }
+                buf ^= 1;
+            }
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+            PVS_TPHASE(10, tp3, tme);
+            return;
+        }
         auto store_chunk = [&](const float (&v)[32], int c, int buf) {
             if (lane == 0) tma_store_wait_read<1>();             // the group that last used this tile has read it
             __syncwarp();
@@ -697,6 +971,8 @@ struct PostPairPolicy {
         PVS_TPHASE(10, tp3, tme);
     }
 };
+using PostPairPolicy = PostPairT<false>;
+using Post16PairPolicy = PostPairT<true>;
 }  // namespace tc2
 namespace tc {
 
@@ -735,6 +1011,38 @@ int tc_prepare_model(pvs_model* m)
     if (e != cudaSuccess) { cudaFree(buf); return fail(PVS_ERR_CUDA, "weight split failed: %s", cudaGetErrorString(e)); }
     m->tc0 = buf;
     m->tc1 = buf + n;
+    if (m->kind == PVS_MODEL_GMM_DIAG && m->h_ok) {
+        // fp16x2 weights: interleaved (-P/2 * 4^e, mu P * 2^e) columns, split into fp16 hi + lo on the host
+        std::vector<float> w(n);
+        if (cudaMemcpy(w.data(), m->wcat, n * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess)
+            return fail(PVS_ERR_CUDA, "weight download failed");
+        std::vector<__half> hl(2 * n);
+        const float sq = ldexpf(1.f, 2 * m->h_exp), sl = ldexpf(1.f, m->h_exp);
+        bool ok = true;
+        for (int j = 0; j < FV_K; ++j)
+            for (int i = 0; i < FV_2D; ++i) {
+                const int dd = i >> 1;
+                const float x = (i & 1) ? w[(size_t)j * FV_2D + FV_D + dd] * sl : w[(size_t)j * FV_2D + dd] * sq;
+                const __half h = __float2half_rn(x);
+                hl[(size_t)j * FV_2D + i] = h;
+                hl[n + (size_t)j * FV_2D + i] = __float2half_rn(x - __half2float(h));
+                ok = ok && fabsf(x) < 30000.f;
+            }
+        void* hb = nullptr;
+        if (ok) {
+            PVS_CUDA(cudaMalloc(&hb, 2 * n * sizeof(__half)));
+            if (cudaMemcpy(hb, hl.data(), 2 * n * sizeof(__half), cudaMemcpyHostToDevice) != cudaSuccess) {
+                cudaFree(hb);
+                return fail(PVS_ERR_CUDA, "fp16 weight upload failed");
+            }
+            m->th0 = hb;
+            m->th1 = (const __half*)hb + n;
+        } else {
+            m->h_ok = false;
+        }
+    } else if (m->kind == PVS_MODEL_GMM_DIAG) {
+        m->h_ok = false;
+    }
     return PVS_OK;
 }
 
@@ -751,15 +1059,25 @@ int tc_fv_plan(const pvs_model* g, const pvs_model* pca, int64_t rows, int64_t n
     char* base = (char*)ws;
     auto take = [&](size_t bytes) { void* p = base ? base + off : nullptr; off += align_up(bytes ? bytes : 16, 1024); return p; };
     pl->n_tiles = (int)ceil_div(rows, 128);
+    pl->rows = rows;
     pl->y = pca ? (float*)take((size_t)rows * FV_D * 4) : nullptr;
     pl->q = (float*)take((size_t)rows * FV_K * 4);
     pl->S = (float*)take((size_t)n_images * FV_K * FV_2D * 4);
-    pl->s0part = (float*)take((size_t)n_images * TC_FV_S0_PARTS * FV_K * 4);
+    pl->s0part = (float*)take((size_t)n_images * TC_FV_S0_PARTS * FV_K * 4 + 16);
+    pl->flag = pl->s0part ? (int*)(pl->s0part + (size_t)n_images * TC_FV_S0_PARTS * FV_K) : nullptr;
+    pl->fp16x2 = pca && g->h_ok && g->th0 && !getenv("PVS_FV_NO_FP16X2");
     pl->total = off + 1024;
     return PVS_OK;
 }
 
-int tc_fv_project(const TcFvPlan& pl, const pvs_model* pca, const float* desc, int64_t rows, cudaStream_t st)
+int tc_fv_begin(const TcFvPlan& pl, int64_t n_images, cudaStream_t st)
+{
+    // a producer group only writes its zeroth-order partial when it owned a k-block of the image
+    PVS_CUDA(cudaMemsetAsync(pl.s0part, 0, (size_t)n_images * TC_FV_S0_PARTS * FV_K * 4 + 16, st));
+    return PVS_OK;
+}
+
+int tc_fv_project(const TcFvPlan& pl, const pvs_model* g, const pvs_model* pca, const float* desc, int64_t rows, cudaStream_t st)
 {
     if (rows <= 0 || !pca) return PVS_OK;
     PVS_CHECK(((uintptr_t)desc & 15) == 0, PVS_ERR_BAD_ARG, "descriptor buffer must be 16-byte aligned");
@@ -769,6 +1087,8 @@ int tc_fv_project(const TcFvPlan& pl, const pvs_model* pca, const float* desc, i
     if ((rc = make_tmap_2d(&p.c_lo, pca->tc1, false, pca->d, pca->d_in, pca->d_in, 32, FV_D))) return rc;
     p.x = desc; p.bias = pca->bias; p.y = pl.y; p.rows = rows;
     p.m_blocks = pl.n_tiles; p.nkb = pca->d_in / 32; p.d_in = pca->d_in;
+    p.flag = pl.fp16x2 ? pl.flag : nullptr;
+    p.lim = ldexpf(255.f, g->h_exp);                          // (y 2^-e)^2 must stay below 65504
     if (pca->d_in == 128) {                                   // CTA pairs, C resident (32 rows per CTA)
         if ((rc = make_tmap_2d(&p.c_hi, pca->tc0, false, pca->d, pca->d_in, pca->d_in, 32, FV_D / 2))) return rc;
         if ((rc = make_tmap_2d(&p.c_lo, pca->tc1, false, pca->d, pca->d_in, pca->d_in, 32, FV_D / 2))) return rc;
@@ -792,17 +1112,37 @@ int tc_fv_posterior(const TcFvPlan& pl, const pvs_model* g, const float* y, int6
     if ((rc = make_tmap_2d(&p.q_map, pl.q, false, rows, FV_K, FV_K, 32, 32))) return rc;
     p.y = y; p.cst = g->cst; p.q = pl.q; p.argmax = argmax; p.rows = rows;
     p.m_blocks = (int)ceil_div(rows, 256);                    // CTA pairs: 256-row tiles, W resident
+    if (!pl.fp16x2) return tc2::launch_tc2<tc2::PostPairPolicy>(p, p.m_blocks, st);
+    // fp16x2 kernel (writes Q as fp16 hi / lo planes for the statistics kernel), and behind it the 3xTF32
+    // kernel (fp32 Q in the same buffer) that only runs when the projection raised the range flag
+    PostParams h = p;
+    h.flag = pl.flag; h.sc_y = ldexpf(1.f, -g->h_exp); h.planes = 1;
+    if ((rc = make_tmap_2d(&h.w_hi, g->th0, true, FV_K, FV_2D, FV_2D, 64, FV_K / 2))) return rc;
+    if ((rc = make_tmap_2d(&h.w_lo, g->th1, true, FV_K, FV_2D, FV_2D, 64, FV_K / 2))) return rc;
+    if ((rc = make_tmap_2d(&h.qh_map, pl.q, true, rows, FV_K, FV_K, 64, 32))) return rc;
+    if ((rc = make_tmap_2d(&h.ql_map, (const __half*)pl.q + (size_t)rows * FV_K, true, rows, FV_K, FV_K, 64, 32))) return rc;
+    if ((rc = tc2::launch_tc2<tc2::Post16PairPolicy>(h, h.m_blocks, st))) return rc;
+    p.flag = pl.flag;
     return tc2::launch_tc2<tc2::PostPairPolicy>(p, p.m_blocks, st);
 }
 
-int tc_fv_stats(const TcFvPlan& pl, const float* y, const int64_t* offsets, int64_t n_images, cudaStream_t st)
+int tc_fv_stats(const TcFvPlan& pl, const pvs_model* g, const float* y, const int64_t* offsets, int64_t n_images, cudaStream_t st)
 {
     if (n_images <= 0) return PVS_OK;
     StatsParams p{};
     p.y = y; p.q = pl.q; p.offsets = offsets; p.S = pl.S; p.s0part = pl.s0part; p.n_images = n_images;
-    // a producer group only writes its partial when it owned a k-block of the image
-    PVS_CUDA(cudaMemsetAsync(pl.s0part, 0, (size_t)n_images * TC_FV_S0_PARTS * FV_K * 4, st));
-    return launch_tc<StatsPolicy>(p, (int)n_images, st);
+    if (!pl.fp16x2) return launch_tc<StatsPolicy>(p, (int)n_images, st);
+    // fp16x2 kernel, and behind it the 3xTF32 kernel that only runs when the range flag was raised
+    Stats16Params h{};
+    h.b = p; h.flag = pl.flag;
+    h.sc_y = ldexpf(1.f, -g->h_exp); h.un1 = ldexpf(1.f, g->h_exp - 14); h.un2 = ldexpf(1.f, 2 * g->h_exp - 14);
+    const int64_t rows = pl.rows;
+    int rc;
+    if ((rc = make_tmap_2d(&h.qh_map, pl.q, true, rows, FV_K, FV_K, 64, Stats16Policy::KT))) return rc;
+    if ((rc = make_tmap_2d(&h.ql_map, (const __half*)pl.q + (size_t)rows * FV_K, true, rows, FV_K, FV_K, 64, Stats16Policy::KT))) return rc;
+    if ((rc = make_tmap_2d(&h.y_map, y, false, rows, FV_D, FV_D, 32, Stats16Policy::KT))) return rc;
+    if ((rc = launch_tc<Stats16Policy>(h, (int)n_images, st))) return rc;
+    return launch_tc<StatsGatedPolicy>(h, (int)n_images, st);
 }
 
 // statistics for any D (K = 256) on tensor cores; S rows have pitch 2d, s0 comes as partials

@@ -454,6 +454,45 @@ def test_fv_tensor_path_ragged_batch_vs_oracle(api):
     assert max(errs) <= 1e-4, errs
 
 
+def test_fv_fp16x2_path_and_range_guard(api):
+    """K=256 / D=64 with a PCA runs the posterior / statistics contractions on fp16 hi+lo operands
+    (scaled by powers of two from the mixture model).  A descriptor far outside the model's range
+    raises the device-side flag and the same call is served by the 3xTF32 kernels instead."""
+    import os
+    w = load_weights("gmm_k256_sift_pca")
+    p = load_weights("pca_k256_sift_f2")
+    rng = np.random.default_rng(21)
+    descs = [np.floor(np.clip(np.abs(rng.normal(0, 40, (t, 128))), 0, 255)).astype(np.float32) for t in (700, 33, 2000)]
+    enc = api.enc.FisherVectorEncoder(feature_extractor=api.feat.Descriptors(128),
+                                      weights=api.enc.GMMWeights.OXFORD102_K256_SIFT_PCA)
+    ref = O.fv_encode(descs, w["weights"], w["means"], w["covariances"], w["precisions_cholesky"],
+                      pca=(p["components"], p["mean"]))
+
+    def run(d, no_fp16):
+        if no_fp16:
+            os.environ["PVS_FV_NO_FP16X2"] = "1"
+        try:
+            api.nat.set_path(api.nat.PATH_TENSOR)
+            return enc.encode(d)
+        finally:
+            api.nat.set_path(api.nat.PATH_AUTO)
+            os.environ.pop("PVS_FV_NO_FP16X2", None)
+
+    fast, slow = run(descs, False), run(descs, True)
+    assert rel_l2(fast, ref) <= 1e-4 and rel_l2(slow, ref) <= 1e-4, (rel_l2(fast, ref), rel_l2(slow, ref))
+    assert not np.array_equal(fast, slow), "the fp16x2 kernels did not run"
+    assert rel_l2(fast, slow) <= 5e-5
+    # one descriptor 200x out of range (|y| ~ 1e5 >> 255 * 2^3): the guard must hand the call to 3xTF32
+    wild = [d.copy() for d in descs]
+    wild[1][7] *= 200.0
+    ref_w = O.fv_encode(wild, w["weights"], w["means"], w["covariances"], w["precisions_cholesky"],
+                        pca=(p["components"], p["mean"]))
+    fast_w, slow_w = run(wild, False), run(wild, True)
+    assert np.isfinite(fast_w).all()
+    assert np.array_equal(fast_w, slow_w), "range guard did not fall back to the 3xTF32 kernels"
+    assert rel_l2(fast_w, ref_w) <= 1e-4
+
+
 def test_fv_tensor_path_without_pca_d64(api):
     """K=256, D=64 GMM fed 64-D descriptors directly (no PCA stage)."""
     w = load_weights("gmm_k256_root_sift_pca")
