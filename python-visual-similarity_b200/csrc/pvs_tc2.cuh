@@ -129,8 +129,16 @@ __device__ unsigned long long g_tc2_timing[16];          // [8..15]: policy-defi
 #define PVS_TPHASE(slot, t0, cond)
 #endif
 
+// Optional: static constexpr int EPI_WARPS = 8 -- two epilogue warps per TMEM lane quarter (warps 2..9; the
+// policy splits the accumulator columns between the two and reconciles row reductions through shared memory);
+// the operand producers then start at warp 10.
+template <class P, class = void> struct policy_epi_warps { static constexpr int value = 4; };
+template <class P> struct policy_epi_warps<P, decltype((void)P::EPI_WARPS)> { static constexpr int value = P::EPI_WARPS; };
+
 template <class P>
 struct Layout2 {
+    static constexpr int EW = policy_epi_warps<P>::value;
+    static_assert(EW == 4 || EW == 8, "4 or 8 epilogue warps");
     static constexpr int PARTS = P::PASSES == 3 ? 2 : 1;
     static constexpr int B_STAGE = P::B_RESIDENT ? 0 : PARTS * P::B_BYTES;
     static constexpr int STAGE_BYTES = PARTS * P::A_BYTES + B_STAGE;
@@ -140,7 +148,7 @@ struct Layout2 {
     static constexpr int SMEM_BYTES = 1024 + RING_BYTES + RES_BYTES + BAR_BYTES + P::SCRATCH_BYTES;
     static constexpr int TMEM_COLS = 2 * P::BLOCK_N <= 32 ? 32 : 2 * P::BLOCK_N <= 64 ? 64 : 2 * P::BLOCK_N <= 128 ? 128
                                      : 2 * P::BLOCK_N <= 256 ? 256 : 512;
-    static constexpr int THREADS = P::MANUAL ? 192 + 128 * P::PGROUPS : 192;
+    static constexpr int THREADS = 64 + 32 * EW + (P::MANUAL ? 128 * P::PGROUPS : 0);
     // arrivals per phase on the leader's full barrier
     static constexpr uint32_t FULL_COUNT = (P::TMA_BYTES > 0 ? 1 : 0) + (P::MANUAL ? 8 : 0);
     static_assert(2 * P::BLOCK_N <= 512, "accumulator does not fit TMEM twice");
@@ -184,7 +192,7 @@ tc2_kernel(const __grid_constant__ typename P::Params prm)
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull[a], 1);
-            mbar_init(&tempty[a], 8);
+            mbar_init(&tempty[a], 2 * L::EW);
         }
         mbar_init(bres, 1);
         fence_barrier_init();
@@ -281,13 +289,13 @@ tc2_kernel(const __grid_constant__ typename P::Params prm)
             if (lane == 0) for (int i = 0; i < 3; ++i) atomicAdd(&g_tc2_timing[i], (unsigned long long)timing_acc[i]);
 #endif
         }
-    } else if (warp >= 6) {
+    } else if (warp >= 2 + L::EW) {
         if constexpr (P::MANUAL) {
             // Operand producers.  fetch() only issues the global loads of a k-block into
             // registers, store() splits and writes the swizzled tiles.  The loads of the NEXT
             // k-block of this group are issued before waiting for its stage to drain, so the
             // global-memory latency overlaps the wait instead of following it.
-            const int pw = (warp - 6) & 3, grp = (warp - 6) >> 2;
+            const int pw = (warp - 2 - L::EW) & 3, grp = (warp - 2 - L::EW) >> 2;
             long long idx = 0;                               // running k-block index over all tiles of this pair
             int it = 0, kb = 0;
             int t = P::tile_at(prm, 0, pair, n_pairs, n_tiles);
@@ -329,7 +337,7 @@ tc2_kernel(const __grid_constant__ typename P::Params prm)
             }
 #ifdef PVS_TIMING
             PVS_TACC(6, t_role);
-            if (warp == 6 && lane == 0 && rank == 0) for (int i = 5; i < 7; ++i) atomicAdd(&g_tc2_timing[i], (unsigned long long)timing_acc[i]);
+            if (warp == 2 + L::EW && lane == 0 && rank == 0) for (int i = 5; i < 7; ++i) atomicAdd(&g_tc2_timing[i], (unsigned long long)timing_acc[i]);
 #endif
         }
     } else {

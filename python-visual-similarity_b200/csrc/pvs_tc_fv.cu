@@ -718,13 +718,18 @@ struct PostPairT {
     struct Tile { int nkb, mb; };
     static constexpr bool BF16 = false, F16 = H, MANUAL = true, B_RESIDENT = true, ACC_INIT = false, TILE_SYNC = false;
     static constexpr int KCOLS = H ? 64 : 32;                         // operand columns per 128-B row = per k-block
-    static constexpr int PASSES = 3, BLOCK_N = FV_K, KSTEPS = 4, NKB_RES = FV_2D / KCOLS, STAGES = 2, PGROUPS = 2;
+    static constexpr int PASSES = 3, BLOCK_N = FV_K, KSTEPS = 4, NKB_RES = FV_2D / KCOLS, STAGES = 2;
+    // fp16x2: one producer group (a tile is only two k-blocks) keeps the CTA at 448 threads, i.e. enough registers
+    // for the eight epilogue warps not to spill
+    static constexpr int PGROUPS = H ? 1 : 2;
     static constexpr int A_BYTES = 128 * 128, B_BYTES = (FV_K / 2) * 128, TMA_BYTES = 0;
-    // scratch starts 256 B past a 1024-B boundary (barrier block): 768 B pad, then 1024-aligned 4-KB
-    // TMA-store staging tiles per epilogue warp (two [32 x 32] fp32 tiles, or two (hi, lo) pairs of
-    // [32 x 64] fp16 tiles), then cst
-    static constexpr int STG_TILES = H ? 4 : 2;
-    static constexpr int STG_OFF = 768, CST_OFF = STG_OFF + 4 * STG_TILES * 4096, SCRATCH_BYTES = CST_OFF + 1024;
+    // scratch starts 256 B past a 1024-B boundary (barrier block): 768 B pad, then two 1024-aligned 4-KB
+    // TMA-store staging tiles per epilogue warp (two [32 x 32] fp32 tiles, or a (hi, lo) pair of
+    // [32 x 64] fp16 tiles), then cst and the exchange area of the warp pairs
+    static constexpr int EPI_WARPS = H ? 8 : 4;                       // (the 3xTF32 variant has no shared memory left for eight)
+    static constexpr int NH = EPI_WARPS / 4, CW = FV_K / NH;          // column halves per lane quarter, columns per warp
+    static constexpr int STG_OFF = 768, CST_OFF = STG_OFF + EPI_WARPS * 8192, XCH_OFF = CST_OFF + 1024,
+                         SCRATCH_BYTES = XCH_OFF + (NH == 2 ? 3072 : 0);
     __device__ static bool enabled(const Params& p) { return !p.flag || (*p.flag == 0) == H; }
     __device__ static void prefetch(const Params& p)
     {
@@ -794,40 +799,48 @@ struct PostPairT {
             }
         }
     }
+    // Eight epilogue warps: the two warps of a TMEM lane quarter split the 256 components of their 32 rows
+    // (half h takes columns [128 h, 128 h + 128)) and reconcile the row maximum and the row sum through shared
+    // memory.  One warp per scheduler and row was latency-bound (dependent TMEM load -> reduce chains); two
+    // independent warps per scheduler halve the time a tile spends in the epilogue.
+    __device__ static void pair_barrier(int quarter) { asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory"); }
     __device__ static void epi_init(const Params& p, uint8_t* scratch, int tid)
     {
         float* c = reinterpret_cast<float*>(scratch + CST_OFF);
-        c[tid] = p.cst[tid];
-        c[tid + 128] = p.cst[tid + 128];
-        epi_barrier();
+        for (int i = tid; i < FV_K; i += 32 * EPI_WARPS) c[i] = p.cst[i];
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
     }
     __device__ static void epi_begin(const Params&, const Tile&, EpiState&, int, int, int) {}
     __device__ static void epilogue(const Params& p, const Tile& t, int rank, uint32_t tmem, int quarter, int lane,
                                     uint8_t* scratch, EpiState&)
     {
+        const int half = NH == 2 ? (((int)threadIdx.x >> 5) - 2) >> 2 : 0;
+        const int c0 = half * CW;
         const int64_t row = (int64_t)t.mb * 256 + rank * 128 + quarter * 32 + lane;
         const bool valid = row < p.rows;
         // The per-component constant is added here in fp32 rather than pre-loaded into the
         // accumulator: the tensor core truncates when it accumulates, relative to the running
         // sum, and starting that sum at |cst| ~ 10^2 cost a factor 3.6 in FV accuracy.
-        // Only one epilogue warp runs per scheduler, so every pass keeps the
-        // TMEM load of the next 32 columns in flight while it works on the current ones and
-        // splits its reductions over four independent chains.
-        // pass 1: row maximum (arg-max only when the caller asked for it)
+        // Every pass keeps the TMEM load of the next 32 columns in flight while it works on the
+        // current ones and splits its reductions over four independent chains.
         float va[32], vb[32];
-        float mx = -INFINITY;
-        int mi = 0;
         const float* cstv = reinterpret_cast<const float*>(scratch + CST_OFF);
+        // [2 halves][max, arg-max, sum][32 rows]: three slots, so that every write is separated from the
+        // partner's last read of the same slot by a pair barrier
+        float* xch = reinterpret_cast<float*>(scratch + XCH_OFF) + quarter * 192;
         auto addc = [&](float (&v)[32], int c) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] += cstv[c + j];
         };
-        const bool tme = quarter == 0 && lane == 0 && rank == 0;
+        const bool tme = quarter == 0 && lane == 0 && rank == 0 && half == 0;
         (void)tme;
         PVS_T0(tp1);
+        // pass 1: maximum of this warp's 128 columns (arg-max only when the caller asked for it)
+        float mx = -INFINITY;
+        int mi = 0;
         if (p.argmax) {
 #pragma unroll 1
-            for (int c = 0; c < FV_K; c += 32) {
+            for (int c = c0; c < c0 + CW; c += 32) {
                 tmem_ld32(tmem + c, va);
                 tmem_ld_wait();
                 addc(va, c);
@@ -837,21 +850,30 @@ struct PostPairT {
             }
         } else {
             float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-            tmem_ld32(tmem, va);
+            tmem_ld32(tmem + c0, va);
 #pragma unroll 1
-            for (int c = 0; c < FV_K; c += 64) {
+            for (int c = c0; c < c0 + CW; c += 64) {
                 tmem_ld_wait();
                 tmem_ld32(tmem + c + 32, vb);
                 addc(va, c);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], va[j]);
                 tmem_ld_wait();
-                if (c + 64 < FV_K) tmem_ld32(tmem + c + 64, va);
+                if (c + 64 < c0 + CW) tmem_ld32(tmem + c + 64, va);
                 addc(vb, c + 32);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], vb[j]);
             }
             mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        }
+        if constexpr (NH == 2) {
+            xch[half * 96 + lane] = mx;
+            xch[half * 96 + 32 + lane] = __int_as_float(mi);
+            pair_barrier(quarter);
+            const float omx = xch[(half ^ 1) * 96 + lane];
+            const int omi = __float_as_int(xch[(half ^ 1) * 96 + 32 + lane]);
+            // the lower half wins ties (lowest index), like one scan over all 256 columns
+            if (half == 0 ? omx > mx : omx >= mx) { mx = omx; mi = omi; }
         }
         PVS_TPHASE(8, tp1, tme);
         PVS_T0(tp2);
@@ -870,63 +892,82 @@ struct PostPairT {
                 s4[j & 3] += e;
             }
         };
-        tmem_ld32(tmem, va);
+        tmem_ld32(tmem + c0, va);
 #pragma unroll 1
-        for (int c = 0; c < FV_K; c += 64) {
+        for (int c = c0; c < c0 + CW; c += 64) {
             tmem_ld_wait();
             tmem_ld32(tmem + c + 32, vb);                      // (tcgen05.st reads its registers at issue)
             addc(va, c);
             exp_chunk(va);
             tmem_st32(tmem + c, va);
             tmem_ld_wait();
-            if (c + 64 < FV_K) tmem_ld32(tmem + c + 64, va);
+            if (c + 64 < c0 + CW) tmem_ld32(tmem + c + 64, va);
             addc(vb, c + 32);
             exp_chunk(vb);
             tmem_st32(tmem + c + 32, vb);
         }
-        tmem_st_wait();
+        const float spart = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+        float inv;
+        if constexpr (NH == 2) {
+            xch[half * 96 + 64 + lane] = spart;
+            tmem_st_wait();
+            pair_barrier(quarter);
+            const float s_lo = half == 0 ? spart : xch[64 + lane], s_hi = half == 0 ? xch[96 + 64 + lane] : spart;
+            inv = 1.f / (s_lo + s_hi);                         // same association in both warps
+        } else {
+            tmem_st_wait();
+            inv = 1.f / spart;
+        }
         PVS_TPHASE(9, tp2, tme);
         PVS_T0(tp3);
-        const float inv = 1.f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
-        if (valid && p.argmax) p.argmax[row] = mi;
+        if (valid && p.argmax && half == 0) p.argmax[row] = mi;
         // pass 3: q = e / sum.  A thread owns a row, so storing straight from registers would
-        // scatter 16-byte pieces over 32 rows per instruction.  Each [32 rows x 32 cols] chunk is
-        // written to a 128-byte-swizzled shared-memory tile instead and leaves through a TMA
-        // store (rows past the end of the batch are clipped by the tensor map); two tiles per
-        // warp, so the stores of one chunk overlap the TMA read of the previous one.
-        uint8_t* stg = scratch + STG_OFF + quarter * (STG_TILES * 4096);
+        // scatter 16-byte pieces over 32 rows per instruction.  Chunks are written to 128-byte-swizzled
+        // shared-memory tiles instead and leave through TMA stores (rows past the end of the batch are
+        // clipped by the tensor map).
+        uint8_t* stg = scratch + STG_OFF + (half * 4 + quarter) * 8192;
+        static_assert(H || NH == 1, "the fp32 store path below assumes one warp per lane quarter");
         const int wrow0 = (int)((int64_t)t.mb * 256 + rank * 128 + quarter * 32);
         if (H && p.planes) {
-            // Q * 2^14 split into fp16 hi + lo: what the statistics kernel's TMA loads expect.  A thread owns a
-            // row; 64 components = one 128-byte row of the hi tile and one of the lo tile.
+            // Q * 2^14 split into fp16 hi + lo: what the statistics kernel's TMA loads expect.  64 components
+            // = one 128-byte row of the hi tile and one of the lo tile; two chunks per warp and tile.
             const float sc = inv * 16384.f;
-            int buf = 0;
-            tmem_ld32(tmem, va);
+            uint8_t* th = stg;
+            uint8_t* tl = stg + 4096;
+            // eight values at a time: convert into one 16-byte chunk of the hi and of the lo row
+            auto conv8 = [&](const float (&v)[32], int j8, uint4& h, uint4& l) {
+                float x[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) x[u] = v[8 * j8 + u] * sc;
+                tc::split8_h(x, h, l);
+            };
+            auto put8 = [&](int j, const uint4& h, const uint4& l) {
+                const uint32_t off = (uint32_t)(lane * 128 + ((j ^ (lane & 7)) << 4));
+                *reinterpret_cast<uint4*>(th + off) = h;
+                *reinterpret_cast<uint4*>(tl + off) = l;
+            };
+            tmem_ld32(tmem + c0, va);
 #pragma unroll 1
-            for (int c = 0; c < FV_K; c += 64) {
+            for (int c = c0; c < c0 + CW; c += 64) {
                 tmem_ld_wait();
                 tmem_ld32(tmem + c + 32, vb);
-                if (lane == 0) tma_store_wait_read<1>();         // the group that last used this tile pair has read it
+                // the first 32 columns are converted BEFORE waiting for the previous chunk's TMA stores to
+                // have read the tiles, so that wait overlaps the conversion
+                uint4 ha[4], la[4];
+#pragma unroll
+                for (int j8 = 0; j8 < 4; ++j8) conv8(va, j8, ha[j8], la[j8]);
+                if (lane == 0) tma_store_wait_read<0>();
                 __syncwarp();
-                uint8_t* th = stg + buf * 8192;
-                uint8_t* tl = th + 4096;
-                auto put = [&](const float (&v)[32], int j0) {
 #pragma unroll
-                    for (int j8 = 0; j8 < 4; ++j8) {
-                        float x[8];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) x[u] = v[8 * j8 + u] * sc;
-                        uint4 h, l;
-                        tc::split8_h(x, h, l);
-                        const uint32_t off = (uint32_t)(lane * 128 + (((j0 + j8) ^ (lane & 7)) << 4));
-                        *reinterpret_cast<uint4*>(th + off) = h;
-                        *reinterpret_cast<uint4*>(tl + off) = l;
-                    }
-                };
-                put(va, 0);
+                for (int j8 = 0; j8 < 4; ++j8) put8(j8, ha[j8], la[j8]);
                 tmem_ld_wait();
-                if (c + 64 < FV_K) tmem_ld32(tmem + c + 64, va);
-                put(vb, 4);
+                if (c + 64 < c0 + CW) tmem_ld32(tmem + c + 64, va);
+#pragma unroll
+                for (int j8 = 0; j8 < 4; ++j8) {
+                    uint4 h, l;
+                    conv8(vb, j8, h, l);
+                    put8(4 + j8, h, l);
+                }
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) {
@@ -934,12 +975,9 @@ struct PostPairT {
                     tma_store_2d(&p.ql_map, tl, c, wrow0);
                     tma_store_commit();
                 }
-                buf ^= 1;
             }
-            if (lane == 0) tma_store_wait_read<0>();
-            __syncwarp();
             PVS_TPHASE(10, tp3, tme);
-            return;
+            return;                                            // (the tiles are waited for before their next use)
         }
         auto store_chunk = [&](const float (&v)[32], int c, int buf) {
             if (lane == 0) tma_store_wait_read<1>();             // the group that last used this tile has read it
@@ -956,18 +994,16 @@ struct PostPairT {
                 tma_store_commit();
             }
         };
-        tmem_ld32(tmem, va);
+        tmem_ld32(tmem + c0, va);
 #pragma unroll 1
-        for (int c = 0; c < FV_K; c += 64) {
+        for (int c = c0; c < c0 + CW; c += 64) {
             tmem_ld_wait();
             tmem_ld32(tmem + c + 32, vb);
             store_chunk(va, c, 0);
             tmem_ld_wait();
-            if (c + 64 < FV_K) tmem_ld32(tmem + c + 64, va);
+            if (c + 64 < c0 + CW) tmem_ld32(tmem + c + 64, va);
             store_chunk(vb, c + 32, 1);
         }
-        if (lane == 0) tma_store_wait_read<0>();                 // tiles are free again (and valid until read)
-        __syncwarp();
         PVS_TPHASE(10, tp3, tme);
     }
 };
