@@ -359,31 +359,41 @@ def run_ours(args):
     dominant = max(stages.items(), key=lambda kv: kv[1][0]) if stages else (None, (0.0, 0))
     flops_per_image = {"pca_project": 2 * T * d_in * D, "gmm_logits": 2 * T * K * 2 * D,
                        "fv_stats": 2 * T * K * 2 * D, "tc_fv_posterior": 2 * T * K * 2 * D,
-                       "tc_fv_stats": 2 * T * K * 2 * D}
-    bytes_per_image = {"gmm_softmax": 2 * T * K * 4, "fv_finalize": K * (2 * D + 1) * 4 + out_dim * 4 * 3}
+                       "tc_fv_stats": 2 * T * K * 2 * D, "tc_fv_project": 2 * T * d_in * D}
+    # algorithmic HBM bytes per image of each kernel: what its interface makes it move
+    bytes_per_image = {"gmm_softmax": 2 * T * K * 4, "fv_finalize": K * (2 * D + 1) * 4 + out_dim * 4 * 3,
+                       "tc_fv_project": T * (d_in + D) * 4,                    # X in, Y out
+                       "tc_fv_posterior": T * (D + K) * 4,                     # Y in, Q out (fp16 hi + lo planes = 4 B)
+                       "tc_fv_stats": T * (D + K) * 4 + K * 2 * D * 4}         # Q + Y in, S out
+    # The fp16x2 kernels (three kind::f16 MMAs per product on power-of-two-scaled fp16 hi + lo operands) need
+    # half the tensor time of 3xTF32, which puts posterior / statistics / projection on the HBM roofline:
+    # they stream Q (1 KB per descriptor) through HBM.  The tensor fraction is reported beside it.
+    hbm_bound = {"tc_fv_project", "tc_fv_posterior", "tc_fv_stats", "gmm_softmax", "fv_finalize"}
     # DRAM bytes per image of each kernel from the committed `ncu --set full` capture
-    # (profiles/ncu_fv_r01b.txt: dram read + write per launch of 592 images)
-    ncu_dram_bytes_per_image = {"tc_fv_project": (0.606374e9 + 0.268744e9) / 592, "tc_fv_posterior": (0.303465e9 + 1.153728e9) / 592,
-                                "tc_fv_stats": (1.515914e9 + 0.070594e9) / 592}
+    # (profiles/ncu_fv_r01c.txt: dram read + write per launch of 592 images)
+    ncu_dram_bytes_per_image = {"tc_fv_project": (0.606463e9 + 0.270842e9) / 592, "tc_fv_posterior": NCU_POST_BYTES / 592,
+                                "tc_fv_stats": (1.515643e9 + 0.063587e9) / 592}
     roofline = None
     if dominant[0]:
         name, (ms, n) = dominant
         per_launch_ms = ms / n
         imgs_per_launch = n_img * prof_steps / n
-        if name in flops_per_image:
-            ach = flops_per_image[name] * imgs_per_launch / (per_launch_ms / 1e3) / 1e12
-            peak = pk["bf16_tflops_sustained"]
-            traffic = ncu_dram_bytes_per_image.get(name)
-            roofline = {"bound": "tensor", "kernel": name, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                        "frac": ach / peak, "traffic": traffic * imgs_per_launch if traffic else None,
-                        "peak_source": f"bf16 dense sustained, {pk['source']} (kernel runs inside a long step)",
-                        "note": "fp32-accurate 3xTF32 contraction: three tf32 MMAs per algorithmic product, so the "
-                                "ceiling of this kernel is peak/6; frac_of_3xtf32_ceiling = frac * 6",
-                        "frac_of_3xtf32_ceiling": 6 * ach / peak}
-        else:
+        traffic = ncu_dram_bytes_per_image.get(name)
+        tflops = flops_per_image.get(name, 0) * imgs_per_launch / (per_launch_ms / 1e3) / 1e12
+        if name in hbm_bound:
             ach = bytes_per_image.get(name, 0) * imgs_per_launch / (per_launch_ms / 1e3) / 1e9
             roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                        "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": f"hbm copy, {pk['source']}"}
+                        "frac": ach / pk["hbm_gbs"], "traffic": traffic * imgs_per_launch if traffic else None,
+                        "peak_source": f"hbm copy, {pk['source']}",
+                        "algorithmic_bytes_per_launch": bytes_per_image.get(name, 0) * imgs_per_launch}
+            if tflops:
+                roofline["tensor"] = {"achieved_tflops": tflops, "frac_of_bf16_sustained": tflops / pk["bf16_tflops_sustained"],
+                                      "note": "fp16x2: three kind::f16 MMAs per algorithmic product (ceiling = peak / 3)"}
+        else:
+            peak = pk["bf16_tflops_sustained"]
+            roofline = {"bound": "tensor", "kernel": name, "achieved": tflops, "peak": peak, "unit": "TFLOP/s",
+                        "frac": tflops / peak, "traffic": traffic * imgs_per_launch if traffic else None,
+                        "peak_source": f"bf16 dense sustained, {pk['source']} (kernel runs inside a long step)"}
         roofline["kernel_ms_per_launch"] = per_launch_ms
         roofline["kernel_share_of_step"] = ms / sum(v[0] for v in stages.values())
         roofline["timing"] = f"{prof_steps} extra single-stream step(s), CUDA events around each launch"
@@ -425,6 +435,9 @@ def run_ours(args):
             "path_hbm": {"algorithmic_bytes_per_image": alg_bytes, "achieved_gbs": path_gbs,
                          "frac_of_hbm_peak": path_gbs / pk["hbm_gbs"]},
             "stages_ms": {k: round(v[0] / max(prof_steps, 1), 4) for k, v in stages.items()},
+            # algorithmic bytes of each stage / its single-stream time, as a fraction of the measured HBM peak
+            "stages_hbm_frac": {k: round(bytes_per_image[k] * n_img / (v[0] / max(prof_steps, 1) / 1e3) / 1e9 / pk["hbm_gbs"], 4)
+                                for k, v in stages.items() if k in bytes_per_image and v[0] > 0},
             "cpu_baseline": cpu,
             "extra": extra,
             "clocks": clocks.summary(),
@@ -434,6 +447,10 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# DRAM read + write bytes of one posterior launch (592 images) in the committed ncu capture
+NCU_POST_BYTES = 0.303380e9 + 1.258173e9
 
 
 def main():

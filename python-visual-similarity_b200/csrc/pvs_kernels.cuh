@@ -61,6 +61,7 @@ struct TcFvPlan {
     float* y;                    // [rows, 64] projected descriptors (NULL without PCA: y = input)
     float* q;                    // [rows, 256] posteriors
     float* S;                    // [n_images, 256, 128] first/second-order sums / T
+    float* rinv;                 // [rows + 16, 4] fp16x2 path: per-descriptor softmax normaliser 1 / sum_k e (16-byte slots)
     float* s0part;               // [n_images, TC_FV_S0_PARTS, 256] raw zeroth-order partial sums
     int* flag;                   // right behind s0part (one memset clears both): raised by the projection when
                                  // some |y| leaves the fp16x2 operand range -> the 3xTF32 kernels do the work

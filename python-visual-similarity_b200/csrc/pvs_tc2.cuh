@@ -135,6 +135,10 @@ __device__ unsigned long long g_tc2_timing[16];          // [8..15]: policy-defi
 template <class P, class = void> struct policy_epi_warps { static constexpr int value = 4; };
 template <class P> struct policy_epi_warps<P, decltype((void)P::EPI_WARPS)> { static constexpr int value = P::EPI_WARPS; };
 
+// Optional: static constexpr bool PREFETCH2 = true -- producers keep two k-blocks of global loads in flight
+template <class P, class = void> struct policy_prefetch2 { static constexpr bool value = false; };
+template <class P> struct policy_prefetch2<P, decltype((void)P::PREFETCH2)> { static constexpr bool value = P::PREFETCH2; };
+
 template <class P>
 struct Layout2 {
     static constexpr int EW = policy_epi_warps<P>::value;
@@ -296,44 +300,74 @@ tc2_kernel(const __grid_constant__ typename P::Params prm)
             // k-block of this group are issued before waiting for its stage to drain, so the
             // global-memory latency overlaps the wait instead of following it.
             const int pw = (warp - 2 - L::EW) & 3, grp = (warp - 2 - L::EW) >> 2;
-            long long idx = 0;                               // running k-block index over all tiles of this pair
-            int it = 0, kb = 0;
-            int t = P::tile_at(prm, 0, pair, n_pairs, n_tiles);
-            typename P::Tile tl{};
-            if (t >= 0) tl = P::tile(prm, t);
-            auto seek = [&]() {                              // advance to the next k-block owned by this group
-                while (t >= 0) {
-                    if (kb >= tl.nkb) {
-                        ++it; kb = 0;
-                        t = P::tile_at(prm, it, pair, n_pairs, n_tiles);
-                        if (t >= 0) tl = P::tile(prm, t);
+            // position of a k-block in this pair's stream of (tile, k-block) pairs; idx = running index
+            struct Pos { long long idx; int it, kb, t; typename P::Tile tl; };
+            auto seek = [&](Pos& q) {                        // settle on the next k-block owned by this group
+                while (q.t >= 0) {
+                    if (q.kb >= q.tl.nkb) {
+                        ++q.it; q.kb = 0;
+                        q.t = P::tile_at(prm, q.it, pair, n_pairs, n_tiles);
+                        if (q.t >= 0) q.tl = P::tile(prm, q.t);
                         continue;
                     }
-                    if ((int)(idx % P::PGROUPS) == grp) return;
-                    ++kb; ++idx;
+                    if ((int)(q.idx % P::PGROUPS) == grp) return;
+                    ++q.kb; ++q.idx;
                 }
             };
-            seek();
-            typename P::Regs cur;
+            auto next = [&](Pos& q) { ++q.kb; ++q.idx; seek(q); };
+            Pos s{0, 0, 0, P::tile_at(prm, 0, pair, n_pairs, n_tiles), {}};
+            if (s.t >= 0) s.tl = P::tile(prm, s.t);
+            seek(s);
 #ifdef PVS_TIMING
             long long timing_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
             PVS_T0(t_role);
-            if (t >= 0) P::fetch(prm, tl, kb, rank, pw, lane, cur);
-            while (t >= 0) {
-                const int stage = (int)(idx % P::STAGES);
-                const uint32_t phase = (uint32_t)((idx / P::STAGES) & 1);
+            auto publish = [&](const Pos& q, const typename P::Regs& r) {
+                const int stage = (int)(q.idx % P::STAGES);
+                const uint32_t phase = (uint32_t)((q.idx / P::STAGES) & 1);
                 PVS_T0(t_em);
                 mbar_wait_cl(&empty[stage], phase ^ 1);
                 PVS_TACC(5, t_em);
                 uint8_t* sp = smem + stage * L::STAGE_BYTES;
-                P::store(prm, tl, kb, cur, sp, sp + P::A_BYTES, pw, lane);
+                P::store(prm, q.tl, q.kb, r, sp, sp + P::A_BYTES, pw, lane);
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_leader(&full[stage]);
-                ++kb; ++idx;
-                seek();
-                if (t >= 0) P::fetch(prm, tl, kb, rank, pw, lane, cur);
+            };
+            if constexpr (policy_prefetch2<P>::value) {
+                // two k-blocks of global loads in flight per group (register double buffer): with a single
+                // group and short tiles one block in flight leaves the loads latency-bound
+                typename P::Regs r0, r1;
+                Pos f = s;
+                if (s.t >= 0) {
+                    P::fetch(prm, f.tl, f.kb, rank, pw, lane, r0);
+                    next(f);
+                    if (f.t >= 0) P::fetch(prm, f.tl, f.kb, rank, pw, lane, r1);
+                }
+                while (s.t >= 0) {
+                    publish(s, r0);
+                    next(s);
+                    if (s.t < 0) break;
+                    next(f);
+                    if (f.t >= 0) P::fetch(prm, f.tl, f.kb, rank, pw, lane, r0);
+                    publish(s, r1);
+                    next(s);
+                    if (s.t < 0) break;
+                    next(f);
+                    if (f.t >= 0) P::fetch(prm, f.tl, f.kb, rank, pw, lane, r1);
+                }
+            } else {
+                // Operand producers.  fetch() only issues the global loads of a k-block into
+                // registers, store() splits and writes the swizzled tiles.  The loads of the NEXT
+                // k-block of this group are issued before waiting for its stage to drain, so the
+                // global-memory latency overlaps the wait instead of following it.
+                typename P::Regs cur;
+                if (s.t >= 0) P::fetch(prm, s.tl, s.kb, rank, pw, lane, cur);
+                while (s.t >= 0) {
+                    publish(s, cur);
+                    next(s);
+                    if (s.t >= 0) P::fetch(prm, s.tl, s.kb, rank, pw, lane, cur);
+                }
             }
 #ifdef PVS_TIMING
             PVS_TACC(6, t_role);

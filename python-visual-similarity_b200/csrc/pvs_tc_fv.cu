@@ -170,6 +170,7 @@ struct PostParams {
                                               // the 3xTF32 variant when it is not
     float sc_y;                               // 2^-e (fp16x2 variant)
     int planes;                               // fp16x2 variant: write the fp16 planes instead of fp32 Q
+    float* rinv;                              // planes: [rows, 4] per-row normaliser 1 / sum_k exp(l - max) (slot 0 of 16 bytes)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -314,6 +315,7 @@ struct Stats16Params {
     CUtensorMap qh_map, ql_map;               // Q * 2^14 as fp16 hi / lo planes [rows, 256], box 64 cols x 16 rows
     CUtensorMap y_map;                        // Y [rows, 64] fp32, box 32 cols x 16 rows
     StatsParams b;
+    const float* rinv;                        // [rows + 16, 4]: per-descriptor softmax normaliser (slot 0 of 16 bytes)
     const int* flag;                          // != 0: operands out of fp16 range -> this kernel does nothing
     float sc_y, un1, un2;                     // 2^-e, 2^(e-14), 2^(2e-14)
 };
@@ -334,7 +336,10 @@ __device__ __forceinline__ void split8_h(const float (&x)[8], uint4& hi, uint4& 
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// The posterior kernel leaves Q already scaled and split (two fp16 planes), so the Q operand of a
+// The posterior kernel leaves e' = 2^14 exp(l - max) split into two fp16 planes plus the per-descriptor
+// normaliser r = 1 / sum_k exp(l - max) (q = r e' / 2^14): r is folded into the [y'^2 | y'] operand rows and
+// into the zeroth-order sums here, which saved the posterior kernel a pass over its accumulator.
+// The planes are already scaled and split, so the Q operand of a
 // stage is eight TMA boxes straight into the swizzled MN-major tiles -- no registers, no conversion,
 // as many stages in flight as shared memory holds.  Y (256 B per descriptor) arrives by TMA as fp32
 // in a staging tile of the stage; four converter warps scale / square / split it into the A tiles,
@@ -351,11 +356,13 @@ struct Stats16Policy {
     static constexpr int A_LBO = KT * 128, B_LBO = KT * 128;          // one [KT rows x 128 B] block per 64 columns
     static constexpr int A_BYTES = (FV_2D / 64) * A_LBO, B_BYTES = (FV_K / 64) * B_LBO, SCRATCH_BYTES = 0;
     static constexpr int Y_STAGE = KT * FV_D * 4;                     // two [16 x 32] fp32 boxes
-    static constexpr int STAGE_EXTRA = Y_STAGE + 1024;                // + the policy's mbarrier
-    static constexpr int TMA_BYTES = 2 * B_BYTES + Y_STAGE;
+    // extra region of a stage: Y staging | r staging (16 x 16 B) | cleaned r (16 floats) | the policy's mbarrier
+    static constexpr int R_OFF = Y_STAGE, RC_OFF = Y_STAGE + KT * 16, BAR_OFF = Y_STAGE + 512;
+    static constexpr int STAGE_EXTRA = Y_STAGE + 1024;
+    static constexpr int TMA_BYTES = 2 * B_BYTES + Y_STAGE + KT * 16;
     __device__ static bool enabled(const Params& p) { return *p.flag == 0; }
     __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.qh_map); tma_prefetch_desc(&p.ql_map); tma_prefetch_desc(&p.y_map); }
-    __device__ static void init_stage(uint8_t* extra) { mbar_init(reinterpret_cast<uint64_t*>(extra + Y_STAGE), 1); }
+    __device__ static void init_stage(uint8_t* extra) { mbar_init(reinterpret_cast<uint64_t*>(extra + BAR_OFF), 1); }
     __device__ static int num_tiles(const Params& p) { return (int)p.b.n_images; }
     __device__ static int tile_at(const Params&, int it, int n) { return strided_tile(it, n); }
     __device__ static Tile tile(const Params& p, int i)
@@ -367,9 +374,10 @@ struct Stats16Policy {
     __device__ static void load(const Params& p, const Tile& t, int kb, uint8_t*, uint8_t*, uint8_t* b_hi, uint8_t* b_lo, uint64_t*)
     {
         uint8_t* extra = b_lo + B_BYTES;
-        uint64_t* bar = reinterpret_cast<uint64_t*>(extra + Y_STAGE);
+        uint64_t* bar = reinterpret_cast<uint64_t*>(extra + BAR_OFF);
         const int row = (int)(t.r0 + (int64_t)kb * KT);
         mbar_expect_tx(bar, TMA_BYTES);
+        bulk_load_1d(extra + R_OFF, p.rinv + (int64_t)row * 4, KT * 16, bar);     // (the array is padded by 16 rows)
 #pragma unroll
         for (int cb = 0; cb < FV_K / 64; ++cb) {
             tma_load_2d(b_hi + cb * B_LBO, &p.qh_map, bar, cb * 64, row);
@@ -385,7 +393,7 @@ struct Stats16Policy {
                                  uint8_t* b_hi, uint8_t* b_lo, int pw, int, int lane, PState& ps)
     {
         uint8_t* extra = b_lo + B_BYTES;
-        mbar_wait(reinterpret_cast<uint64_t*>(extra + Y_STAGE), (ps.uses / STAGES) & 1u);
+        mbar_wait(reinterpret_cast<uint64_t*>(extra + BAR_OFF), (ps.uses / STAGES) & 1u);
         ++ps.uses;
         const int valid = t.t - kb * KT;                   // rows of this stage that belong to the image
         // a lane owns 8 dims of one row: row r = 4 pw + lane / 8, dims [8 (lane % 8), +8)
@@ -394,12 +402,14 @@ struct Stats16Policy {
         const uint8_t* src = extra + blk * (Y_STAGE / 2);
         float4 y0 = *reinterpret_cast<const float4*>(src + sw128_off(r, c0));
         float4 y1 = *reinterpret_cast<const float4*>(src + sw128_off(r, c0 + 1));
-        if (r >= valid) y0 = y1 = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float v[8] = {y0.x * p.sc_y, y0.y * p.sc_y, y0.z * p.sc_y, y0.w * p.sc_y,
+        float rn = *reinterpret_cast<const float*>(extra + R_OFF + r * 16);
+        if (r >= valid) { y0 = y1 = make_float4(0.f, 0.f, 0.f, 0.f); rn = 0.f; }
+        if ((lane & 7) == 0) *reinterpret_cast<float*>(extra + RC_OFF + r * 4) = rn;   // for the zeroth-order sums
+        const float w[8] = {y0.x * p.sc_y, y0.y * p.sc_y, y0.z * p.sc_y, y0.w * p.sc_y,
                             y1.x * p.sc_y, y1.y * p.sc_y, y1.z * p.sc_y, y1.w * p.sc_y};
-        float sq[8];
+        float sq[8], v[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) sq[i] = v[i] * v[i];
+        for (int i = 0; i < 8; ++i) { sq[i] = w[i] * w[i] * rn; v[i] = w[i] * rn; }
         uint4 h, l;
         const uint32_t off = sw128_off(r, lane & 7);       // y'^2 -> column block 0, y' -> block 1
         split8_h(sq, h, l);
@@ -427,14 +437,21 @@ struct Stats16Policy {
     {
         const uint32_t base = (uint32_t)(quarter * B_LBO + (lane & 3) * 4);
         const int ch = lane >> 2;
+        const float4* rc = reinterpret_cast<const float4*>(b_lo + B_BYTES + RC_OFF);   // cleaned normalisers of the 16 rows
         float2 acc = st.s0;
 #pragma unroll
-        for (int r = 0; r < KT; ++r) {
-            const uint32_t off = base + (uint32_t)(r * 128 + ((ch ^ (r & 7)) << 4));
-            const float2 h = __half22float2(*reinterpret_cast<const __half2*>(b_hi + off));
-            const float2 l = __half22float2(*reinterpret_cast<const __half2*>(b_lo + off));
-            acc.x += h.x + l.x;
-            acc.y += h.y + l.y;
+        for (int r4 = 0; r4 < KT / 4; ++r4) {
+            const float4 rr = rc[r4];
+            const float rv[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int r = r4 * 4 + u;
+                const uint32_t off = base + (uint32_t)(r * 128 + ((ch ^ (r & 7)) << 4));
+                const float2 h = __half22float2(*reinterpret_cast<const __half2*>(b_hi + off));
+                const float2 l = __half22float2(*reinterpret_cast<const __half2*>(b_lo + off));
+                acc.x = fmaf(h.x + l.x, rv[u], acc.x);
+                acc.y = fmaf(h.y + l.y, rv[u], acc.y);
+            }
         }
         st.s0 = acc;
     }
@@ -722,6 +739,7 @@ struct PostPairT {
     // fp16x2: one producer group (a tile is only two k-blocks) keeps the CTA at 448 threads, i.e. enough registers
     // for the eight epilogue warps not to spill
     static constexpr int PGROUPS = H ? 1 : 2;
+    static constexpr bool PREFETCH2 = H;                              // ... with both k-blocks of the next tile in flight
     static constexpr int A_BYTES = 128 * 128, B_BYTES = (FV_K / 2) * 128, TMA_BYTES = 0;
     // scratch starts 256 B past a 1024-B boundary (barrier block): 768 B pad, then two 1024-aligned 4-KB
     // TMA-store staging tiles per epilogue warp (two [32 x 32] fp32 tiles, or a (hi, lo) pair of
@@ -883,6 +901,75 @@ struct PostPairT {
         constexpr float LOG2E = 1.4426950408889634f;
         const float nb = -base * LOG2E;
         float s4[4] = {0.f, 0.f, 0.f, 0.f};
+        if (H && p.planes) {
+            // Plane output with the normalisation deferred to the consumer: e' = 2^14 exp(l - max) (<= 2^14, so it
+            // sits in fp16's range by construction) leaves as fp16 hi + lo planes in the same pass that computes
+            // it, and the per-row factor 1 / sum_k exp(l - max) goes to rinv; the statistics kernel folds it into
+            // its [y'^2 | y'] operand rows and its zeroth-order sums.  One TMEM read pass less, no TMEM write.
+            const int wrow0 = (int)((int64_t)t.mb * 256 + rank * 128 + quarter * 32);
+            uint8_t* th = scratch + STG_OFF + (half * 4 + quarter) * 8192;
+            uint8_t* tl = th + 4096;
+            const float nb14 = nb + 14.f;
+            auto exp8 = [&](float (&v)[32], int j8, uint4& h, uint4& l) {
+                float x[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(x[u]) : "f"(fmaf(v[8 * j8 + u], LOG2E, nb14)));
+                    s4[u & 3] += x[u];
+                }
+                tc::split8_h(x, h, l);
+            };
+            auto put8 = [&](int j, const uint4& h, const uint4& l) {
+                const uint32_t off = (uint32_t)(lane * 128 + ((j ^ (lane & 7)) << 4));
+                *reinterpret_cast<uint4*>(th + off) = h;
+                *reinterpret_cast<uint4*>(tl + off) = l;
+            };
+            tmem_ld32(tmem + c0, va);
+#pragma unroll 1
+            for (int c = c0; c < c0 + CW; c += 64) {
+                tmem_ld_wait();
+                tmem_ld32(tmem + c + 32, vb);
+                addc(va, c);
+                // the first 32 columns are converted BEFORE waiting for the previous chunk's TMA stores to
+                // have read the tiles, so that wait overlaps the exponentials
+                uint4 ha[4], la[4];
+#pragma unroll
+                for (int j8 = 0; j8 < 4; ++j8) exp8(va, j8, ha[j8], la[j8]);
+                if (lane == 0) tma_store_wait_read<0>();
+                __syncwarp();
+#pragma unroll
+                for (int j8 = 0; j8 < 4; ++j8) put8(j8, ha[j8], la[j8]);
+                tmem_ld_wait();
+                if (c + 64 < c0 + CW) tmem_ld32(tmem + c + 64, va);
+                addc(vb, c + 32);
+#pragma unroll
+                for (int j8 = 0; j8 < 4; ++j8) {
+                    uint4 h, l;
+                    exp8(vb, j8, h, l);
+                    put8(4 + j8, h, l);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&p.qh_map, th, c, wrow0);
+                    tma_store_2d(&p.ql_map, tl, c, wrow0);
+                    tma_store_commit();
+                }
+            }
+            const float spart = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+            float tot = spart;
+            if constexpr (NH == 2) {
+                xch[half * 96 + 64 + lane] = spart;
+                pair_barrier(quarter);
+                tot = (half == 0 ? spart : xch[64 + lane]) + (half == 0 ? xch[96 + 64 + lane] : spart);
+            }
+            if (half == 0 && valid) {
+                p.rinv[row * 4] = 16384.f / tot;             // = 1 / sum_k exp(l - max)
+                if (p.argmax) p.argmax[row] = mi;
+            }
+            PVS_TPHASE(9, tp2, tme);
+            return;                                            // (the staging tiles are waited for before their next use)
+        }
         auto exp_chunk = [&](float (&v)[32]) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -928,57 +1015,6 @@ struct PostPairT {
         uint8_t* stg = scratch + STG_OFF + (half * 4 + quarter) * 8192;
         static_assert(H || NH == 1, "the fp32 store path below assumes one warp per lane quarter");
         const int wrow0 = (int)((int64_t)t.mb * 256 + rank * 128 + quarter * 32);
-        if (H && p.planes) {
-            // Q * 2^14 split into fp16 hi + lo: what the statistics kernel's TMA loads expect.  64 components
-            // = one 128-byte row of the hi tile and one of the lo tile; two chunks per warp and tile.
-            const float sc = inv * 16384.f;
-            uint8_t* th = stg;
-            uint8_t* tl = stg + 4096;
-            // eight values at a time: convert into one 16-byte chunk of the hi and of the lo row
-            auto conv8 = [&](const float (&v)[32], int j8, uint4& h, uint4& l) {
-                float x[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) x[u] = v[8 * j8 + u] * sc;
-                tc::split8_h(x, h, l);
-            };
-            auto put8 = [&](int j, const uint4& h, const uint4& l) {
-                const uint32_t off = (uint32_t)(lane * 128 + ((j ^ (lane & 7)) << 4));
-                *reinterpret_cast<uint4*>(th + off) = h;
-                *reinterpret_cast<uint4*>(tl + off) = l;
-            };
-            tmem_ld32(tmem + c0, va);
-#pragma unroll 1
-            for (int c = c0; c < c0 + CW; c += 64) {
-                tmem_ld_wait();
-                tmem_ld32(tmem + c + 32, vb);
-                // the first 32 columns are converted BEFORE waiting for the previous chunk's TMA stores to
-                // have read the tiles, so that wait overlaps the conversion
-                uint4 ha[4], la[4];
-#pragma unroll
-                for (int j8 = 0; j8 < 4; ++j8) conv8(va, j8, ha[j8], la[j8]);
-                if (lane == 0) tma_store_wait_read<0>();
-                __syncwarp();
-#pragma unroll
-                for (int j8 = 0; j8 < 4; ++j8) put8(j8, ha[j8], la[j8]);
-                tmem_ld_wait();
-                if (c + 64 < c0 + CW) tmem_ld32(tmem + c + 64, va);
-#pragma unroll
-                for (int j8 = 0; j8 < 4; ++j8) {
-                    uint4 h, l;
-                    conv8(vb, j8, h, l);
-                    put8(4 + j8, h, l);
-                }
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) {
-                    tma_store_2d(&p.qh_map, th, c, wrow0);
-                    tma_store_2d(&p.ql_map, tl, c, wrow0);
-                    tma_store_commit();
-                }
-            }
-            PVS_TPHASE(10, tp3, tme);
-            return;                                            // (the tiles are waited for before their next use)
-        }
         auto store_chunk = [&](const float (&v)[32], int c, int buf) {
             if (lane == 0) tma_store_wait_read<1>();             // the group that last used this tile has read it
             __syncwarp();
@@ -1099,6 +1135,7 @@ int tc_fv_plan(const pvs_model* g, const pvs_model* pca, int64_t rows, int64_t n
     pl->y = pca ? (float*)take((size_t)rows * FV_D * 4) : nullptr;
     pl->q = (float*)take((size_t)rows * FV_K * 4);
     pl->S = (float*)take((size_t)n_images * FV_K * FV_2D * 4);
+    pl->rinv = (float*)take(((size_t)rows + 16) * 16);
     pl->s0part = (float*)take((size_t)n_images * TC_FV_S0_PARTS * FV_K * 4 + 16);
     pl->flag = pl->s0part ? (int*)(pl->s0part + (size_t)n_images * TC_FV_S0_PARTS * FV_K) : nullptr;
     pl->fp16x2 = pca && g->h_ok && g->th0 && !getenv("PVS_FV_NO_FP16X2");
@@ -1152,7 +1189,7 @@ int tc_fv_posterior(const TcFvPlan& pl, const pvs_model* g, const float* y, int6
     // fp16x2 kernel (writes Q as fp16 hi / lo planes for the statistics kernel), and behind it the 3xTF32
     // kernel (fp32 Q in the same buffer) that only runs when the projection raised the range flag
     PostParams h = p;
-    h.flag = pl.flag; h.sc_y = ldexpf(1.f, -g->h_exp); h.planes = 1;
+    h.flag = pl.flag; h.sc_y = ldexpf(1.f, -g->h_exp); h.planes = 1; h.rinv = pl.rinv;
     if ((rc = make_tmap_2d(&h.w_hi, g->th0, true, FV_K, FV_2D, FV_2D, 64, FV_K / 2))) return rc;
     if ((rc = make_tmap_2d(&h.w_lo, g->th1, true, FV_K, FV_2D, FV_2D, 64, FV_K / 2))) return rc;
     if ((rc = make_tmap_2d(&h.qh_map, pl.q, true, rows, FV_K, FV_K, 64, 32))) return rc;
@@ -1170,7 +1207,7 @@ int tc_fv_stats(const TcFvPlan& pl, const pvs_model* g, const float* y, const in
     if (!pl.fp16x2) return launch_tc<StatsPolicy>(p, (int)n_images, st);
     // fp16x2 kernel, and behind it the 3xTF32 kernel that only runs when the range flag was raised
     Stats16Params h{};
-    h.b = p; h.flag = pl.flag;
+    h.b = p; h.flag = pl.flag; h.rinv = pl.rinv;
     h.sc_y = ldexpf(1.f, -g->h_exp); h.un1 = ldexpf(1.f, g->h_exp - 14); h.un2 = ldexpf(1.f, 2 * g->h_exp - 14);
     const int64_t rows = pl.rows;
     int rc;
