@@ -272,6 +272,7 @@ extern "C" int pvs_model_destroy(pvs_model* m)
     if (m->tc0) cudaFree((void*)m->tc0);
     if (m->tcg0) cudaFree((void*)m->tcg0);
     if (m->th0) cudaFree((void*)m->th0);
+    if (m->h_flags) cudaFree(m->h_flags);
     delete m;
     return PVS_OK;
 }

@@ -92,4 +92,9 @@ struct pvs_model {
     int h_exp = 0;
     const void* th0 = nullptr;
     const void* th1 = nullptr;
+    // K-Means: th0 / th1 = fp16 hi / lo parts of the centres * 2^-h_exp, zero-padded to th_ld (multiple of 64)
+    // columns; h_flags = ring of device-side range flags (one per call in flight)
+    int th_ld = 0;
+    int* h_flags = nullptr;
+    mutable std::atomic<unsigned> h_flag_next{0};
 };

@@ -12,6 +12,7 @@
 //                 (tools/tf32_split_study.py: any cheaper split misses the 1e-4 parity bar).
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include "pvs_common.cuh"
 
@@ -177,6 +178,24 @@ __device__ __forceinline__ void tf32_split(float x, float& hi, float& lo)
 {
     hi = tf32_rn(x);
     lo = tf32_rn(x - hi);
+}
+
+// fp16x2 split: x = hi + lo (+ O(2^-22 |x|)) with both parts fp16 -- for operands that were scaled into
+// fp16's range by an exact power of two
+__device__ __forceinline__ uint32_t pack_h2(__half2 v) { return *reinterpret_cast<uint32_t*>(&v); }
+// eight fp32 values -> 16-byte chunks of fp16 hi and lo parts (x = hi + lo + O(2^-22 |x|))
+__device__ __forceinline__ void split8_h(const float (&x)[8], uint4& hi, uint4& lo)
+{
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __half2 hh = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+        const float2 back = __half22float2(hh);
+        h[i] = pack_h2(hh);
+        l[i] = pack_h2(__floats2half2_rn(x[2 * i] - back.x, x[2 * i + 1] - back.y));
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -320,22 +320,6 @@ struct Stats16Params {
     float sc_y, un1, un2;                     // 2^-e, 2^(e-14), 2^(2e-14)
 };
 
-__device__ __forceinline__ uint32_t pack_h2(__half2 v) { return *reinterpret_cast<uint32_t*>(&v); }
-// eight fp32 values -> 16-byte chunks of fp16 hi and lo parts (x = hi + lo + O(2^-22 |x|))
-__device__ __forceinline__ void split8_h(const float (&x)[8], uint4& hi, uint4& lo)
-{
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const __half2 hh = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
-        const float2 back = __half22float2(hh);
-        h[i] = pack_h2(hh);
-        l[i] = pack_h2(__floats2half2_rn(x[2 * i] - back.x, x[2 * i + 1] - back.y));
-    }
-    hi = make_uint4(h[0], h[1], h[2], h[3]);
-    lo = make_uint4(l[0], l[1], l[2], l[3]);
-}
-
 // The posterior kernel leaves e' = 2^14 exp(l - max) split into two fp16 planes plus the per-descriptor
 // normaliser r = 1 / sum_k exp(l - max) (q = r e' / 2^14): r is folded into the [y'^2 | y'] operand rows and
 // into the zeroth-order sums here, which saved the posterior kernel a pass over its accumulator.

@@ -153,6 +153,42 @@ def test_vlad_tensor_assignment_odd_shapes_vs_oracle(api, k, d, images):
         assert np.array_equal(out_tc, out_cc)      # same aggregation kernel, same order
 
 
+@pytest.mark.parametrize("d", [128, 514, 64, 33])
+def test_vlad_fp16x2_assignment_and_range_guard(api, d):
+    """Hard assignment runs on fp16 hi+lo operands scaled by a power of two taken from the centres; a
+    descriptor far outside fp16's range raises the device-side flag and the 3xTF32 kernel redoes the call."""
+    import os
+    rng = np.random.default_rng(40 + d)
+    k = 256
+    centers = (3.0 * rng.standard_normal((k, d))).astype(np.float32)
+    descs = [(centers[rng.integers(0, k, t)] + 1.5 * rng.standard_normal((t, d))).astype(np.float32) for t in (700, 1, 300)]
+    enc = vlad_encoder(api, centers, d)
+
+    def run(dd, no_fp16):
+        if no_fp16:
+            os.environ["PVS_VLAD_NO_FP16X2"] = "1"
+        try:
+            api.nat.set_path(api.nat.PATH_TENSOR)
+            return enc.encode_descriptors(dd, return_labels=True)
+        finally:
+            api.nat.set_path(api.nat.PATH_AUTO)
+            os.environ.pop("PVS_VLAD_NO_FP16X2", None)
+
+    desc_all = np.vstack(descs)
+    gold = O.kmeans_predict(desc_all, centers)
+    (out_h, lab_h), (out_t, lab_t) = run(descs, False), run(descs, True)
+    assert_labels(lab_h, gold, desc_all, centers, max_near_ties=3)
+    assert_labels(lab_t, gold, desc_all, centers, max_near_ties=3)
+    assert rel_l2(out_h, O.vlad_encode(descs, centers)) <= 1e-4
+    # 1e7 * 2^-e is far beyond fp16's 65504: the guard has to hand the call to the 3xTF32 kernel
+    wild = [x.copy() for x in descs]
+    wild[0][5, 3] = 1.0e7
+    wild_all = np.vstack(wild)
+    (out_hw, lab_hw), (out_tw, lab_tw) = run(wild, False), run(wild, True)
+    assert np.array_equal(lab_hw, lab_tw) and np.array_equal(out_hw, out_tw)
+    assert_labels(lab_hw, O.kmeans_predict(wild_all, centers), wild_all, centers, max_near_ties=3)
+
+
 def test_vlad_long_image_takes_the_label_scan_path(api):
     """An image with more descriptors than the shared-memory member list holds (here forced
     by a batch whose mean T is small) must give the same block as the sorted path."""
