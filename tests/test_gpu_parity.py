@@ -300,6 +300,35 @@ def test_fv_device_resident_equals_host_and_oracle_c2_shape(api):
     assert np.allclose(np.linalg.norm(host, axis=1), 1.0, atol=1e-5)
 
 
+def test_fv_image_independence_across_chunks_and_batch_order(api):
+    """Size-independent properties on a multi-chunk, ragged batch (fp16x2 path, two streams): unit norms;
+    an image's encoding depends on nothing but its own descriptors -- the same images in reverse order and
+    with a different chunking give bit-identical rows; a subset against the fp64 oracle."""
+    rng = np.random.default_rng(77)
+    n = 700
+    ts = rng.integers(40, 400, n)
+    ts[[0, 5, n - 1]] = [1, 16, 17]
+    offs = np.concatenate([[0], np.cumsum(ts)]).astype(np.int64)
+    x = np.floor(np.clip(np.abs(rng.normal(0, 40, (int(offs[-1]), 128))), 0, 255)).astype(np.float32)
+    enc = api.enc.FisherVectorEncoder(feature_extractor=api.feat.Descriptors(128),
+                                      weights=api.enc.GMMWeights.OXFORD102_K256_SIFT_PCA)
+    xd = torch.from_numpy(x).cuda()
+    a = enc.encode_descriptors(xd, torch.from_numpy(offs), images_per_call=256).cpu().numpy()
+    assert np.allclose(np.linalg.norm(a, axis=1), 1.0, atol=1e-5)
+    order = np.arange(n)[::-1]
+    xr = np.concatenate([x[offs[i]:offs[i + 1]] for i in order])
+    offr = np.concatenate([[0], np.cumsum(ts[order])]).astype(np.int64)
+    b = enc.encode_descriptors(torch.from_numpy(xr).cuda(), torch.from_numpy(offr), images_per_call=97).cpu().numpy()
+    assert np.array_equal(a, b[::-1])
+    w = load_weights("gmm_k256_sift_pca")
+    p = load_weights("pca_k256_sift_f2")
+    pick = [0, 5, 123, n - 1]
+    ref = O.fv_encode([x[offs[i]:offs[i + 1]] for i in pick], w["weights"], w["means"], w["covariances"],
+                      w["precisions_cholesky"], pca=(p["components"], p["mean"]))
+    for r, i in enumerate(pick):
+        assert rel_l2(a[i], ref[r]) <= 1e-4, (i, rel_l2(a[i], ref[r]))
+
+
 def test_fv_generic_k32(api):
     """A k=32 vocabulary (what getting_started.ipynb trains) takes the generic path:
     shape formula 2*32*64+32 = 4128 and parity with the oracle."""
