@@ -371,8 +371,8 @@ def run_ours(args):
     hbm_bound = {"tc_fv_project", "tc_fv_posterior", "tc_fv_stats", "gmm_softmax", "fv_finalize"}
     # DRAM bytes per image of each kernel from the committed `ncu --set full` capture
     # (profiles/ncu_fv_r01c.txt: dram read + write per launch of 592 images)
-    ncu_dram_bytes_per_image = {"tc_fv_project": (0.606463e9 + 0.270842e9) / 592, "tc_fv_posterior": NCU_POST_BYTES / 592,
-                                "tc_fv_stats": (1.515643e9 + 0.063587e9) / 592}
+    ncu_dram_bytes_per_image = {"tc_fv_project": (0.606304e9 + 0.272666e9) / 592, "tc_fv_posterior": NCU_POST_BYTES / 592,
+                                "tc_fv_stats": (1.534512e9 + 0.063308e9) / 592}
     roofline = None
     if dominant[0]:
         name, (ms, n) = dominant
@@ -450,7 +450,7 @@ def run_ours(args):
 
 
 # DRAM read + write bytes of one posterior launch (592 images) in the committed ncu capture
-NCU_POST_BYTES = 0.303380e9 + 1.258173e9
+NCU_POST_BYTES = 0.321038e9 + 1.172946e9
 
 
 def main():
