@@ -45,11 +45,11 @@ constexpr int64_t ASSIGN_CHUNK_ROWS = 1 << 18;
 // ---- optional per-stage device timing (CUDA events on the launching stream) -------------
 enum Stage { ST_PCA = 0, ST_KM_SCORES, ST_KM_ARGMIN, ST_VLAD_AGG, ST_GMM_LOGITS, ST_GMM_SOFTMAX, ST_FV_STATS,
              ST_FV_FINALIZE, ST_L2NORM, ST_SIM_GEMM, ST_TOPK_SELECT, ST_TC_VLAD_ASSIGN, ST_TC_FV_POSTERIOR,
-             ST_TC_FV_STATS, ST_TC_SIM_TOPK, ST_TC_FV_PREP, ST_TC_FV_PROJECT, ST_TC_GEMM_PCA, ST_TC_GEMM_LOGITS, ST_COUNT };
+             ST_TC_FV_STATS, ST_TC_SIM_TOPK, ST_TC_FV_PREP, ST_TC_FV_PROJECT, ST_TC_GEMM_PCA, ST_TC_GEMM_LOGITS, ST_TC_FV_FUSED, ST_COUNT };
 static const char* kStageNames[ST_COUNT] = {
     "pca_project", "kmeans_scores", "kmeans_argmin", "vlad_aggregate", "gmm_logits", "gmm_softmax", "fv_stats",
     "fv_finalize", "l2_normalize", "sim_gemm", "topk_select", "tc_vlad_assign", "tc_fv_posterior", "tc_fv_stats",
-    "tc_sim_topk", "tc_fv_prep", "tc_fv_project", "tc_gemm_pca", "tc_gemm_logits"};
+    "tc_sim_topk", "tc_fv_prep", "tc_fv_project", "tc_gemm_pca", "tc_gemm_logits", "tc_fv_poststats_fused"};
 struct StageRec { int stage; cudaEvent_t a, b; };
 static std::mutex g_prof_mu;
 static std::atomic<int> g_prof_on{0};
@@ -227,6 +227,7 @@ extern "C" int pvs_gmm_create(const double* w, const double* mu, const double* c
         }
     }
     if (int s = upload_block(m, h)) { delete m; return s; }
+    m->cst_host.assign(cst, cst + k);
     const float* b = (const float*)m->block;
     m->wcat = b;
     m->cst = b + 2 * kd;
@@ -467,8 +468,16 @@ extern "C" int pvs_fv_encode(const pvs_model* g, const pvs_model* pca, const flo
         if (int rc = tc_fv_begin(pl, n_images, st)) return rc;
         if (pca)
             if (int rc = PVS_STAGE(ST_TC_FV_PROJECT, st, tc_fv_project(pl, g, pca, desc, total_rows, st))) return rc;
-        if (int rc = PVS_STAGE(ST_TC_FV_POSTERIOR, st, tc_fv_posterior(pl, g, y, total_rows, argmax_out, st))) return rc;
-        if (int rc = PVS_STAGE(ST_TC_FV_STATS, st, tc_fv_stats(pl, g, y, offsets, n_images, st))) return rc;
+        if (pl.fp16x2 && !argmax_out && tc_fv_fused_enabled()) {
+            // posterior + statistics in one kernel (the posteriors never leave the SM); behind it the two
+            // 3xTF32 kernels that only run when the projection raised the range flag
+            if (int rc = PVS_STAGE(ST_TC_FV_FUSED, st, tc_fv_poststats_fused(pl, g, y, offsets, n_images, st))) return rc;
+            if (int rc = PVS_STAGE(ST_TC_FV_POSTERIOR, st, tc_fv_posterior(pl, g, y, total_rows, argmax_out, st, true))) return rc;
+            if (int rc = PVS_STAGE(ST_TC_FV_STATS, st, tc_fv_stats(pl, g, y, offsets, n_images, st, true))) return rc;
+        } else {
+            if (int rc = PVS_STAGE(ST_TC_FV_POSTERIOR, st, tc_fv_posterior(pl, g, y, total_rows, argmax_out, st))) return rc;
+            if (int rc = PVS_STAGE(ST_TC_FV_STATS, st, tc_fv_stats(pl, g, y, offsets, n_images, st))) return rc;
+        }
         return PVS_STAGE(ST_FV_FINALIZE, st, launch_fv_finalize(pl.S, 2 * g->d, pl.s0part, TC_FV_S0_PARTS, offsets, g, n_images, power,
                                                                  norm_order, eps, out, st));
     }

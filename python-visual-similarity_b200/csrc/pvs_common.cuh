@@ -94,6 +94,7 @@ struct pvs_model {
     const void* th1 = nullptr;
     // K-Means: th0 / th1 = fp16 hi / lo parts of the centres * 2^-h_exp, zero-padded to th_ld (multiple of 64)
     // columns; h_flags = ring of device-side range flags (one per call in flight)
+    std::vector<float> cst_host;    // GMM: host copy of cst (passed to the fused kernel in its parameter block)
     int th_ld = 0;
     int* h_flags = nullptr;
     mutable std::atomic<unsigned> h_flag_next{0};

@@ -74,8 +74,14 @@ bool tc_fv_supported(const pvs_model* g, const pvs_model* pca, int64_t rows, int
 int tc_fv_plan(const pvs_model* g, const pvs_model* pca, int64_t rows, int64_t n_images, void* ws, TcFvPlan* plan);
 int tc_fv_begin(const TcFvPlan& pl, int64_t n_images, cudaStream_t st);   // clears s0part + flag
 int tc_fv_project(const TcFvPlan& pl, const pvs_model* g, const pvs_model* pca, const float* desc, int64_t rows, cudaStream_t st);
-int tc_fv_posterior(const TcFvPlan& pl, const pvs_model* g, const float* y, int64_t rows, int32_t* argmax, cudaStream_t st);
-int tc_fv_stats(const TcFvPlan& pl, const pvs_model* g, const float* y, const int64_t* offsets, int64_t n_images, cudaStream_t st);
+// fallback_only: launch just the gated 3xTF32 kernel (the fp16x2 work was done by the fused kernel)
+int tc_fv_posterior(const TcFvPlan& pl, const pvs_model* g, const float* y, int64_t rows, int32_t* argmax, cudaStream_t st,
+                    bool fallback_only = false);
+bool tc_fv_fused_enabled();
+int tc_fv_poststats_fused(const TcFvPlan& pl, const pvs_model* g, const float* y, const int64_t* offsets, int64_t n_images,
+                          cudaStream_t st);
+int tc_fv_stats(const TcFvPlan& pl, const pvs_model* g, const float* y, const int64_t* offsets, int64_t n_images, cudaStream_t st,
+                bool fallback_only = false);
 
 // generic fp32-accurate contraction on tensor cores (pvs_tc_gemmnt.cu), any shape
 int tc_prepare_generic(pvs_model* m);

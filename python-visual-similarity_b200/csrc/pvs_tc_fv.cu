@@ -1156,7 +1156,8 @@ int tc_fv_project(const TcFvPlan& pl, const pvs_model* g, const pvs_model* pca, 
     return launch_tc<PcaPolicy>(p, p.m_blocks, st);
 }
 
-int tc_fv_posterior(const TcFvPlan& pl, const pvs_model* g, const float* y, int64_t rows, int32_t* argmax, cudaStream_t st)
+int tc_fv_posterior(const TcFvPlan& pl, const pvs_model* g, const float* y, int64_t rows, int32_t* argmax, cudaStream_t st,
+                    bool fallback_only)
 {
     if (rows <= 0) return PVS_OK;
     PVS_CHECK(((uintptr_t)y & 15) == 0, PVS_ERR_BAD_ARG, "descriptor buffer must be 16-byte aligned");
@@ -1178,12 +1179,13 @@ int tc_fv_posterior(const TcFvPlan& pl, const pvs_model* g, const float* y, int6
     if ((rc = make_tmap_2d(&h.w_lo, g->th1, true, FV_K, FV_2D, FV_2D, 64, FV_K / 2))) return rc;
     if ((rc = make_tmap_2d(&h.qh_map, pl.q, true, rows, FV_K, FV_K, 64, 32))) return rc;
     if ((rc = make_tmap_2d(&h.ql_map, (const __half*)pl.q + (size_t)rows * FV_K, true, rows, FV_K, FV_K, 64, 32))) return rc;
-    if ((rc = tc2::launch_tc2<tc2::Post16PairPolicy>(h, h.m_blocks, st))) return rc;
+    if (!fallback_only && (rc = tc2::launch_tc2<tc2::Post16PairPolicy>(h, h.m_blocks, st))) return rc;
     p.flag = pl.flag;
     return tc2::launch_tc2<tc2::PostPairPolicy>(p, p.m_blocks, st);
 }
 
-int tc_fv_stats(const TcFvPlan& pl, const pvs_model* g, const float* y, const int64_t* offsets, int64_t n_images, cudaStream_t st)
+int tc_fv_stats(const TcFvPlan& pl, const pvs_model* g, const float* y, const int64_t* offsets, int64_t n_images, cudaStream_t st,
+                bool fallback_only)
 {
     if (n_images <= 0) return PVS_OK;
     StatsParams p{};
@@ -1198,7 +1200,7 @@ int tc_fv_stats(const TcFvPlan& pl, const pvs_model* g, const float* y, const in
     if ((rc = make_tmap_2d(&h.qh_map, pl.q, true, rows, FV_K, FV_K, 64, Stats16Policy::KT))) return rc;
     if ((rc = make_tmap_2d(&h.ql_map, (const __half*)pl.q + (size_t)rows * FV_K, true, rows, FV_K, FV_K, 64, Stats16Policy::KT))) return rc;
     if ((rc = make_tmap_2d(&h.y_map, y, false, rows, FV_D, FV_D, 32, Stats16Policy::KT))) return rc;
-    if ((rc = launch_tc<Stats16Policy>(h, (int)n_images, st))) return rc;
+    if (!fallback_only && (rc = launch_tc<Stats16Policy>(h, (int)n_images, st))) return rc;
     return launch_tc<StatsGatedPolicy>(h, (int)n_images, st);
 }
 

@@ -558,6 +558,38 @@ def test_fv_fp16x2_path_and_range_guard(api):
     assert rel_l2(fast_w, ref_w) <= 1e-4
 
 
+def test_fv_fused_posterior_statistics_kernel(api):
+    """Opt-in fused kernel (PVS_FV_FUSED=1: posterior + statistics in one kernel, the [y^2|y] tile serving
+    as K-major operand of the logit MMA and as MN-major operand of the statistics MMA): ragged images
+    incl. T = 1, 127, 128, 129 vs the fp64 oracle and vs the default (unfused) path."""
+    import os
+    w = load_weights("gmm_k256_sift_pca")
+    p = load_weights("pca_k256_sift_f2")
+    r = np.random.RandomState(9)
+    descs = []
+    for t in (1, 127, 128, 129, 300, 2000, 16):
+        comp = r.choice(256, size=t, p=w["weights"] / w["weights"].sum())
+        y = w["means"][comp] + r.standard_normal((t, 64)) * np.sqrt(w["covariances"][comp])
+        descs.append((y @ p["components"] + p["mean"]).astype(np.float32))
+    enc = api.enc.FisherVectorEncoder(feature_extractor=api.feat.Descriptors(128),
+                                      weights=api.enc.GMMWeights.OXFORD102_K256_SIFT_PCA)
+    base = enc.encode(descs)
+    os.environ["PVS_FV_FUSED"] = "1"
+    try:
+        n0 = api.nat.lib().pvs_launch_count()
+        fused = enc.encode(descs)
+        launches = api.nat.lib().pvs_launch_count() - n0
+    finally:
+        os.environ.pop("PVS_FV_FUSED", None)
+    ref = O.fv_encode(descs, w["weights"], w["means"], w["covariances"], w["precisions_cholesky"],
+                      pca=(p["components"], p["mean"]))
+    errs = [rel_l2(fused[i], ref[i]) for i in range(len(descs))]
+    assert max(errs) <= 1e-4, errs
+    assert rel_l2(fused, base) <= 5e-5
+    assert not np.array_equal(fused, base), "the fused kernel did not run"
+    assert launches == 5          # project, fused, two gated 3xTF32 kernels, finalize
+
+
 def test_fv_tensor_path_without_pca_d64(api):
     """K=256, D=64 GMM fed 64-D descriptors directly (no PCA stage)."""
     w = load_weights("gmm_k256_root_sift_pca")
