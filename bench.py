@@ -359,7 +359,8 @@ def run_ours(args):
     dominant = max(stages.items(), key=lambda kv: kv[1][0]) if stages else (None, (0.0, 0))
     flops_per_image = {"pca_project": 2 * T * d_in * D, "gmm_logits": 2 * T * K * 2 * D,
                        "fv_stats": 2 * T * K * 2 * D, "tc_fv_posterior": 2 * T * K * 2 * D,
-                       "tc_fv_stats": 2 * T * K * 2 * D, "tc_fv_project": 2 * T * d_in * D}
+                       "tc_fv_stats": 2 * T * K * 2 * D, "tc_fv_project": 2 * T * d_in * D,
+                       "tc_fv_poststats_fused": 4 * T * K * 2 * D}        # logits + statistics in one kernel
     # algorithmic HBM bytes per image of each kernel: what its interface makes it move
     bytes_per_image = {"gmm_softmax": 2 * T * K * 4, "fv_finalize": K * (2 * D + 1) * 4 + out_dim * 4 * 3,
                        "tc_fv_project": T * (d_in + D) * 4,                    # X in, Y out
@@ -393,7 +394,10 @@ def run_ours(args):
             peak = pk["bf16_tflops_sustained"]
             roofline = {"bound": "tensor", "kernel": name, "achieved": tflops, "peak": peak, "unit": "TFLOP/s",
                         "frac": tflops / peak, "traffic": traffic * imgs_per_launch if traffic else None,
-                        "peak_source": f"bf16 dense sustained, {pk['source']} (kernel runs inside a long step)"}
+                        "peak_source": f"bf16 dense sustained, {pk['source']} (kernel runs inside a long step)",
+                        "note": "fp16x2: three kind::f16 MMAs per algorithmic product, so the ceiling of this kernel is "
+                                "peak / 3; frac_of_fp16x2_ceiling = 3 * frac",
+                        "frac_of_fp16x2_ceiling": 3 * tflops / peak}
         roofline["kernel_ms_per_launch"] = per_launch_ms
         roofline["kernel_share_of_step"] = ms / sum(v[0] for v in stages.values())
         roofline["timing"] = f"{prof_steps} extra single-stream step(s), CUDA events around each launch"

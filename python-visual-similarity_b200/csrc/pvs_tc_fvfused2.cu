@@ -1,0 +1,535 @@
+// pvs_tc_fvfused2.cu -- Fisher vector, K = 256 / D = 64: posterior + per-image statistics in one
+// kernel, CLUSTER version.  pvs_tc_fvfused.cu showed that one CTA cannot overlap anything: the
+// logits (256 columns) and the statistics (256 columns) fill TMEM.  Here a 2-CTA cluster splits
+// the 256 mixture components: both CTAs walk the same 128-descriptor tiles of the same images,
+// CTA r owns components [128 r, 128 r + 128).  Per CTA that leaves room for
+//   TMEM   two logit accumulators (2 x 128 columns) + the statistics (128 columns)
+//   smem   W' slice RESIDENT (64 KB, no streaming), two A1 tiles (2 x 64 KB), one Q chunk buffer (32 KB)
+// so the logit MMA of tile i+1 runs while the softmax warps work on tile i.  All MMAs are
+// cta_group::1; what crosses the CTA boundary is two floats per descriptor (row maximum, row
+// sum of exponentials), exchanged through distributed shared memory with cluster-scope mbarriers.
+//
+// Per CTA: warp 0 loads W' once; warp 1 issues MMA1(g) then MMA2(g-1) (software pipeline);
+// warps 2-9 softmax (two per TMEM lane quarter, 64 components each): max -> exchange -> exp,
+// stash, sum -> exchange -> q 2^14 as fp16 hi + lo rows of the MN-major operand of MMA2 (chunk of
+// 64 components, one buffer used twice per tile); warps 10-13 convert Y rows into A1(g+1)
+// (interleaved (y'^2, y') fp16 hi + lo; K-major operand of MMA1 and, read through an MN-major
+// descriptor, operand of MMA2) and then take the zeroth-order sums of the Q chunks of tile g.
+// Image end: S / T and the zeroth-order partials go where the unfused kernels put them.
+#include "pvs_tc.cuh"
+#include "pvs_kernels.cuh"
+#include <string.h>
+
+namespace pvs {
+namespace tc {
+namespace fusedc {
+
+#ifdef PVS_TIMING
+// MMA warp: [0] wait a1_full [1] wait l_free [2] wait q_full [3] total; softmax warp 2: [4] wait l_full
+// [5] pass 1 [6] exchange max [7] pass 2 [8] exchange sum [9] pass 3 [10] wait q_empty [11] image end [12] total
+__device__ unsigned long long g_ft[16];
+#define FT0(v) const long long v = clock64()
+#define FTA(slot, v) ft[slot] += clock64() - (v)
+#else
+#define FT0(v)
+#define FTA(slot, v)
+#endif
+
+constexpr int K = 256, CK = 128, D = 64, AUG = 128, TT = 128, QC = 64;
+constexpr int A1_BYTES = 65536, W_BYTES = 65536, Q_BYTES = 32768;
+constexpr int OFF_A1 = 0, OFF_W = 2 * A1_BYTES, OFF_Q = OFF_W + W_BYTES, OFF_BAR = OFF_Q + Q_BYTES;
+constexpr int OFF_XI = OFF_BAR + 128;          // intra-CTA exchange: [4 quarters][2 halves][32 rows], one slot reused for max and sum
+constexpr int OFF_XO = OFF_XI + 1024;          // inter-CTA exchange (written by the peer): [max, sum][128 rows]
+constexpr int SMEM_BYTES = OFF_XO + 1024;
+constexpr int THREADS = 448;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
+
+struct Params {
+    CUtensorMap w_hi, w_lo;                // W' [256, 128] fp16, box 64 cols x 128 rows
+    float cst[K];
+    const float* y;                        // [rows, 64]
+    const int64_t* offsets;
+    float* S;                              // [n_images, 256, 128]
+    float* s0part;                         // [n_images, 16, 256] (slots 0-3 used)
+    int64_t n_images;
+    const int* flag;
+    float sc_y, un1, un2;
+};
+
+__device__ __forceinline__ uint32_t cluster_rank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_remote_f32(uint32_t cluster_addr, float v)
+{
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void arrive_remote_release(uint32_t cluster_bar_addr)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
+}
+__device__ __forceinline__ void wait_acquire_cluster(uint64_t* bar, uint32_t parity)
+{
+    const uint32_t a = smem_u32(bar);
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t ok;
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) return;
+        if (clock64() - t0 > 6000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void cluster_sync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) kernel(const __grid_constant__ Params p)
+{
+    if (*p.flag != 0) return;                                  // uniform over the grid
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    uint64_t *a1_full = bars, *a1_free = bars + 2, *l_full = bars + 4, *l_free = bars + 6;
+    uint64_t *s_full = bars + 8, *q_full = bars + 9, *q_empty = bars + 10, *w_res = bars + 11, *x_max = bars + 12, *x_sum = bars + 13;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_rank(), peer = rank ^ 1;
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&a1_full[i], 4);
+            mbar_init(&a1_free[i], 1);
+            mbar_init(&l_full[i], 1);
+            mbar_init(&l_free[i], 8);
+        }
+        mbar_init(s_full, 1);
+        mbar_init(q_full, 4);
+        mbar_init(q_empty, 1 + 4);
+        mbar_init(w_res, 1);
+        mbar_init(x_max, 128);                                 // one arrival per thread of the peer's half-0 softmax warps
+        mbar_init(x_sum, 128);
+        fence_barrier_init();
+        tma_prefetch_desc(&p.w_hi);
+        tma_prefetch_desc(&p.w_lo);
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tcgen05_fence_before();
+    cluster_sync();                                            // the peer's barriers exist before anybody signals them
+    tcgen05_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem_S = tmem + 256;                        // logits: columns [0,128) and [128,256)
+
+    auto n_tiles_of = [&](int64_t img, int64_t& r0, int& T) {
+        r0 = p.offsets[img];
+        T = (int)(p.offsets[img + 1] - r0);
+        return (T + TT - 1) / TT;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {                                       // this CTA's 128 rows of W', both k-blocks, hi and lo
+            mbar_expect_tx(w_res, W_BYTES);
+            uint8_t* w = smem + OFF_W;
+            tma_load_2d(w, &p.w_hi, w_res, 0, (int)rank * CK);
+            tma_load_2d(w + 16384, &p.w_hi, w_res, 64, (int)rank * CK);
+            tma_load_2d(w + 32768, &p.w_lo, w_res, 0, (int)rank * CK);
+            tma_load_2d(w + 49152, &p.w_lo, w_res, 64, (int)rank * CK);
+        }
+    } else if (warp == 1) {
+        // ---- MMA issuer: MMA1(g), then MMA2(g - 1) ----
+        constexpr uint32_t idesc1 = make_idesc(false, false, false, 128, CK, true);     // K-major x K-major, N = 128
+        constexpr uint32_t idesc2 = make_idesc(false, true, true, 128, QC, true);       // MN-major x MN-major, N = 64
+        const uint32_t a1b = smem_u32(smem + OFF_A1), wb = smem_u32(smem + OFF_W), qb = smem_u32(smem + OFF_Q);
+#ifdef PVS_TIMING
+        long long ft[16] = {0};
+#endif
+        FT0(t_all);
+        mbar_wait(w_res, 0);
+        uint32_t g = 0;
+        bool have_prev = false;
+        int prev_tile = 0;
+        bool prev_last = false;
+        auto mma2 = [&](uint32_t gp, int tile, bool last) {
+            const uint32_t a1 = a1b + (gp & 1) * A1_BYTES;
+            for (int n = 0; n < 2; ++n) {
+                const uint32_t use = 2 * gp + (uint32_t)n;
+                FT0(t2);
+                mbar_wait(q_full, use & 1);
+                FTA(2, t2);
+                tcgen05_fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int ks = 0; ks < TT / 16; ++ks) {
+                        const uint64_t a_hi = make_smem_desc(a1 + ks * 2048, 32768, 1024, LAYOUT_SW128);
+                        const uint64_t a_lo = make_smem_desc(a1 + 16384 + ks * 2048, 32768, 1024, LAYOUT_SW128);
+                        const uint64_t b_hi = make_smem_desc(qb + ks * 2048, 16384, 1024, LAYOUT_SW128);
+                        const uint64_t b_lo = make_smem_desc(qb + 16384 + ks * 2048, 16384, 1024, LAYOUT_SW128);
+                        const uint32_t d = tmem_S + (uint32_t)(n * QC);
+                        umma<true>(d, a_hi, b_lo, idesc2, (tile | ks) ? 1u : 0u);
+                        umma<true>(d, a_lo, b_hi, idesc2, 1u);
+                        umma<true>(d, a_hi, b_hi, idesc2, 1u);
+                    }
+                    umma_commit(q_empty);
+                }
+                __syncwarp();
+            }
+            if (elect_one()) {
+                umma_commit(&a1_free[gp & 1]);
+                if (last) umma_commit(s_full);
+            }
+            __syncwarp();
+        };
+        for (int64_t img = cluster_id; img < p.n_images; img += n_clusters) {
+            int64_t r0; int T;
+            const int nt = n_tiles_of(img, r0, T);
+            for (int tile = 0; tile < nt; ++tile, ++g) {
+                const uint32_t b = g & 1, ph = (g >> 1) & 1;
+                FT0(t0);
+                mbar_wait(&a1_full[b], ph);
+                FTA(0, t0);
+                FT0(t1);
+                mbar_wait(&l_free[b], ph ^ 1);
+                FTA(1, t1);
+                tcgen05_fence_after();
+                if (elect_one()) {
+                    const uint32_t a1 = a1b + b * A1_BYTES;
+#pragma unroll
+                    for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint64_t a_hi = make_smem_desc(a1 + kb * 32768 + ks * 32, 16, 1024, LAYOUT_SW128);
+                            const uint64_t a_lo = make_smem_desc(a1 + kb * 32768 + 16384 + ks * 32, 16, 1024, LAYOUT_SW128);
+                            const uint64_t b_hi = make_smem_desc(wb + kb * 16384 + ks * 32, 16, 1024, LAYOUT_SW128);
+                            const uint64_t b_lo = make_smem_desc(wb + 32768 + kb * 16384 + ks * 32, 16, 1024, LAYOUT_SW128);
+                            const uint32_t d = tmem + b * CK;
+                            umma<true>(d, a_hi, b_lo, idesc1, (kb | ks) ? 1u : 0u);
+                            umma<true>(d, a_lo, b_hi, idesc1, 1u);
+                            umma<true>(d, a_hi, b_hi, idesc1, 1u);
+                        }
+                    umma_commit(&l_full[b]);
+                }
+                __syncwarp();
+                if (have_prev) mma2(g - 1, prev_tile, prev_last);
+                have_prev = true;
+                prev_tile = tile;
+                prev_last = tile == nt - 1;
+            }
+        }
+        if (have_prev) mma2(g - 1, prev_tile, prev_last);
+#ifdef PVS_TIMING
+        FTA(3, t_all);
+        if (lane == 0 && rank == 0) for (int i = 0; i < 4; ++i) atomicAdd(&g_ft[i], (unsigned long long)ft[i]);
+#endif
+    } else if (warp < 10) {
+        // ---- softmax / epilogue: thread = descriptor row; warp (quarter, half) takes 64 of this CTA's 128 components ----
+        const int quarter = warp & 3, half = (warp - 2) >> 2;
+        const int c0 = half * 64;                              // first column of this warp inside the CTA's 128
+        const float* cstv = p.cst + rank * CK;
+        float* xi = reinterpret_cast<float*>(smem + OFF_XI) + quarter * 64;
+        float* xo = reinterpret_cast<float*>(smem + OFF_XO);
+        const uint32_t xo_remote = map_to_cta(smem_u32(xo), peer);
+        const uint32_t xmax_remote = map_to_cta(smem_u32(x_max), peer), xsum_remote = map_to_cta(smem_u32(x_sum), peer);
+        auto pair_barrier = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory"); };
+        const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+        const int trow = quarter * 32 + lane;
+        constexpr float LOG2E = 1.4426950408889634f;
+        uint32_t g = 0, imgs = 0;
+#ifdef PVS_TIMING
+        long long ft[16] = {0};
+#endif
+        FT0(t_all);
+        for (int64_t img = cluster_id; img < p.n_images; img += n_clusters) {
+            int64_t r0; int T;
+            const int nt = n_tiles_of(img, r0, T);
+            for (int tile = 0; tile < nt; ++tile, ++g) {
+                const uint32_t b = g & 1, ph = (g >> 1) & 1;
+                const bool valid = tile * TT + trow < T;
+                FT0(t4);
+                mbar_wait(&l_full[b], ph);
+                FTA(4, t4);
+                FT0(t5);
+                tcgen05_fence_after();
+                const uint32_t tl = tmem + b * CK + lane_off + c0;
+                float va[32], vb[32];
+                auto addc = [&](float (&v)[32], int c) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] += cstv[c + j];
+                };
+                // pass 1: maximum of this warp's 64 columns
+                tmem_ld32(tl, va);
+                tmem_ld32(tl + 32, vb);
+                tmem_ld_wait();
+                addc(va, c0);
+                addc(vb, c0 + 32);
+                float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+                for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], fmaxf(va[j], vb[j]));
+                float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+                // the logits now live in registers: hand the accumulator back to the MMA warp at once
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&l_free[b]);
+                FTA(5, t5);
+                FT0(t6);
+                // exchange: partner warp (other 64 columns of this CTA), then the peer CTA (other 128 components).
+                // One slot per warp, reused for max and sum: every write is fenced from the partner's previous read
+                // by a pair barrier.
+                xi[half * 32 + lane] = mx;
+                pair_barrier();
+                mx = fmaxf(mx, xi[(half ^ 1) * 32 + lane]);
+                pair_barrier();
+                if (half == 0) {
+                    st_remote_f32(xo_remote + (uint32_t)trow * 4, mx);
+                    arrive_remote_release(xmax_remote);
+                }
+                wait_acquire_cluster(x_max, g & 1);
+                mx = fmaxf(mx, xo[trow]);
+                FTA(6, t6);
+                FT0(t7);
+                const float base = (mx > -INFINITY && mx < INFINITY) ? mx : 0.f;
+                const float nb = -base * LOG2E;
+                // pass 2: e = exp(l - max) (the logits + constants are still in registers), stashed in the accumulator
+                float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float e0, e1;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(va[j], LOG2E, nb)));
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(vb[j], LOG2E, nb)));
+                    va[j] = e0;
+                    vb[j] = e1;
+                    s4[j & 3] += e0 + e1;
+                }
+                float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+                FTA(7, t7);
+                FT0(t8);
+                xi[half * 32 + lane] = sum;
+                pair_barrier();
+                sum = half == 0 ? sum + xi[32 + lane] : xi[lane] + sum;               // same association in both warps
+                pair_barrier();
+                if (half == 0) {
+                    st_remote_f32(xo_remote + 512u + (uint32_t)trow * 4, sum);
+                    arrive_remote_release(xsum_remote);
+                }
+                wait_acquire_cluster(x_sum, g & 1);
+                const float tot = rank == 0 ? sum + xo[128 + trow] : xo[128 + trow] + sum;   // same association in both CTAs
+                const float sc = valid ? 16384.f / tot : 0.f;
+                FTA(8, t8);
+                FT0(t9);
+                // pass 3: q 2^14 as fp16 hi + lo rows of the MN-major operand of the statistics MMA (chunk `half`)
+                {
+                    const uint32_t use = 2 * g + (uint32_t)half;
+                    uint8_t* qh = smem + OFF_Q;
+                    uint8_t* ql = qh + 16384;
+                    FT0(t10);
+                    mbar_wait(q_empty, (use & 1) ^ 1);
+                    FTA(10, t10);
+#pragma unroll
+                    for (int j8 = 0; j8 < 8; ++j8) {
+                        float x[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) x[u] = (j8 < 4 ? va[8 * j8 + u] : vb[8 * (j8 - 4) + u]) * sc;
+                        uint4 h, l;
+                        split8_h(x, h, l);
+                        const uint32_t off = (uint32_t)(trow * 128 + ((j8 ^ (trow & 7)) << 4));
+                        *reinterpret_cast<uint4*>(qh + off) = h;
+                        *reinterpret_cast<uint4*>(ql + off) = l;
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(q_full);
+                }
+                FTA(9, t9);
+            }
+            FT0(t11);
+            // image end: this CTA's 128 components of S / T, operand scales undone, in fv_finalize's [k][ s1 | s2 ] layout
+            float* Simg = p.S + img * (int64_t)(K * AUG) + (int64_t)(rank * CK) * AUG;
+            const int m = trow, dd = 32 * (m >> 6) + ((m & 63) >> 1);
+            const bool lin = m & 1;
+            const int col = lin ? dd : D + dd;
+            if (nt > 0) {
+                mbar_wait(s_full, imgs & 1);
+                ++imgs;
+                tcgen05_fence_after();
+                const float scale = (lin ? p.un1 : p.un2) / (float)T;
+                const uint32_t ts = tmem_S + lane_off;
+#pragma unroll 1
+                for (int c = c0; c < c0 + 64; c += 32) {
+                    float v[32];
+                    tmem_ld32(ts + c, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) Simg[(int64_t)(c + j) * AUG + col] = v[j] * scale;
+                }
+                tcgen05_fence_before();
+            } else {
+                const float nanv = __int_as_float(0x7fc00000);
+                for (int c = c0; c < c0 + 64; ++c) Simg[(int64_t)c * AUG + col] = nanv;
+            }
+            FTA(11, t11);
+        }
+#ifdef PVS_TIMING
+        FTA(12, t_all);
+        if (warp == 2 && lane == 0 && rank == 0) for (int i = 4; i < 13; ++i) atomicAdd(&g_ft[i], (unsigned long long)ft[i]);
+#endif
+    } else {
+        // ---- converters: A1(g + 1) first, then the zeroth-order sums of tile g ----
+        const int cw = warp - 10;
+        const int c = lane & 7;
+        float4 yv[16];
+        auto fetch = [&](int64_t r0, int T, int tile) {
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int t = tile * TT + cw * 32 + i * 4 + (lane >> 3);
+                    yv[kb * 8 + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (t < T) yv[kb * 8 + i] = __ldg(reinterpret_cast<const float4*>(p.y + (r0 + t) * D + kb * 32 + c * 4));
+                }
+        };
+        auto convert = [&](uint32_t gg) {                      // registers -> A1[gg & 1]
+            mbar_wait(&a1_free[gg & 1], ((gg >> 1) & 1) ^ 1);
+            uint8_t* a1 = smem + OFF_A1 + (gg & 1) * A1_BYTES;
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = cw * 32 + i * 4 + (lane >> 3);
+                    const float4 v = yv[kb * 8 + i];
+                    const float a = v.x * p.sc_y, b = v.y * p.sc_y, cc = v.z * p.sc_y, d = v.w * p.sc_y;
+                    const float x[8] = {a * a, a, b * b, b, cc * cc, cc, d * d, d};
+                    uint4 h, l;
+                    split8_h(x, h, l);
+                    const uint32_t off = (uint32_t)(kb * 32768 + row * 128 + ((c ^ (row & 7)) << 4));
+                    *reinterpret_cast<uint4*>(a1 + off) = h;
+                    *reinterpret_cast<uint4*>(a1 + 16384 + off) = l;
+                }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a1_full[gg & 1]);
+        };
+        // walk the (image, tile) sequence one tile ahead of the tile whose Q chunks are being summed
+        int64_t f_img = cluster_id, f_r0 = 0;
+        int f_T = 0, f_nt = 0, f_tile = 0;
+        auto f_settle = [&]() {                                // skip empty images
+            while (f_img < p.n_images && (f_nt = n_tiles_of(f_img, f_r0, f_T)) == 0) f_img += n_clusters;
+        };
+        auto f_next = [&]() {
+            if (++f_tile >= f_nt) { f_tile = 0; f_img += n_clusters; f_settle(); }
+        };
+        f_settle();
+        uint32_t g = 0;                                        // tile whose Q chunks are summed next
+        if (f_img < p.n_images) {
+            fetch(f_r0, f_T, 0);
+            convert(0);
+        }
+        int64_t s_img = f_img;
+        bool s_last = f_img < p.n_images && f_nt == 1;
+        bool more = f_img < p.n_images;
+        if (more) {
+            f_next();
+            if (f_img < p.n_images) fetch(f_r0, f_T, f_tile);
+        }
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        while (more) {
+            const bool have_next = f_img < p.n_images;
+            if (have_next) convert(g + 1);
+            const int64_t n_img = f_img;
+            const bool n_last = have_next && f_tile == f_nt - 1;
+            if (have_next) {
+                f_next();
+                if (f_img < p.n_images) fetch(f_r0, f_T, f_tile);
+            }
+            for (int n = 0; n < 2; ++n) {
+                const uint32_t use = 2 * g + (uint32_t)n;
+                mbar_wait(q_full, use & 1);
+                const uint8_t* qh = smem + OFF_Q;
+                const uint8_t* ql = qh + 16384;
+                float ax = 0.f, ay = 0.f;
+#pragma unroll 8
+                for (int rr = 0; rr < 32; ++rr) {
+                    const int r = cw * 32 + rr;
+                    const uint32_t off = (uint32_t)(r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
+                    const float2 h = __half22float2(*reinterpret_cast<const __half2*>(qh + off));
+                    const float2 l = __half22float2(*reinterpret_cast<const __half2*>(ql + off));
+                    ax += h.x + l.x;
+                    ay += h.y + l.y;
+                }
+                acc[2 * n] += ax;
+                acc[2 * n + 1] += ay;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(q_empty);
+            }
+            if (s_last) {
+                float* dst = p.s0part + (s_img * TC_FV_S0_PARTS + cw) * (int64_t)K + rank * CK;
+#pragma unroll
+                for (int n = 0; n < 2; ++n) {
+                    *reinterpret_cast<float2*>(dst + n * QC + 2 * lane) = make_float2(acc[2 * n] * (1.f / 16384.f), acc[2 * n + 1] * (1.f / 16384.f));
+                    acc[2 * n] = acc[2 * n + 1] = 0.f;
+                }
+            }
+            ++g;
+            more = have_next;
+            s_img = n_img;
+            s_last = n_last;
+        }
+    }
+    tcgen05_fence_before();
+    cluster_sync();                                            // nobody exits while the peer may still write into its shared memory
+    if (warp == 1) tmem_dealloc<512>(tmem);
+}
+}  // namespace fusedc
+}  // namespace tc
+
+using namespace tc;
+
+int tc_fv_poststats_fused_cluster(const TcFvPlan& pl, const pvs_model* g, const float* y, const int64_t* offsets, int64_t n_images,
+                                  cudaStream_t st)
+{
+    if (n_images <= 0) return PVS_OK;
+    static bool configured = false;
+    if (!configured) {
+        PVS_CUDA(cudaFuncSetAttribute(fusedc::kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fusedc::SMEM_BYTES));
+        configured = true;
+    }
+    fusedc::Params p{};
+    int rc;
+    if ((rc = make_tmap_2d(&p.w_hi, g->th0, true, fusedc::K, fusedc::AUG, fusedc::AUG, 64, 128))) return rc;
+    if ((rc = make_tmap_2d(&p.w_lo, g->th1, true, fusedc::K, fusedc::AUG, fusedc::AUG, 64, 128))) return rc;
+    PVS_CHECK((int)g->cst_host.size() == fusedc::K, PVS_ERR_BAD_ARG, "GMM model lacks the host copy of its constants");
+    memcpy(p.cst, g->cst_host.data(), sizeof(p.cst));
+    p.y = y; p.offsets = offsets; p.S = pl.S; p.s0part = pl.s0part; p.n_images = n_images; p.flag = pl.flag;
+    p.sc_y = ldexpf(1.f, -g->h_exp); p.un1 = ldexpf(1.f, g->h_exp - 14); p.un2 = ldexpf(1.f, 2 * g->h_exp - 14);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int clusters = n_images < sms / 2 ? (int)n_images : sms / 2;
+    fusedc::kernel<<<2 * clusters, fusedc::THREADS, fusedc::SMEM_BYTES, st>>>(p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PVS_ERR_CUDA, "fused (cluster) posterior + statistics kernel launch failed: %s", cudaGetErrorString(e));
+#ifdef PVS_TIMING
+    if (getenv("PVS_TIMING_PRINT")) {
+        cudaStreamSynchronize(st);
+        unsigned long long h[16], z[16] = {0};
+        cudaMemcpyFromSymbol(h, fusedc::g_ft, sizeof(h));
+        cudaMemcpyToSymbol(fusedc::g_ft, z, sizeof(z));
+        const double np = clusters * 1e3;
+        fprintf(stderr, "[fusedc timing] per cluster (kcycles): mma total %.0f wait a1_full %.0f l_free %.0f q_full %.0f | softmax total %.0f wait l_full %.0f p1 %.0f xmax %.0f p2 %.0f xsum %.0f p3 %.0f (q_empty %.0f) image end %.0f\n",
+                h[3] / np, h[0] / np, h[1] / np, h[2] / np, h[12] / np, h[4] / np, h[5] / np, h[6] / np, h[7] / np, h[8] / np, h[9] / np, h[10] / np, h[11] / np);
+    }
+#endif
+    return PVS_OK;
+}
+
+}  // namespace pvs
