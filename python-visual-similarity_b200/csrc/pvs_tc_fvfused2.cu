@@ -38,9 +38,9 @@ __device__ unsigned long long g_ft[16];
 constexpr int K = 256, CK = 128, D = 64, AUG = 128, TT = 128, QC = 64;
 constexpr int A1_BYTES = 65536, W_BYTES = 65536, Q_BYTES = 32768;
 constexpr int OFF_A1 = 0, OFF_W = 2 * A1_BYTES, OFF_Q = OFF_W + W_BYTES, OFF_BAR = OFF_Q + Q_BYTES;
-constexpr int OFF_XI = OFF_BAR + 128;          // intra-CTA exchange: [4 quarters][2 halves][32 rows], one slot reused for max and sum
-constexpr int OFF_XO = OFF_XI + 1024;          // inter-CTA exchange (written by the peer): [max, sum][128 rows]
-constexpr int SMEM_BYTES = OFF_XO + 1024;
+constexpr int OFF_XI = OFF_BAR + 128;          // intra-CTA exchange: [4 quarters][32 rows], one slot per warp pair
+constexpr int OFF_XO = OFF_XI + 512;           // inter-CTA exchange (written by the peer): [tile parity][shift, sum][128 rows]
+constexpr int SMEM_BYTES = OFF_XO + 2048;
 constexpr int THREADS = 448;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
 
@@ -101,7 +101,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) kernel(c
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t *a1_full = bars, *a1_free = bars + 2, *l_full = bars + 4, *l_free = bars + 6;
-    uint64_t *s_full = bars + 8, *q_full = bars + 9, *q_empty = bars + 10, *w_res = bars + 11, *x_max = bars + 12, *x_sum = bars + 13;
+    uint64_t *s_full = bars + 8, *q_full = bars + 9, *q_empty = bars + 10, *w_res = bars + 11, *x_sum = bars + 12;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_rank(), peer = rank ^ 1;
@@ -118,8 +118,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) kernel(c
         mbar_init(q_full, 4);
         mbar_init(q_empty, 1 + 4);
         mbar_init(w_res, 1);
-        mbar_init(x_max, 128);                                 // one arrival per thread of the peer's half-0 softmax warps
-        mbar_init(x_sum, 128);
+        mbar_init(x_sum, 128);                                 // one arrival per thread of the peer's half-0 softmax warps
         fence_barrier_init();
         tma_prefetch_desc(&p.w_hi);
         tma_prefetch_desc(&p.w_lo);
@@ -236,11 +235,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) kernel(c
         const int quarter = warp & 3, half = (warp - 2) >> 2;
         const int c0 = half * 64;                              // first column of this warp inside the CTA's 128
         const float* cstv = p.cst + rank * CK;
-        float* xi = reinterpret_cast<float*>(smem + OFF_XI) + quarter * 64;
+        float* xi = reinterpret_cast<float*>(smem + OFF_XI) + quarter * 32;
         float* xo = reinterpret_cast<float*>(smem + OFF_XO);
         const uint32_t xo_remote = map_to_cta(smem_u32(xo), peer);
-        const uint32_t xmax_remote = map_to_cta(smem_u32(x_max), peer), xsum_remote = map_to_cta(smem_u32(x_sum), peer);
+        const uint32_t xsum_remote = map_to_cta(smem_u32(x_sum), peer);
         auto pair_barrier = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory"); };
+        // value shared by the two warps of a lane quarter: half 1 deposits, half 0 combines and puts the result back
+        auto pair_combine = [&](float v, bool is_max) {
+            if (half == 1) xi[lane] = v;
+            pair_barrier();
+            if (half == 0) {
+                const float o = xi[lane];
+                v = is_max ? fmaxf(v, o) : v + o;
+                xi[lane] = v;
+            }
+            pair_barrier();
+            if (half == 1) v = xi[lane];
+            return v;
+        };
         const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
         const int trow = quarter * 32 + lane;
         constexpr float LOG2E = 1.4426950408889634f;
@@ -282,24 +294,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) kernel(c
                 if (lane == 0) mbar_arrive(&l_free[b]);
                 FTA(5, t5);
                 FT0(t6);
-                // exchange: partner warp (other 64 columns of this CTA), then the peer CTA (other 128 components).
-                // One slot per warp, reused for max and sum: every write is fenced from the partner's previous read
-                // by a pair barrier.
-                xi[half * 32 + lane] = mx;
-                pair_barrier();
-                mx = fmaxf(mx, xi[(half ^ 1) * 32 + lane]);
-                pair_barrier();
-                if (half == 0) {
-                    st_remote_f32(xo_remote + (uint32_t)trow * 4, mx);
-                    arrive_remote_release(xmax_remote);
-                }
-                wait_acquire_cluster(x_max, g & 1);
-                mx = fmaxf(mx, xo[trow]);
+                // this CTA's maximum over its 128 components (partner warp = the other 64 columns).  The peer CTA is
+                // NOT consulted for the maximum: each CTA shifts by its own and the two are reconciled with the sums.
+                mx = pair_combine(mx, true);
                 FTA(6, t6);
                 FT0(t7);
                 const float base = (mx > -INFINITY && mx < INFINITY) ? mx : 0.f;
                 const float nb = -base * LOG2E;
-                // pass 2: e = exp(l - max) (the logits + constants are still in registers), stashed in the accumulator
+                // pass 2: e = exp(l - base) in registers (nothing goes back to TMEM), and its sum
                 float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
@@ -313,17 +315,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) kernel(c
                 float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
                 FTA(7, t7);
                 FT0(t8);
-                xi[half * 32 + lane] = sum;
-                pair_barrier();
-                sum = half == 0 ? sum + xi[32 + lane] : xi[lane] + sum;               // same association in both warps
-                pair_barrier();
+                sum = pair_combine(sum, false);
+                // one exchange with the peer CTA per tile: (shift, sum of exponentials) of its 128 components
+                const uint32_t xoff = (g & 1) * 1024u;
                 if (half == 0) {
-                    st_remote_f32(xo_remote + 512u + (uint32_t)trow * 4, sum);
+                    st_remote_f32(xo_remote + xoff + (uint32_t)trow * 4, base);
+                    st_remote_f32(xo_remote + xoff + 512u + (uint32_t)trow * 4, sum);
                     arrive_remote_release(xsum_remote);
                 }
                 wait_acquire_cluster(x_sum, g & 1);
-                const float tot = rank == 0 ? sum + xo[128 + trow] : xo[128 + trow] + sum;   // same association in both CTAs
-                const float sc = valid ? 16384.f / tot : 0.f;
+                const float pbase = xo[(g & 1) * 256 + trow], psum = xo[(g & 1) * 256 + 128 + trow];
+                const float big = fmaxf(base, pbase);
+                float f_me, f_peer;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(f_me) : "f"((base - big) * LOG2E));
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(f_peer) : "f"((pbase - big) * LOG2E));
+                const float tot = sum * f_me + psum * f_peer;
+                const float sc = valid ? 16384.f * f_me / tot : 0.f;
                 FTA(8, t8);
                 FT0(t9);
                 // pass 3: q 2^14 as fp16 hi + lo rows of the MN-major operand of the statistics MMA (chunk `half`)

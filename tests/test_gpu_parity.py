@@ -520,7 +520,7 @@ def test_fv_tensor_path_ragged_batch_vs_oracle(api):
 
 
 # fused kernels under test: "1" single CTA; "2" (2-CTA clusters) joins once it has passed on hardware
-FUSED_MODES = ["1"]
+FUSED_MODES = ["1", "2"]
 
 
 def test_fv_fp16x2_path_and_range_guard(api):
