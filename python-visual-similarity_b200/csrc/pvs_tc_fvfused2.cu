@@ -16,6 +16,16 @@
 // (interleaved (y'^2, y') fp16 hi + lo; K-major operand of MMA1 and, read through an MN-major
 // descriptor, operand of MMA2) and then take the zeroth-order sums of the Q chunks of tile g.
 // Image end: S / T and the zeroth-order partials go where the unfused kernels put them.
+//
+// Status (B200, C2 batch): parity-green, 8.0-8.7 ms against 8.2 ms for the two unfused kernels, so it stays opt-in
+// (PVS_FV_FUSED=2).  Role timing per 128-descriptor tile and cluster: tensor pipe busy 4.8 k cycles (MMA1 N = 128: 1.5 k;
+// MMA2 as two N = 64 chunks at the 64-cycle-per-instruction floor: 3.1 k), softmax chain 7 k (accumulator -> max ->
+// exp -> sums -> peer exchange -> operand rows; the two warps of a lane quarter share a scheduler, and the exchange
+// waits absorb the skew between the CTAs), converters 1.4 k on the critical path (A1(g+2) can only be written once
+// MMA2(g) has released the buffer).  Tried on top of this: two softmax teams on alternate tiles (704 threads = 80
+// registers: the chains overlap, but the converters' bubble and the spills then dominate, 10.4-13.3 ms).  What is
+// missing is shared memory for a third A1 tile or an N = 128 Q buffer; the next step is a 4-CTA cluster (W' slice
+// 32 KB per CTA) or fp8-packed lo parts.
 #include "pvs_tc.cuh"
 #include "pvs_kernels.cuh"
 #include <string.h>
