@@ -362,7 +362,8 @@ def run_ours(args):
                        "tc_fv_stats": 2 * T * K * 2 * D, "tc_fv_project": 2 * T * d_in * D,
                        "tc_fv_poststats_fused": 4 * T * K * 2 * D}        # logits + statistics in one kernel
     # algorithmic HBM bytes per image of each kernel: what its interface makes it move
-    bytes_per_image = {"gmm_softmax": 2 * T * K * 4, "fv_finalize": K * (2 * D + 1) * 4 + out_dim * 4 * 3,
+    bytes_per_image = {"gmm_softmax": 2 * T * K * 4,
+                       "fv_finalize": K * 2 * D * 4 + 16 * K * 4 + out_dim * 4,  # S + zeroth-order partials in, encoding out
                        "tc_fv_project": T * (d_in + D) * 4,                    # X in, Y out
                        "tc_fv_posterior": T * (D + K) * 4,                     # Y in, Q out (fp16 hi + lo planes = 4 B)
                        "tc_fv_stats": T * (D + K) * 4 + K * 2 * D * 4}         # Q + Y in, S out
