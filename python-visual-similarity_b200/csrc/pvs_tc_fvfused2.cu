@@ -23,7 +23,10 @@
 // exp -> sums -> peer exchange -> operand rows; the two warps of a lane quarter share a scheduler, and the exchange
 // waits absorb the skew between the CTAs), converters 1.4 k on the critical path (A1(g+2) can only be written once
 // MMA2(g) has released the buffer).  Tried on top of this: two softmax teams on alternate tiles (704 threads = 80
-// registers: the chains overlap, but the converters' bubble and the spills then dominate, 10.4-13.3 ms).  What is
+// registers: the chains overlap, but the converters' bubble and the spills then dominate, 10.4-13.3 ms); one softmax
+// warp per lane quarter with all 128 logits of a row in registers (320 threads, no pair exchange: a single warp per
+// scheduler runs the row at ~0.3 IPC, chain 9.4 k, 12.1 ms); publishing the two k-blocks of A1 separately (removes the
+// a1_full wait, kept for the next version).  What is
 // missing is shared memory for a third A1 tile or an N = 128 Q buffer; the next step is a 4-CTA cluster (W' slice
 // 32 KB per CTA) or fp8-packed lo parts.
 #include "pvs_tc.cuh"
