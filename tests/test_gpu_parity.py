@@ -596,6 +596,33 @@ def test_fv_fused_posterior_statistics_kernel(api, mode):
     assert launches == 5          # project, fused, two gated 3xTF32 kernels, finalize
 
 
+@pytest.mark.parametrize("mode", FUSED_MODES)
+def test_fv_fused_kernels_many_images_per_cta(api, mode):
+    """More images than CTAs / clusters (several images per persistent CTA, statistics accumulator reused,
+    image-end hand-over) and two chunkings: the fused kernels against the default path, bit-identical between
+    the chunkings."""
+    import os
+    rng = np.random.default_rng(123)
+    n = 400
+    ts = rng.integers(1, 300, n)
+    ts[:4] = [1, 128, 129, 256]
+    offs = np.concatenate([[0], np.cumsum(ts)]).astype(np.int64)
+    x = np.floor(np.clip(np.abs(rng.normal(0, 40, (int(offs[-1]), 128))), 0, 255)).astype(np.float32)
+    enc = api.enc.FisherVectorEncoder(feature_extractor=api.feat.Descriptors(128),
+                                      weights=api.enc.GMMWeights.OXFORD102_K256_SIFT_PCA)
+    xd, od = torch.from_numpy(x).cuda(), torch.from_numpy(offs)
+    base = enc.encode_descriptors(xd, od, images_per_call=400).cpu().numpy()
+    os.environ["PVS_FV_FUSED"] = mode
+    try:
+        a = enc.encode_descriptors(xd, od, images_per_call=400).cpu().numpy()
+        b = enc.encode_descriptors(xd, od, images_per_call=150).cpu().numpy()
+    finally:
+        os.environ.pop("PVS_FV_FUSED", None)
+    assert np.array_equal(a, b)
+    assert np.isfinite(a).all() and not np.array_equal(a, base)
+    assert max(rel_l2(a[i], base[i]) for i in range(n)) <= 5e-5
+
+
 def test_fv_tensor_path_without_pca_d64(api):
     """K=256, D=64 GMM fed 64-D descriptors directly (no PCA stage)."""
     w = load_weights("gmm_k256_root_sift_pca")
