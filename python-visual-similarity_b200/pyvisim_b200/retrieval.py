@@ -212,6 +212,52 @@ def all_pairs_topk(vectors, k: int, *, dtype: str = "bf16", rank: int = 0, world
     return scores, idx
 
 
+def all_pairs_topk_ring(vectors, k: int, *, dtype: str = "bf16", rank: int = 0, world: int = 1, group=None,
+                        gather: bool = False, normalized: bool = False):
+    """All-pairs cosine top-k with the database SHARDED and never assembled on one GPU
+    (variant ii; BASELINE.json configs[4]: 1 M x 164 608-D in bf16 is 329 GB,
+    41 GB per rank on 8 GPUs).  Every rank holds its ``shard_bounds`` rows (queries = its own rows).
+    The normalised shards travel around a ring: in step s a rank scores its queries against the
+    shard of rank ``(rank + s) % world`` with the fused top-k kernel while that shard is already on its
+    way to the left neighbour (NCCL send / recv overlapped with the GEMM), and folds the partial list
+    into its running top-k with ``pvs_topk_merge``.  ``world`` steps, ``world - 1`` shard transfers per
+    rank, two shard buffers.  Same ordering rule as a single pass (score descending, lowest global index
+    first), so the result equals ``all_pairs_topk`` on the replicated database.
+    Returns the rank's ``(scores, indices)`` or, with ``gather=True``, all rows on every rank."""
+    import torch
+    import torch.distributed as dist
+    xn = vectors if normalized else l2_normalize(vectors, dtype)
+    if world == 1:
+        return cosine_topk(xn, xn, k)
+    counts = [hi - lo for lo, hi in (shard_bounds_total(xn.shape[0], world, group, r) for r in range(world))]
+    starts = np.concatenate([[0], np.cumsum(counts)])
+    if min(counts) < k:
+        raise ValueError(f"every shard needs at least k = {k} rows (smallest shard: {min(counts)})")
+    pad = max(counts)
+    cur = xn.new_zeros((pad, xn.shape[1]))
+    cur[:xn.shape[0]] = xn
+    nxt = torch.empty_like(cur)
+    best_s = best_i = None
+    left, right = (rank - 1) % world, (rank + 1) % world
+    for step in range(world):
+        src = (rank + step) % world                      # whose shard `cur` holds
+        reqs = []
+        if step + 1 < world:                             # pass it on while it is being scored
+            reqs = dist.batch_isend_irecv([dist.P2POp(dist.isend, cur, left, group),
+                                           dist.P2POp(dist.irecv, nxt, right, group)])
+        s, i = cosine_topk(xn, cur[:counts[src]], k, index_offset=int(starts[src]))
+        if best_s is None:
+            best_s, best_i = s, i
+        else:
+            best_s, best_i = merge_topk(torch.stack([best_s, s]), torch.stack([best_i, i]), k)
+        for r in reqs:
+            r.wait()
+        cur, nxt = nxt, cur
+    if gather:
+        return gather_topk(best_s, best_i, int(starts[-1]), group)
+    return best_s, best_i
+
+
 def shard_bounds_total(local_rows: int, world: int, group, r: int) -> tuple[int, int]:
     """Row range of rank r when only local row counts are known (all ranks call this)."""
     import torch

@@ -165,6 +165,59 @@ def test_gather_topk_world_size_2_gloo(tmp_path):
     assert all("ok" in o for o in outs)
 
 
+RING_WORKER = """
+import os, sys
+sys.path.insert(0, {pkg!r})
+import numpy as np, torch, torch.distributed as dist
+from pyvisim_b200 import retrieval as R
+W = 3
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=W)
+rank = dist.get_rank()
+# CPU stand-ins for the two device calls (test infrastructure: the ring schedule is what is under test)
+def topk_cpu(q, db, k, index_offset=0):
+    s = q @ db.T
+    i = torch.argsort(-s, dim=1, stable=True)[:, :k]
+    return torch.gather(s, 1, i), i + index_offset
+def merge_cpu(sc, ix, k):
+    parts, nq, kk = sc.shape
+    s = sc.permute(1, 0, 2).reshape(nq, parts * kk)
+    i = ix.permute(1, 0, 2).reshape(nq, parts * kk)
+    key = torch.argsort(i, dim=1, stable=True)                    # lowest index first on ties ...
+    s, i = torch.gather(s, 1, key), torch.gather(i, 1, key)
+    o = torch.argsort(-s, dim=1, stable=True)[:, :k]              # ... then score descending (stable)
+    return torch.gather(s, 1, o), torch.gather(i, 1, o)
+R.cosine_topk, R.merge_topk = topk_cpu, merge_cpu
+g = torch.Generator().manual_seed(0)
+n, d, k = 37, 16, 5
+x = torch.randn((n, d), generator=g)
+x = x / x.norm(dim=1, keepdim=True)
+x[7] = x[3]                                                        # exact ties across shards
+lo, hi = R.shard_bounds(n, W, rank)
+s, i = R.all_pairs_topk_ring(x[lo:hi].clone(), k, rank=rank, world=W, normalized=True, gather=True)
+rs, ri = topk_cpu(x, x, k)
+assert torch.equal(i, ri), (rank, (i != ri).nonzero()[:4])
+assert torch.allclose(s, rs)
+dist.barrier()
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_ring_pass_sharded_database_world_size_3_gloo(tmp_path):
+    """all_pairs_topk_ring: every rank only ever holds two shards of the database; three ranks, uneven shards,
+    exact ties across shards; result = a single pass over the whole database."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    script = tmp_path / "ring_worker.py"
+    script.write_text(textwrap.dedent(RING_WORKER.format(pkg=os.path.join(ROOT, "python-visual-similarity_b200"), port=port)))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(3)]
+    outs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("ok" in o for o in outs)
+
+
 def test_allgather_topk_argument_checks_without_a_communicator():
     """C1 export: a NULL communicator is a bad argument (no NCCL, no device needed)."""
     from pyvisim_b200 import _native as N

@@ -23,6 +23,8 @@ ap.add_argument("--dim", type=int, default=32768)
 ap.add_argument("--topk", type=int, default=100)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--native-comm", action="store_true", help="all-gather through pvs_allgather_topk (library-owned NCCL communicator)")
+ap.add_argument("--ring", action="store_true", help="database sharded, shards passed around a ring (retrieval.all_pairs_topk_ring); "
+                                                    "checked against the replicated-database path")
 a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -43,6 +45,8 @@ comm = retrieval.NativeComm() if (a.native_comm and world > 1) else None
 
 
 def step():
+    if a.ring:                                                   # this rank only ever touches two shards at a time
+        return retrieval.all_pairs_topk_ring(x[lo:hi], a.topk, rank=rank, world=world, normalized=True, gather=True)
     s, i = retrieval.cosine_topk(x[lo:hi], x, a.topk)            # this rank's query rows vs the whole database
     return retrieval.gather_topk(s, i, a.rows, comm=comm) if world > 1 else (s, i)
 
@@ -71,9 +75,12 @@ if rank == 0:
     rows = torch.tensor([0, a.rows // 2, a.rows - 1], device=dev)
     s1, i1 = retrieval.cosine_topk(x[rows], x, a.topk)
     ok = bool(torch.equal(i1, i[rows]) and torch.equal(s1, s[rows]))
+    if a.ring:                                                   # the whole result against the replicated-database path
+        s2, i2 = retrieval.cosine_topk(x[lo:hi], x, a.topk)
+        ok = ok and bool(torch.equal(i2, i[lo:hi]) and torch.equal(s2, s[lo:hi]))
     print(json.dumps({"n_gpus": world, "n": a.rows, "d": a.dim, "k": a.topk, "ms": ms, "tflops_total": 2.0 * a.rows * a.rows * a.dim / ms / 1e9,
                       "queries_per_s": a.rows / ms * 1e3, "gathered_shape": list(s.shape),
-                      "gathered_rows_match_single_gpu_pass": ok, "collective": "pvs_allgather_topk" if comm else "torch.distributed all_gather_into_tensor", "scaling": "strong (fixed database, query rows split)"}))
+                      "gathered_rows_match_single_gpu_pass": ok, "collective": ("ring pass of the database shards (NCCL send/recv) + " if a.ring else "") + ("pvs_allgather_topk" if comm else "torch.distributed all_gather_into_tensor"), "scaling": "strong (fixed database, query rows split)"}))
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()
