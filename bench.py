@@ -175,7 +175,7 @@ def run_extras(dev, pk):
 
     out = {}
     g = torch.Generator(device=dev).manual_seed(7)
-    for name, (n, T, D) in {"vlad_c1_rootsift128": (1024, 2000, 128), "vlad_c3_vgg514": (8192, 196, 514)}.items():
+    for name, (n, T, D) in {"vlad_c1_rootsift128": (4096, 2000, 128), "vlad_c3_vgg514": (16384, 196, 514)}.items():
         x = torch.randn((n * T, D), device=dev, generator=g)
         if D == 128:                                      # RootSIFT-like: non-negative, unit L2
             x = x.abs_()
