@@ -471,7 +471,8 @@ extern "C" int pvs_fv_encode(const pvs_model* g, const pvs_model* pca, const flo
         if (pl.fp16x2 && !argmax_out && tc_fv_fused_enabled()) {
             // posterior + statistics in one kernel (the posteriors never leave the SM); behind it the two
             // 3xTF32 kernels that only run when the projection raised the range flag
-            if (int rc = PVS_STAGE(ST_TC_FV_FUSED, st, tc_fv_poststats_fused(pl, g, y, offsets, n_images, st))) return rc;
+            if (int rc = PVS_STAGE(ST_TC_FV_FUSED, st, tc_fv_fused_mode() == 2 ? tc_fv_poststats_fused_cluster(pl, g, y, offsets, n_images, st)
+                                                                               : tc_fv_poststats_fused(pl, g, y, offsets, n_images, st))) return rc;
             if (int rc = PVS_STAGE(ST_TC_FV_POSTERIOR, st, tc_fv_posterior(pl, g, y, total_rows, argmax_out, st, true))) return rc;
             if (int rc = PVS_STAGE(ST_TC_FV_STATS, st, tc_fv_stats(pl, g, y, offsets, n_images, st, true))) return rc;
         } else {

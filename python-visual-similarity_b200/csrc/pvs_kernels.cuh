@@ -77,7 +77,12 @@ int tc_fv_project(const TcFvPlan& pl, const pvs_model* g, const pvs_model* pca, 
 // fallback_only: launch just the gated 3xTF32 kernel (the fp16x2 work was done by the fused kernel)
 int tc_fv_posterior(const TcFvPlan& pl, const pvs_model* g, const float* y, int64_t rows, int32_t* argmax, cudaStream_t st,
                     bool fallback_only = false);
-bool tc_fv_fused_enabled();       // PVS_FV_FUSED set: posterior + statistics in one kernel (opt-in, see pvs_tc_fvfused.cu)
+int tc_fv_poststats_fused_cluster(const TcFvPlan& pl, const pvs_model* g, const float* y, const int64_t* offsets, int64_t n_images,
+                                  cudaStream_t st);
+// PVS_FV_FUSED: posterior + statistics in one kernel (opt-in): 1 = one CTA per SM (pvs_tc_fvfused.cu),
+// 2 = 2-CTA clusters that split the components (pvs_tc_fvfused2.cu)
+int tc_fv_fused_mode();
+inline bool tc_fv_fused_enabled() { return tc_fv_fused_mode() != 0; }
 int tc_fv_poststats_fused(const TcFvPlan& pl, const pvs_model* g, const float* y, const int64_t* offsets, int64_t n_images,
                           cudaStream_t st);
 int tc_fv_stats(const TcFvPlan& pl, const pvs_model* g, const float* y, const int64_t* offsets, int64_t n_images, cudaStream_t st,

@@ -493,7 +493,11 @@ using namespace tc;
 
 // Opt-in (PVS_FV_FUSED=1): parity-green but, at 9.4 ms against 8.2 ms for the two unfused kernels on the C2
 // batch, not the default -- see the header comment and DESIGN.md section 8.
-bool tc_fv_fused_enabled() { return getenv("PVS_FV_FUSED") != nullptr; }
+int tc_fv_fused_mode()
+{
+    const char* e = getenv("PVS_FV_FUSED");
+    return !e ? 0 : (e[0] == '2' ? 2 : 1);
+}
 
 int tc_fv_poststats_fused(const TcFvPlan& pl, const pvs_model* g, const float* y, const int64_t* offsets, int64_t n_images,
                           cudaStream_t st)

@@ -1,12 +1,3 @@
-// NOT COMPILED, NOT PART OF THE LIBRARY.  Kept as the starting point for the next attempt.
-// State: passes tests/test_gpu_parity.py::test_fv_fused_* (ragged images, several images per cluster, two chunkings) and
-// ran the full C2 batch at 7.6-8.7 k cycles per tile in builds with -DPVS_TIMING, but the plain build dies with
-// "unspecified launch failure" (a bounded mbarrier wait trapping, i.e. a hang) on the full batch (592 images per call)
-// even with CUDA_LAUNCH_BLOCKING=1 -- a timing-dependent fault in the cross-CTA exchange that was not found.  The
-// single-CTA kernel (csrc/pvs_tc_fvfused.cu), which shares everything except the exchange, runs the same batch cleanly.
-// One hazard found and fixed here on the way: with ONE count-128 exchange barrier for all four lane quarters, a fast
-// warp's arrivals for tile g + 1 are counted into the phase of tile g while a slower sibling has not delivered its rows;
-// this version has one barrier per lane quarter.
 // pvs_tc_fvfused2.cu -- Fisher vector, K = 256 / D = 64: posterior + per-image statistics in one
 // kernel, CLUSTER version.  pvs_tc_fvfused.cu showed that one CTA cannot overlap anything: the
 // logits (256 columns) and the statistics (256 columns) fill TMEM.  Here a 2-CTA cluster splits
@@ -26,18 +17,20 @@
 // descriptor, operand of MMA2) and then take the zeroth-order sums of the Q chunks of tile g.
 // Image end: S / T and the zeroth-order partials go where the unfused kernels put them.
 //
-// Status (B200, C2 batch): parity-green, 8.0-8.7 ms against 8.2 ms for the two unfused kernels, so it stays opt-in
-// (PVS_FV_FUSED=2).  Role timing per 128-descriptor tile and cluster: tensor pipe busy 4.8 k cycles (MMA1 N = 128: 1.5 k;
-// MMA2 as two N = 64 chunks at the 64-cycle-per-instruction floor: 3.1 k), softmax chain 7 k (accumulator -> max ->
-// exp -> sums -> peer exchange -> operand rows; the two warps of a lane quarter share a scheduler, and the exchange
-// waits absorb the skew between the CTAs), converters 1.4 k on the critical path (A1(g+2) can only be written once
-// MMA2(g) has released the buffer).  Tried on top of this: two softmax teams on alternate tiles (704 threads = 80
-// registers: the chains overlap, but the converters' bubble and the spills then dominate, 10.4-13.3 ms); one softmax
-// warp per lane quarter with all 128 logits of a row in registers (320 threads, no pair exchange: a single warp per
-// scheduler runs the row at ~0.3 IPC, chain 9.4 k, 12.1 ms); publishing the two k-blocks of A1 separately (removes the
-// a1_full wait, kept for the next version).  What is
-// missing is shared memory for a third A1 tile or an N = 128 Q buffer; the next step is a 4-CTA cluster (W' slice
-// 32 KB per CTA) or fp8-packed lo parts.
+// Status (B200, C2 batch): parity-green, stress-tested on the full batch, 780 k images/s for the whole FV step against
+// 705-720 k with the two unfused kernels; opt-in (PVS_FV_FUSED=2) until it has seen more boxes.  Role timing per
+// 128-descriptor tile and cluster: tensor pipe busy 4.8 k cycles (MMA1 N = 128: 1.5 k; MMA2 as two N = 64 chunks at the
+// 64-cycle-per-instruction floor: 3.1 k), softmax chain ~7 k (accumulator -> max -> exp -> sums -> peer exchange ->
+// operand rows; the two warps of a lane quarter share a scheduler), converters 0.5 k on the critical path.
+// Two synchronisation hazards found on the way (both only bit in uninstrumented builds on the full batch):
+//  * one Q-buffer barrier pair polled by parity: with softmax(g) overlapping MMA2(g - 1) a producer can be two uses
+//    ahead of the barrier -> ring of four barriers (use % 4);
+//  * one exchange barrier for all four lane quarters: a fast warp's next-tile arrivals complete the current phase
+//    -> one barrier per lane quarter.
+// Variants measured and dropped: two softmax teams on alternate tiles (704 threads = 80 registers: spills and the
+// converter bubble dominate, 10-13 ms for the kernel); one softmax warp per lane quarter with the whole row in registers
+// (a single warp per scheduler runs at ~0.3 IPC, 12 ms).  Next: shared memory for an N = 128 Q buffer and a third A1
+// tile (4-CTA cluster, 32 KB W' slice per CTA).
 #include "pvs_tc.cuh"
 #include "pvs_kernels.cuh"
 #include <string.h>
@@ -124,8 +117,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) kernel(c
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t *a1_full = bars, *a1_free = bars + 4, *l_full = bars + 6, *l_free = bars + 8;           // a1_full[buffer * 2 + k-block]
-    uint64_t *s_full = bars + 10, *q_full = bars + 11, *q_empty = bars + 12, *w_res = bars + 13, *x_sum = bars + 14;   // x_sum[4]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+    // The one Q buffer is used twice per tile, and the softmax of tile g overlaps the statistics MMAs of tile g - 1: a
+    // producer can be TWO uses ahead of the barrier it polls, and a parity wait is only unambiguous one phase ahead.
+    // So use u signals / polls barrier u % 4 (with a single barrier the uninstrumented build overwrote a chunk that was
+    // still being read and hung on the full C2 batch).
+    uint64_t *s_full = bars + 10, *q_full = bars + 11, *q_empty = bars + 15, *w_res = bars + 19, *x_sum = bars + 20;   // q_full[4], q_empty[4], x_sum[4]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_rank(), peer = rank ^ 1;
     const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
@@ -138,8 +135,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) kernel(c
             mbar_init(&l_free[i], 8);
         }
         mbar_init(s_full, 1);
-        mbar_init(q_full, 4);
-        mbar_init(q_empty, 1 + 4);
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&q_full[i], 4);
+            mbar_init(&q_empty[i], 1 + 4);
+        }
         mbar_init(w_res, 1);
         // One exchange barrier PER LANE QUARTER, signalled by the 32 lanes of the peer's half-0 warp of the same quarter.
         // With one barrier for all four, a fast warp's arrivals for tile g + 1 were counted into the phase of tile g while a
@@ -191,7 +190,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) kernel(c
             for (int n = 0; n < 2; ++n) {
                 const uint32_t use = 2 * gp + (uint32_t)n;
                 FT0(t2);
-                mbar_wait(q_full, use & 1);
+                mbar_wait(&q_full[use & 3], (use >> 2) & 1);
                 FTA(2, t2);
                 tcgen05_fence_after();
                 if (elect_one()) {
@@ -206,7 +205,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) kernel(c
                         umma<true>(d, a_lo, b_hi, idesc2, 1u);
                         umma<true>(d, a_hi, b_hi, idesc2, 1u);
                     }
-                    umma_commit(q_empty);
+                    umma_commit(&q_empty[use & 3]);
                 }
                 __syncwarp();
             }
@@ -366,7 +365,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) kernel(c
                     uint8_t* qh = smem + OFF_Q;
                     uint8_t* ql = qh + 16384;
                     FT0(t10);
-                    mbar_wait(q_empty, (use & 1) ^ 1);
+                    if (use > 0) mbar_wait(&q_empty[(use - 1) & 3], ((use - 1) >> 2) & 1);   // the previous use has been consumed
                     FTA(10, t10);
 #pragma unroll
                     for (int j8 = 0; j8 < 8; ++j8) {
@@ -381,7 +380,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) kernel(c
                     }
                     fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(q_full);
+                    if (lane == 0) mbar_arrive(&q_full[use & 3]);
                 }
                 FTA(9, t9);
             }
@@ -487,7 +486,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) kernel(c
             }
             for (int n = 0; n < 2; ++n) {
                 const uint32_t use = 2 * g + (uint32_t)n;
-                mbar_wait(q_full, use & 1);
+                mbar_wait(&q_full[use & 3], (use >> 2) & 1);
                 const uint8_t* qh = smem + OFF_Q;
                 const uint8_t* ql = qh + 16384;
                 float ax = 0.f, ay = 0.f;
@@ -503,7 +502,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) kernel(c
                 acc[2 * n] += ax;
                 acc[2 * n + 1] += ay;
                 __syncwarp();
-                if (lane == 0) mbar_arrive(q_empty);
+                if (lane == 0) mbar_arrive(&q_empty[use & 3]);
             }
             if (s_last) {
                 float* dst = p.s0part + (s_img * TC_FV_S0_PARTS + cw) * (int64_t)K + rank * CK;
