@@ -50,7 +50,9 @@ typedef enum pvs_status {
 } pvs_status;
 
 typedef enum pvs_model_kind { PVS_MODEL_KMEANS = 1, PVS_MODEL_GMM_DIAG = 2, PVS_MODEL_PCA = 3 } pvs_model_kind;
-typedef enum pvs_dtype { PVS_F32 = 0, PVS_BF16 = 1 } pvs_dtype;
+/* PVS_F16X2: a normalised row v as two fp16 planes with v * 2^15 = hi + lo (22 mantissa bits): hi plane [n, d]
+ * followed by the lo plane [n, d].  Operand format of the fp32-accurate tensor-core similarity. */
+typedef enum pvs_dtype { PVS_F32 = 0, PVS_BF16 = 1, PVS_F16X2 = 2 } pvs_dtype;
 
 /* compute path selector for the contractions (see DESIGN.md "kernels") */
 typedef enum pvs_path {
@@ -125,11 +127,14 @@ int pvs_fv_encode(const pvs_model* gmm, const pvs_model* pca, const float* desc_
 /* posterior only: q fp32 [rows, k] (GaussianMixture.predict_proba, fisher_vector.py:99);
  * y_dev is already PCA-projected [rows, d] */
 int pvs_gmm_posterior(const pvs_model* gmm, const float* y_dev, int64_t rows, float* q_dev, void* stream);
-/* hard assignment only: labels int32 [rows] (KMeans.predict, vlad.py:95) */
-int pvs_kmeans_assign(const pvs_model* kmeans, const float* y_dev, int64_t rows, int32_t* labels_dev, void* stream);
+/* hard assignment only: labels int32 [rows] (KMeans.predict, vlad.py:95).  The score scratch of the
+ * CUDA-core path (k > 256) comes from the caller like every other workspace; 0 bytes on the tcgen05 path. */
+size_t pvs_kmeans_assign_workspace_bytes(const pvs_model* kmeans, int64_t rows);
+int pvs_kmeans_assign(const pvs_model* kmeans, const float* y_dev, int64_t rows, int32_t* labels_dev,
+                      void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* ---- a10: cosine similarity  (_utils.py:312-330 -> sklearn cosine_similarity) --------- */
-/* row L2-normalise fp32 [n, d] -> fp32 or bf16 [n, d]; zero rows stay zero */
+/* row L2-normalise fp32 [n, d] -> fp32 or bf16 [n, d], or PVS_F16X2 planes [2, n, d]; zero rows stay zero */
 int pvs_l2_normalize_rows(const float* x_dev, int64_t n, int64_t d, void* out_dev, int out_dtype, void* stream);
 /* full matrix, fp32: s[n, m] = normalise(x) @ normalise(y)^T.  x/y are RAW (un-normalised)
  * fp32; workspace holds the two normalised copies. */
@@ -142,7 +147,9 @@ int pvs_cosine_matrix(const float* x_dev, int64_t n, const float* y_dev, int64_t
  * For every query row the k best database rows by score, ties broken by lowest index
  * (the reference's np.argsort order on exact ties is unspecified).  Scores descending.
  * idx_out = local database row + db_index_offset (global ids for a sharded database).
- * k <= PVS_TOPK_MAX. */
+ * k <= PVS_TOPK_MAX on the fused tensor-core paths; with fp32 operands any k <= n_db is accepted (the
+ * reference's default k=None ranks the whole database, eval.py:76-80): beyond PVS_TOPK_MAX the scores of a
+ * block of query rows are materialised in the workspace and ranked in passes of PVS_TOPK_MAX. */
 #define PVS_TOPK_MAX 1024
 size_t pvs_cosine_topk_workspace_bytes(int64_t n_q, int64_t n_db, int64_t d, int k, int dtype);
 int pvs_cosine_topk(const void* q_dev, const void* db_dev, int dtype, int64_t n_q, int64_t n_db,
@@ -177,6 +184,30 @@ int pvs_allgather_topk(pvs_comm* comm, const float* scores_dev, const int64_t* i
 int pvs_topk_label_metrics(const int64_t* idx_dev, const int32_t* db_labels_dev,
                            const int32_t* query_labels_dev, int64_t n_q, int k,
                            int32_t* hits_out_dev, float* ap_out_dev, void* stream);
+
+/* ---- f4: learn()  (ImageEncoderBase.learn, encoders/_base_encoder.py:311-342) ----------------
+ * The reference fits KMeans (VLAD) or a diagonal GaussianMixture (FV) with scikit-learn.  These calls are
+ * ONE pass of the respective iteration over the training descriptors x_dev [rows, d]: the E-step runs
+ * the encode path's own kernels (hard assignment / posteriors), the M-step accumulators leave in fp64.
+ * The parameter update (division, variance floor, convergence test) is a few hundred scalars and stays
+ * with the caller, where sklearn does it (cluster/_kmeans.py:_kmeans_single_lloyd,
+ * mixture/_base.py:fit_predict).
+ *   pvs_kmeans_lloyd_step : labels[rows] = arg-min (lowest index on ties), sums[k, d] = sum of the members,
+ *                           counts[k], inertia[1] = sum ||x - c_label||^2
+ *   pvs_gmm_em_step       : s0[k] = sum_t q, s1[k, d] = q^T x, s2[k, d] = q^T x^2,
+ *                           loglik[1] = sum_t logsumexp_k (weighted log prob)  (lower bound * rows)
+ *   pvs_cluster_sums      : the M-step accumulator alone (labels NULL = every row in cluster 0: column sums)
+ *   pvs_rows_sub          : x[r, :] -= v  (sklearn centres X on its mean before Lloyd, _kmeans.py:fit) */
+int pvs_rows_sub(float* x_dev, int64_t rows, int d, const float* v_dev, void* stream);
+int pvs_cluster_sums(const float* x_dev, const int32_t* labels_dev, int64_t rows, int d, int k,
+                     const float* centers_dev, double* sums_dev, int64_t* counts_dev, double* inertia_dev, void* stream);
+size_t pvs_kmeans_lloyd_workspace_bytes(const pvs_model* kmeans, int64_t rows);
+int pvs_kmeans_lloyd_step(const pvs_model* kmeans, const float* x_dev, int64_t rows, int32_t* labels_dev,
+                          double* sums_dev, int64_t* counts_dev, double* inertia_dev, void* workspace_dev,
+                          size_t workspace_bytes, void* stream);
+size_t pvs_gmm_em_workspace_bytes(const pvs_model* gmm, int64_t rows);
+int pvs_gmm_em_step(const pvs_model* gmm, const float* x_dev, int64_t rows, double* s0_dev, double* s1_dev,
+                    double* s2_dev, double* loglik_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* ---- host-buffer entry points (what encode()/similarity_func call with NumPy arrays) --
  * Pinned or pageable host pointers; inputs are staged in image chunks of at most

@@ -35,7 +35,7 @@ __all__ = [
     "pca_transform", "kmeans_predict", "vlad_encode_one", "vlad_encode",
     "gmm_predict_proba", "fv_encode_one", "fv_encode", "pipeline_encode",
     "cosine_similarity", "topk_indices", "cosine_topk", "similarity_score",
-    "top_k_accuracy_from_lists", "top_k_map_from_lists",
+    "top_k_accuracy_from_lists", "top_k_map_from_lists", "kmeans_lloyd", "gmm_em_diag",
 ]
 
 
@@ -299,3 +299,81 @@ def top_k_map_from_lists(topk_idx: np.ndarray, db_labels: np.ndarray, query_labe
         ranks = np.arange(1, len(row) + 1)
         aps.append(float((np.cumsum(rel)[rel] / ranks[rel]).sum() / r))
     return float(np.mean(aps))
+
+
+# --------------------------------------------------------------------------------------
+# f4  learn(): K-Means Lloyd and diagonal-GMM EM with given initial parameters
+# --------------------------------------------------------------------------------------
+def kmeans_lloyd(x: np.ndarray, init: np.ndarray, max_iter: int = 300, tol: float = 1e-4):
+    """``KMeans(init=array, n_init=1, algorithm="lloyd").fit`` as reached from
+    ``_base_encoder.py:333-334,341`` (sklearn ``cluster/_kmeans.py``: ``fit`` centres X on its
+    mean, scales ``tol`` by the mean feature variance, ``_kmeans_single_lloyd`` alternates
+    arg-min labels (lowest index on ties) and member means until the labels repeat or the
+    squared centre shift is <= tol, then re-labels once and adds the mean back).  Clusters that
+    lose all members keep their centre here (sklearn relocates them to far points; the fixtures
+    never trigger it).  Returns (centers, labels, n_iter, inertia) in x's dtype."""
+    x = np.array(x, copy=True)
+    dt = x.dtype
+    mean = x.mean(axis=0)
+    x -= mean
+    centers = np.array(init, dtype=dt, copy=True) - mean
+    tol_abs = np.mean(np.var(x, axis=0)) * tol
+    labels_old = np.full(x.shape[0], -1, np.int32)
+    strict = False
+    n_iter = 0
+    for it in range(max_iter):
+        n_iter = it + 1
+        labels = kmeans_predict(x, centers)
+        new = centers.copy()
+        for j in range(centers.shape[0]):
+            m = labels == j
+            if m.any():
+                new[j] = x[m].sum(axis=0, dtype=dt) / dt.type(m.sum())
+        shift = ((new - centers) ** 2).sum()
+        centers = new
+        if np.array_equal(labels, labels_old):
+            strict = True
+            break
+        if shift <= tol_abs:
+            break
+        labels_old = labels
+    if not strict:
+        labels = kmeans_predict(x, centers)
+    inertia = float(((x - centers[labels]) ** 2).sum(dtype=np.float64))
+    return centers + mean, labels.astype(np.int32), n_iter, inertia
+
+
+def gmm_em_diag(x: np.ndarray, weights_init, means_init, precisions_init, max_iter: int = 100, tol: float = 1e-3,
+                reg_covar: float = 1e-6):
+    """``GaussianMixture(covariance_type="diag", weights_init=, means_init=, precisions_init=).fit``
+    as reached from ``_base_encoder.py:335-341`` (sklearn ``mixture/_base.py:fit_predict`` and
+    ``_gaussian_mixture.py``: E-step = normalised log responsibilities, M-step = nk (+10 eps),
+    means, ``avg_X2 - means**2 + reg_covar``, weights / sum; stop when the mean log-likelihood
+    changes by less than tol).  Returns a dict with the fitted parameters."""
+    x = np.asarray(x)
+    dt = np.result_type(x.dtype, np.asarray(means_init).dtype)   # float32 data with float64 initial parameters runs in float64
+    w = np.asarray(weights_init, dtype=dt)
+    mu = np.asarray(means_init, dtype=dt)
+    pc = np.sqrt(np.asarray(precisions_init, dtype=dt))
+    cov = None
+    lower = -np.inf
+    converged = False
+    n_iter = 0
+    for n_iter in range(1, max_iter + 1):
+        prev = lower
+        wlp = gmm_weighted_log_prob(x, w, mu, pc)
+        lpn = _logsumexp_rows(wlp)
+        with np.errstate(under="ignore"):
+            resp = np.exp(wlp - lpn[:, None])
+        nk = resp.sum(axis=0) + 10 * np.finfo(resp.dtype).eps
+        mu = (resp.T @ x) / nk[:, None]
+        cov = (resp.T @ (x * x)) / nk[:, None] - mu ** 2 + reg_covar
+        w = nk / x.shape[0]
+        w = w / w.sum()
+        pc = 1.0 / np.sqrt(cov)
+        lower = float(np.mean(lpn))
+        if abs(lower - prev) < tol:
+            converged = True
+            break
+    return {"weights": w, "means": mu, "covariances": cov, "precisions_cholesky": pc, "n_iter": n_iter,
+            "lower_bound": lower, "converged": converged}

@@ -324,7 +324,16 @@ static bool assign_use_tc(const pvs_model* km, int64_t rows)
     return g_path.load() != PVS_PATH_SIMT && tc_assign_supported(km, rows);
 }
 
-extern "C" int pvs_kmeans_assign(const pvs_model* km, const float* y, int64_t rows, int32_t* labels, void* stream)
+extern "C" size_t pvs_kmeans_assign_workspace_bytes(const pvs_model* km, int64_t rows)
+{
+    if (!km || km->kind != PVS_MODEL_KMEANS || rows <= 0) return 0;
+    if (assign_use_tc(km, rows)) return 0;                   // the tcgen05 kernel keeps the scores in TMEM
+    const int64_t chunk = rows < ASSIGN_CHUNK_ROWS ? rows : ASSIGN_CHUNK_ROWS;
+    return align_up((size_t)chunk * km->k * sizeof(float), 256) + 256;
+}
+
+extern "C" int pvs_kmeans_assign(const pvs_model* km, const float* y, int64_t rows, int32_t* labels, void* workspace,
+                                 size_t workspace_bytes, void* stream)
 {
     PVS_CHECK(km && km->kind == PVS_MODEL_KMEANS, PVS_ERR_BAD_ARG, "pvs_kmeans_assign: not a K-Means model");
     PVS_CHECK(rows >= 0 && (rows == 0 || (y && labels)), PVS_ERR_BAD_ARG, "pvs_kmeans_assign: bad buffers");
@@ -332,17 +341,17 @@ extern "C" int pvs_kmeans_assign(const pvs_model* km, const float* y, int64_t ro
     cudaStream_t st = (cudaStream_t)stream;
     if (assign_use_tc(km, rows)) return PVS_STAGE(ST_TC_VLAD_ASSIGN, st, tc_vlad_assign(km, y, rows, labels, st));
     PVS_CHECK(g_path.load() != PVS_PATH_TENSOR, PVS_ERR_UNSUPPORTED, "pvs_kmeans_assign: the tensor-core path handles k <= 256 only");
+    const size_t need = pvs_kmeans_assign_workspace_bytes(km, rows);
+    PVS_CHECK(workspace && workspace_bytes >= need, PVS_ERR_WORKSPACE, "pvs_kmeans_assign: workspace %zu < required %zu",
+              workspace_bytes, need);
     const int64_t chunk = rows < ASSIGN_CHUNK_ROWS ? rows : ASSIGN_CHUNK_ROWS;
-    float* scores = nullptr;
-    PVS_CUDA(cudaMallocAsync((void**)&scores, (size_t)chunk * km->k * sizeof(float), st));
-    int rc = PVS_OK;
-    for (int64_t r = 0; r < rows && rc == PVS_OK; r += chunk) {
+    float* scores = (float*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    for (int64_t r = 0; r < rows; r += chunk) {
         const int64_t n = rows - r < chunk ? rows - r : chunk;
-        rc = PVS_STAGE(ST_KM_SCORES, st, launch_gemm_nt(y + r * km->d, km->d, km->centers, km->d, scores, km->k, n, km->k, km->d, 0, -2.f, km->c2, st));
-        if (rc == PVS_OK) rc = PVS_STAGE(ST_KM_ARGMIN, st, launch_row_argmin(scores, n, km->k, labels + r, st));
+        if (int rc = PVS_STAGE(ST_KM_SCORES, st, launch_gemm_nt(y + r * km->d, km->d, km->centers, km->d, scores, km->k, n, km->k, km->d, 0, -2.f, km->c2, st))) return rc;
+        if (int rc = PVS_STAGE(ST_KM_ARGMIN, st, launch_row_argmin(scores, n, km->k, labels + r, st))) return rc;
     }
-    cudaFreeAsync(scores, st);
-    return rc;
+    return PVS_OK;
 }
 
 extern "C" int pvs_gmm_posterior(const pvs_model* g, const float* y, int64_t rows, float* q, void* stream)
@@ -548,6 +557,12 @@ extern "C" int pvs_cosine_matrix(const float* x, int64_t n, const float* y, int6
     return launch_gemm_nt(xn, d, yn, d, s, m, n, (int)m, (int)d, 0, 1.f, nullptr, st);
 }
 
+// S[n, n_db] = Q . DB^T for ALREADY normalised fp32 rows (CUDA-core path)
+static int dense_scores(const float* qf, const float* dbf, int64_t n, int64_t n_db, int64_t d, float* block, cudaStream_t st)
+{
+    return launch_gemm_nt(qf, d, dbf, d, block, n_db, n, (int)n_db, (int)d, 0, 1.f, nullptr, st);
+}
+
 // query rows scored per pass by the dense-block top-k path
 static int64_t topk_block_rows(int64_t n_q, int64_t n_db)
 {
@@ -566,7 +581,8 @@ extern "C" size_t pvs_cosine_topk_workspace_bytes(int64_t n_q, int64_t n_db, int
 {
     if (n_q < 0 || n_db <= 0 || d <= 0 || k <= 0) return 0;
     if (sim_use_tc(dtype, n_q, n_db, d, k)) return tc_sim_workspace_bytes(n_q, n_db, k);
-    size_t b = align_up((size_t)topk_block_rows(n_q, n_db) * n_db * 4, 256) + 256;
+    const int64_t qb = topk_block_rows(n_q, n_db);
+    size_t b = align_up((size_t)qb * n_db * 4, 256) + 2 * align_up((size_t)qb * 8, 256) + 256;
     if (dtype == PVS_BF16) b += align_up((size_t)n_q * d * 4, 256) + align_up((size_t)n_db * d * 4, 256);
     return b;
 }
@@ -576,7 +592,8 @@ extern "C" int pvs_cosine_topk(const void* q, const void* db, int dtype, int64_t
                                size_t workspace_bytes, void* stream)
 {
     PVS_CHECK(n_q >= 0 && n_db > 0 && d >= 2, PVS_ERR_BAD_SHAPE, "pvs_cosine_topk: bad shape");
-    PVS_CHECK(k >= 1 && k <= PVS_TOPK_MAX, PVS_ERR_BAD_ARG, "k must be in [1, %d] (got %d)", PVS_TOPK_MAX, k);
+    PVS_CHECK(k >= 1 && (k <= PVS_TOPK_MAX || k <= n_db), PVS_ERR_BAD_ARG,
+              "k must be in [1, max(%d, n_db = %lld)] (got %d)", PVS_TOPK_MAX, (long long)n_db, k);
     PVS_CHECK(dtype == PVS_F32 || dtype == PVS_BF16, PVS_ERR_BAD_ARG, "unknown dtype %d", dtype);
     if (n_q == 0) return PVS_OK;
     PVS_CHECK(q && db && scores_out && idx_out, PVS_ERR_BAD_ARG, "pvs_cosine_topk: NULL buffer");
@@ -586,7 +603,7 @@ extern "C" int pvs_cosine_topk(const void* q, const void* db, int dtype, int64_t
                          tc_sim_topk(q, db, n_q, n_db, d, k, db_index_offset, scores_out, idx_out, workspace,
                                      workspace_bytes, (cudaStream_t)stream));
     PVS_CHECK(g_path.load() != PVS_PATH_TENSOR, PVS_ERR_UNSUPPORTED,
-              "pvs_cosine_topk: the tensor-core path handles bf16 operands with d %% 8 == 0, d >= 64 only");
+              "pvs_cosine_topk: the tensor-core path handles d %% 8 == 0, d >= 64, k <= %d only", PVS_TOPK_MAX);
     const size_t need = pvs_cosine_topk_workspace_bytes(n_q, n_db, d, k, dtype);
     PVS_CHECK(workspace && workspace_bytes >= need, PVS_ERR_WORKSPACE, "pvs_cosine_topk: workspace %zu < %zu",
               workspace_bytes, need);
@@ -594,10 +611,12 @@ extern "C" int pvs_cosine_topk(const void* q, const void* db, int dtype, int64_t
     char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     const int64_t qb = topk_block_rows(n_q, n_db);
     float* block = (float*)ws;
+    char* p = ws + align_up((size_t)qb * n_db * 4, 256);
+    unsigned long long* bound[2] = {(unsigned long long*)p, (unsigned long long*)(p + align_up((size_t)qb * 8, 256))};
+    p += 2 * align_up((size_t)qb * 8, 256);
     const float* qf = (const float*)q;
     const float* dbf = (const float*)db;
     if (dtype == PVS_BF16) {
-        char* p = ws + align_up((size_t)qb * n_db * 4, 256);
         float* q32 = (float*)p;
         float* db32 = (float*)(p + align_up((size_t)n_q * d * 4, 256));
         if (int rc = launch_bf16_to_f32(q, n_q * d, q32, st)) return rc;
@@ -607,8 +626,15 @@ extern "C" int pvs_cosine_topk(const void* q, const void* db, int dtype, int64_t
     }
     for (int64_t r = 0; r < n_q; r += qb) {
         const int64_t n = n_q - r < qb ? n_q - r : qb;
-        if (int rc = PVS_STAGE(ST_SIM_GEMM, st, launch_gemm_nt(qf + r * d, d, dbf, d, block, n_db, n, (int)n_db, (int)d, 0, 1.f, nullptr, st))) return rc;
-        if (int rc = PVS_STAGE(ST_TOPK_SELECT, st, launch_topk_rows(block, n_db, n, n_db, k, db_index_offset, scores_out + r * k, idx_out + r * k, st))) return rc;
+        if (int rc = PVS_STAGE(ST_SIM_GEMM, st, dense_scores(qf + r * d, dbf, n, n_db, d, block, st))) return rc;
+        // k <= PVS_TOPK_MAX: one selection pass.  Larger k (the reference's default k=None ranks the whole
+        // database, eval.py:76-80): pass p selects the next PVS_TOPK_MAX keys below the last key of pass p - 1.
+        for (int done = 0, pass = 0; done < k; done += PVS_TOPK_MAX, ++pass) {
+            const int kk = k - done < PVS_TOPK_MAX ? k - done : PVS_TOPK_MAX;
+            if (int rc = PVS_STAGE(ST_TOPK_SELECT, st, launch_topk_rows(block, n_db, n, n_db, kk, db_index_offset, scores_out + r * k + done,
+                                                                        idx_out + r * k + done, st, k, pass ? bound[(pass - 1) & 1] : nullptr,
+                                                                        done + kk < k ? bound[pass & 1] : nullptr))) return rc;
+        }
     }
     return PVS_OK;
 }
@@ -646,10 +672,13 @@ struct HostCtx {
     std::mutex mu;
     Slot slot[2];
 };
+// one context per device ordinal: the streams and the staging arena belong to a device
 HostCtx& host_ctx()
 {
-    static HostCtx c;
-    return c;
+    static HostCtx c[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return c[dev & 63];
 }
 int slot_reserve(Slot& s, size_t bytes, size_t n_offs)
 {
@@ -791,7 +820,8 @@ extern "C" int pvs_cosine_topk_host(const float* q, int64_t n_q, const float* db
                                     int use_bf16, float* scores_out, int64_t* idx_out)
 {
     PVS_CHECK(n_q >= 0 && n_db > 0 && d >= 2, PVS_ERR_BAD_SHAPE, "pvs_cosine_topk_host: bad shape");
-    PVS_CHECK(k >= 1 && k <= PVS_TOPK_MAX, PVS_ERR_BAD_ARG, "k must be in [1, %d] (got %d)", PVS_TOPK_MAX, k);
+    PVS_CHECK(k >= 1 && (k <= PVS_TOPK_MAX || (k <= n_db && !use_bf16)), PVS_ERR_BAD_ARG,
+              "k must be in [1, %d] (fp32: up to n_db) (got %d)", PVS_TOPK_MAX, k);
     if (n_q == 0) return PVS_OK;
     PVS_CHECK(q && db && scores_out && idx_out, PVS_ERR_BAD_ARG, "NULL host buffer");
     if (int s = require_device()) return s;

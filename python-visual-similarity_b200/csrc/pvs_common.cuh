@@ -44,6 +44,27 @@ extern std::atomic<int> g_path;
     } while (0)
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Function attributes (dynamic shared-memory limit) and device capabilities are per DEVICE: one bit per
+// device ordinal, so a process that drives several GPUs configures every kernel on each of them.
+// need() is true the first time it is asked about the current device (a duplicate set under a race is harmless).
+struct PerDeviceOnce {
+    std::atomic<unsigned long long> done{0};
+    bool need(int* dev_out = nullptr)
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev_out) *dev_out = dev;
+        const unsigned long long bit = 1ull << (dev & 63);
+        return (done.load(std::memory_order_acquire) & bit) == 0;
+    }
+    void mark()
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        done.fetch_or(1ull << (dev & 63), std::memory_order_release);
+    }
+};
 static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 
 }  // namespace pvs

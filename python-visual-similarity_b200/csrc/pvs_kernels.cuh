@@ -38,8 +38,10 @@ int launch_bf16_to_f32(const void* x, int64_t n, float* out, cudaStream_t st);
 // s[n, m] = cosine of raw rows, for small n * m (one CTA per pair, no workspace)
 int launch_cosine_small(const float* x, int64_t n, const float* y, int64_t m, int64_t d, float* s, cudaStream_t st);
 // per-row top-k of a dense score block S [rows, n_db] (row stride lds)
+// out_ld: row pitch of the outputs (0 = k); upper_in / last_out: multi-pass ranking for k > PVS_TOPK_MAX
 int launch_topk_rows(const float* S, int64_t lds, int64_t rows, int64_t n_db, int k, int64_t idx_offset,
-                     float* scores_out, int64_t* idx_out, cudaStream_t st);
+                     float* scores_out, int64_t* idx_out, cudaStream_t st, int64_t out_ld = 0,
+                     const unsigned long long* upper_in = nullptr, unsigned long long* last_out = nullptr);
 int launch_topk_merge(const float* scores, const int64_t* idx, int parts, int64_t n_q, int k,
                       float* scores_out, int64_t* idx_out, cudaStream_t st);
 int launch_label_metrics(const int64_t* idx, const int32_t* db_labels, const int32_t* q_labels,

@@ -14,6 +14,7 @@
 //   fv_stats/finalize pyvisim/encoders/fisher_vector.py:102-133
 //   l2_normalize      sklearn preprocessing.normalize as used by cosine_similarity
 //   topk_rows         pyvisim/eval.py:40-43 (np.argsort(-scores)[:k])
+#include <cuda_fp16.h>
 #include "pvs_kernels.cuh"
 
 namespace pvs {
@@ -825,6 +826,40 @@ l2_normalize_kernel(const float* __restrict__ x, int64_t d, OutT* __restrict__ o
     }
 }
 
+// Row L2 normalisation into the operand format of the fp32-accurate tensor-core similarity (pvs_tc_sim3.cu):
+// v = x / |x| in fp32 like the other variants, then v * 2^15 = hi + lo with both parts fp16 (|v| <= 1, so the
+// scaled value fits fp16; lo stays a normal fp16 number down to |v| ~ 4e-6).  hi plane [n, d], lo plane right
+// behind it (plane stride n * d).  hi + lo carries 22 mantissa bits of v.
+__global__ void __launch_bounds__(256)
+l2_normalize_split_kernel(const float* __restrict__ x, int64_t d, __half* __restrict__ hi, __half* __restrict__ lo)
+{
+    __shared__ float red[8];
+    __shared__ float s_inv;
+    const float* p = x + (int64_t)blockIdx.x * d;
+    float s = 0.f;
+    for (int64_t j = threadIdx.x; j < d; j += blockDim.x) { const float v = p[j]; s = fmaf(v, v, s); }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(FULL, s, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        const float n = sqrtf(t);
+        s_inv = n == 0.f ? 1.f : n;
+    }
+    __syncthreads();
+    const float n = s_inv;
+    __half* oh = hi + (int64_t)blockIdx.x * d;
+    __half* ol = lo + (int64_t)blockIdx.x * d;
+    for (int64_t j = threadIdx.x; j < d; j += blockDim.x) {
+        const float v = (p[j] / n) * 32768.f;
+        const __half h = __float2half_rn(v);
+        oh[j] = h;
+        ol[j] = __float2half_rn(v - __half2float(h));
+    }
+}
+
 __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ x, int64_t n, float* __restrict__ out)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -881,6 +916,7 @@ int launch_l2_normalize(const float* x, int64_t n, int64_t d, void* out, int out
     PVS_CHECK(n < 2147483647LL, PVS_ERR_BAD_SHAPE, "too many rows");
     if (out_dtype == PVS_F32) PVS_LAUNCH(l2_normalize_kernel<float>, (unsigned)n, 256, 0, st, x, d, (float*)out);
     else if (out_dtype == PVS_BF16) PVS_LAUNCH(l2_normalize_kernel<__nv_bfloat16>, (unsigned)n, 256, 0, st, x, d, (__nv_bfloat16*)out);
+    else if (out_dtype == PVS_F16X2) PVS_LAUNCH(l2_normalize_split_kernel, (unsigned)n, 256, 0, st, x, d, (__half*)out, (__half*)out + n * d);
     else return fail(PVS_ERR_BAD_ARG, "unknown dtype %d", out_dtype);
     return PVS_OK;
 }
@@ -935,8 +971,12 @@ constexpr int TK_CAP = 2048;
 
 __global__ void __launch_bounds__(256)
 topk_rows_kernel(const float* __restrict__ S, int64_t lds, int64_t n_db, int k, int64_t idx_offset,
-                 float* __restrict__ scores_out, int64_t* __restrict__ idx_out)
+                 float* __restrict__ scores_out, int64_t* __restrict__ idx_out, int64_t out_ld,
+                 const unsigned long long* __restrict__ upper_in, unsigned long long* __restrict__ last_out)
 {
+    // upper_in (optional, per row): only keys strictly below it take part -- pass p of a k > TOPK_MAX ranking
+    // continues below the last key of pass p - 1 (last_out).  Keys are unique, so the passes tile the order.
+    const unsigned long long upper = upper_in ? upper_in[blockIdx.x] : ~0ull;
     __shared__ unsigned long long buf[TK_CAP];
     __shared__ int count;
     __shared__ unsigned long long tau;
@@ -944,28 +984,35 @@ topk_rows_kernel(const float* __restrict__ S, int64_t lds, int64_t n_db, int k, 
     for (int i = threadIdx.x; i < TK_CAP; i += blockDim.x) buf[i] = 0ull;
     if (threadIdx.x == 0) { count = 0; tau = 0ull; }
     __syncthreads();
+    // `cnt` mirrors the shared `count` in a register of every thread: it only changes by the result of a
+    // block-wide __syncthreads_count, so the decision to prune is uniform by construction (reading the
+    // shared counter here would race with the appends of warps that are already past the test).
+    int cnt = 0;
     for (int64_t base = 0; base < n_db; base += blockDim.x) {
-        if (count + (int)blockDim.x > TK_CAP) {              // uniform: count read after a barrier
+        if (cnt + (int)blockDim.x > TK_CAP) {
             bitonic_desc(buf, TK_CAP);
             if (threadIdx.x == 0) { tau = buf[k - 1]; count = k; }
+            cnt = k;
             __syncthreads();
             for (int i = k + threadIdx.x; i < TK_CAP; i += blockDim.x) buf[i] = 0ull;
             __syncthreads();
         }
         const int64_t i = base + threadIdx.x;
+        bool appended = false;
         if (i < n_db) {
             const unsigned long long key = topk_key(row[i], (unsigned)i);
-            if (key > tau) buf[atomicAdd(&count, 1)] = key;
+            if (key > tau && key < upper) { buf[atomicAdd(&count, 1)] = key; appended = true; }
         }
-        __syncthreads();
+        cnt += __syncthreads_count(appended);
     }
     bitonic_desc(buf, TK_CAP);
     for (int j = threadIdx.x; j < k; j += blockDim.x) {
         const unsigned long long key = buf[j];
         const bool valid = key != 0ull;
-        scores_out[(int64_t)blockIdx.x * k + j] = valid ? key_score(key) : -INFINITY;
-        idx_out[(int64_t)blockIdx.x * k + j] = valid ? (int64_t)key_index(key) + idx_offset : -1;
+        scores_out[(int64_t)blockIdx.x * out_ld + j] = valid ? key_score(key) : -INFINITY;
+        idx_out[(int64_t)blockIdx.x * out_ld + j] = valid ? (int64_t)key_index(key) + idx_offset : -1;
     }
+    if (last_out && threadIdx.x == 0) last_out[blockIdx.x] = buf[k - 1];     // 0 once the row is exhausted
 }
 
 __global__ void __launch_bounds__(256)
@@ -1001,23 +1048,25 @@ __global__ void label_metrics_kernel(const int64_t* __restrict__ idx, const int3
     if (q >= n_q) return;
     const int32_t lbl = q_labels[q];
     int rel = 0;
-    float psum = 0.f;
+    double psum = 0.0;                                       // the reference sums Python floats (eval.py:88-92)
     for (int j = 0; j < k; ++j) {
-        const int64_t id = idx[q * k + j];
-        if (id >= 0 && db_labels[id] == lbl) { ++rel; psum += (float)rel / (float)(j + 1); }
+        const int64_t id = idx[q * (int64_t)k + j];
+        if (id >= 0 && db_labels[id] == lbl) { ++rel; psum += (double)rel / (double)(j + 1); }
     }
     if (hits) hits[q] = rel > 0;
-    if (ap) ap[q] = rel > 0 ? psum / (float)rel : 0.f;      // quirk Q6: R counted inside the list
+    if (ap) ap[q] = rel > 0 ? (float)(psum / (double)rel) : 0.f;      // quirk Q6: R counted inside the list
 }
 }  // namespace
 
 int launch_topk_rows(const float* S, int64_t lds, int64_t rows, int64_t n_db, int k, int64_t idx_offset,
-                     float* scores_out, int64_t* idx_out, cudaStream_t st)
+                     float* scores_out, int64_t* idx_out, cudaStream_t st, int64_t out_ld,
+                     const unsigned long long* upper_in, unsigned long long* last_out)
 {
     if (rows <= 0) return PVS_OK;
-    PVS_CHECK(k >= 1 && k <= PVS_TOPK_MAX, PVS_ERR_BAD_ARG, "k must be in [1, %d] (got %d)", PVS_TOPK_MAX, k);
+    PVS_CHECK(k >= 1 && k <= PVS_TOPK_MAX, PVS_ERR_BAD_ARG, "k must be in [1, %d] per pass (got %d)", PVS_TOPK_MAX, k);
     PVS_CHECK(n_db < 4294967295LL, PVS_ERR_BAD_SHAPE, "database shard must have < 2^32 rows");
-    PVS_LAUNCH(topk_rows_kernel, (unsigned)rows, 256, 0, st, S, lds, n_db, k, idx_offset, scores_out, idx_out);
+    PVS_LAUNCH(topk_rows_kernel, (unsigned)rows, 256, 0, st, S, lds, n_db, k, idx_offset, scores_out, idx_out,
+               out_ld > 0 ? out_ld : (int64_t)k, upper_in, last_out);
     return PVS_OK;
 }
 

@@ -531,10 +531,10 @@ template <class P>
 int launch_tc(const typename P::Params& prm, int n_tiles, cudaStream_t st, int grid_override = 0)
 {
     using L = Layout<P>;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.need()) {
         PVS_CUDA(cudaFuncSetAttribute(tc_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_BYTES));
-        configured = true;
+        configured.mark();
     }
     if (n_tiles <= 0) return PVS_OK;
     int dev = 0, sms = 148;

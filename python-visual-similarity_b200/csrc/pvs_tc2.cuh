@@ -428,10 +428,10 @@ template <class P>
 int launch_tc2(const typename P::Params& prm, int n_tiles, cudaStream_t st, int pairs_override = 0)
 {
     using L = Layout2<P>;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.need()) {
         PVS_CUDA(cudaFuncSetAttribute(tc2_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_BYTES));
-        configured = true;
+        configured.mark();
     }
     if (n_tiles <= 0) return PVS_OK;
     int dev = 0, sms = 148;

@@ -495,18 +495,20 @@ using namespace tc;
 // batch, not the default -- see the header comment and DESIGN.md section 8.
 int tc_fv_fused_mode()
 {
+    // default: the 2-CTA cluster kernel (pvs_tc_fvfused2.cu).  PVS_FV_FUSED=0 selects the two unfused kernels,
+    // =1 the single-CTA fused kernel (both kept as parity references for the tests).
     const char* e = getenv("PVS_FV_FUSED");
-    return !e ? 0 : (e[0] == '2' ? 2 : 1);
+    return !e ? 2 : (e[0] == '0' ? 0 : e[0] == '1' ? 1 : 2);
 }
 
 int tc_fv_poststats_fused(const TcFvPlan& pl, const pvs_model* g, const float* y, const int64_t* offsets, int64_t n_images,
                           cudaStream_t st)
 {
     if (n_images <= 0) return PVS_OK;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.need()) {
         PVS_CUDA(cudaFuncSetAttribute(fused::kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::SMEM_BYTES));
-        configured = true;
+        configured.mark();
     }
     fused::Params p{};
     int rc;

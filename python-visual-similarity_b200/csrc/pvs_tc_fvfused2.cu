@@ -531,10 +531,10 @@ int tc_fv_poststats_fused_cluster(const TcFvPlan& pl, const pvs_model* g, const 
                                   cudaStream_t st)
 {
     if (n_images <= 0) return PVS_OK;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.need()) {
         PVS_CUDA(cudaFuncSetAttribute(fusedc::kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fusedc::SMEM_BYTES));
-        configured = true;
+        configured.mark();
     }
     fusedc::Params p{};
     int rc;

@@ -213,15 +213,19 @@ static int run_gemm2(const GemmParams& prm, cudaStream_t st) { return tc2::launc
 
 bool tc_available()
 {
-    static int ok = -1;
-    if (ok < 0) {
-        int dev = 0, major = 0;
-        ok = (cudaGetDevice(&dev) == cudaSuccess &&
-              cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) == cudaSuccess && major == 10 &&
-              tc::encode_tiled_fn() != nullptr) ? 1 : 0;
+    // cached per device ordinal (0 = unknown, 1 = yes, 2 = no): a process may drive several GPUs
+    static std::atomic<signed char> ok[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return false; }
+    signed char v = ok[dev & 63].load(std::memory_order_relaxed);
+    if (v == 0) {
+        int major = 0;
+        v = (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) == cudaSuccess && major == 10 &&
+             tc::encode_tiled_fn() != nullptr) ? 1 : 2;
         cudaGetLastError();
+        ok[dev & 63].store(v, std::memory_order_relaxed);
     }
-    return ok == 1;
+    return v == 1;
 }
 
 }  // namespace pvs

@@ -60,7 +60,8 @@ EXPORTS = {
     "pvs_fv_workspace_bytes": (_sz, [_vp, _vp, _i64, _i64]),
     "pvs_fv_encode": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _f32, _f32, _f32, _vp, _vp, _vp, _sz, _vp]),
     "pvs_gmm_posterior": (_i32, [_vp, _vp, _i64, _vp, _vp]),
-    "pvs_kmeans_assign": (_i32, [_vp, _vp, _i64, _vp, _vp]),
+    "pvs_kmeans_assign_workspace_bytes": (_sz, [_vp, _i64]),
+    "pvs_kmeans_assign": (_i32, [_vp, _vp, _i64, _vp, _vp, _sz, _vp]),
     "pvs_l2_normalize_rows": (_i32, [_vp, _i64, _i64, _vp, _i32, _vp]),
     "pvs_cosine_matrix_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "pvs_cosine_matrix": (_i32, [_vp, _i64, _vp, _i64, _i64, _vp, _vp, _sz, _vp]),
@@ -68,6 +69,12 @@ EXPORTS = {
     "pvs_cosine_topk": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _i32, _i64, _vp, _vp, _vp, _sz, _vp]),
     "pvs_topk_merge": (_i32, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp]),
     "pvs_topk_label_metrics": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "pvs_rows_sub": (_i32, [_vp, _i64, _i32, _vp, _vp]),
+    "pvs_cluster_sums": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "pvs_kmeans_lloyd_workspace_bytes": (_sz, [_vp, _i64]),
+    "pvs_kmeans_lloyd_step": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "pvs_gmm_em_workspace_bytes": (_sz, [_vp, _i64]),
+    "pvs_gmm_em_step": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pvs_nccl_load": (_i32, [C.c_char_p]),
     "pvs_comm_unique_id": (_i32, [_vp]),
     "pvs_comm_create": (_i32, [_vp, _i32, _i32, _pp]),

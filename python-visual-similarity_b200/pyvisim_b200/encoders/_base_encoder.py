@@ -318,6 +318,32 @@ class ImageEncoderBase(SimilarityMetric):
             images = [images]                                   # single image
         return [self.feature_extractor(image) for image in images]
 
+    def _extract_on_device(self, images, batch: int = 64):
+        """Extractors that can run batched on the GPU (``DeepConvFeature.extract_batch``) hand their
+        descriptors to the encoder device-to-device: no ``.cpu().numpy()`` bounce per image
+        (reference ``_features.py:283-300``).  Returns (descriptors CUDA tensor, offsets) or None."""
+        fe = self.feature_extractor
+        if not hasattr(fe, "extract_batch") or getattr(getattr(fe, "device", None), "type", "cpu") != "cuda":
+            return None
+        import itertools
+        import torch
+        if isinstance(images, torch.Tensor):
+            raise RuntimeError("Torch images are not supported yet.")
+        if isinstance(images, np.ndarray) and images.ndim == 3:
+            images = [images]
+        it = iter(images)
+        descs, counts = [], []
+        while True:
+            chunk = list(itertools.islice(it, batch))
+            if not chunk:
+                break
+            d, o = fe.extract_batch(chunk)
+            descs.append(d)
+            counts.extend(np.diff(o.cpu().numpy()).tolist())
+        if not descs:
+            raise ValueError("need at least one array to concatenate")
+        return torch.cat(descs), np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+
     @abc.abstractmethod
     def encode(self, images: Iterable[np.ndarray] | np.ndarray) -> np.ndarray:
         raise NotImplementedError
@@ -328,24 +354,29 @@ class ImageEncoderBase(SimilarityMetric):
 
     def learn(self, images: Iterable[np.ndarray], /, *, n_clusters: int, dim_reduction_factor: int = None,
               **kwargs) -> None:
-        """Fit the vocabulary (reference ``_base_encoder.py:311-342``).  Training is not on
-        the hot path and runs scikit-learn on the host; the
-        fitted estimator is then uploaded like any other."""
-        from sklearn.cluster import KMeans
-        from sklearn.decomposition import PCA
-        from sklearn.mixture import GaussianMixture
+        """Fit the vocabulary (reference ``_base_encoder.py:311-342``): same signature, prints and
+        estimator objects, but the Lloyd / EM iterations run on the GPU (``encoders/_learn.py``:
+        ``pvs_kmeans_lloyd_step`` / ``pvs_gmm_em_step`` through the C ABI).  ``**kwargs`` are scikit-learn's
+        ``KMeans`` / ``GaussianMixture`` keywords, as in the reference.  The optional PCA
+        (``dim_reduction_factor``) is a one-off SVD of the training matrix and stays with scikit-learn."""
+        from ._learn import fit_gmm, fit_kmeans
         feats = np.vstack([self.feature_extractor(image) for image in images])
+        print("[INFO] Learning the visual vocabulary with the following parameters:")
+        print("   - Number of clusters:", n_clusters)
+        print("   - Feature Extractor used:", self.feature_extractor.__class__.__name__)
+        print("   - Dimension of the feature space:", feats.shape[1])
         if dim_reduction_factor:
+            from sklearn.decomposition import PCA
+            print("   - New dimension after PCA reduction:", feats.shape[1] // dim_reduction_factor)
             self._pca = PCA(n_components=feats.shape[1] // dim_reduction_factor)
             feats = self._pca.fit(feats).transform(feats)
             self._handles.pop("pca", None)
         if type(self).__name__ == "VLADEncoder":
-            model = KMeans(n_clusters=n_clusters, **kwargs)
+            model = fit_kmeans(feats, n_clusters, **kwargs)
         elif type(self).__name__ == "FisherVectorEncoder":
-            model = GaussianMixture(n_components=n_clusters, **kwargs, covariance_type="diag")
+            model = fit_gmm(feats, n_clusters, **kwargs)
         else:
             raise ValueError("Unknown encoder class.")
-        model.fit(feats)
         self.clustering_model = model
 
     @_tupleize_first_arg

@@ -67,6 +67,9 @@ class FisherVectorEncoder(ImageEncoderBase):
         return int(2 * k * d + k)
 
     def encode(self, images: Iterable[np.ndarray] | np.ndarray) -> np.ndarray:
+        on_dev = self._extract_on_device(images)
+        if on_dev is not None:                                  # conv features stay on the device
+            return self.encode_descriptors(*on_dev).cpu().numpy().astype(self.output_dtype, copy=False)
         descs = self._extract(images)
         for dsc in descs:
             if dsc is None or dsc.shape[0] == 0:

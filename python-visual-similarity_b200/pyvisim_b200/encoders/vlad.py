@@ -56,8 +56,12 @@ class VLADEncoder(ImageEncoderBase):
         return int(c.shape[0] * c.shape[1])
 
     def encode(self, images: Iterable[np.ndarray] | np.ndarray) -> np.ndarray:
-        descs = self._extract(images)
         k, d = self.clustering_model.cluster_centers_.shape
+        on_dev = self._extract_on_device(images)
+        if on_dev is not None:                                  # conv features: never empty, stay on the device
+            out = self.encode_descriptors(*on_dev).cpu().numpy()
+            return out if self.flatten else out.reshape(out.shape[0] * k, d)
+        descs = self._extract(images)
         for dsc in descs:
             if dsc is None or dsc.shape[0] == 0:
                 if self.pca:

@@ -184,7 +184,7 @@ def all_pairs_topk(vectors, k: int, *, dtype: str = "bf16", rank: int = 0, world
     import torch.distributed as dist
     xn = l2_normalize(vectors, dtype)
     if world > 1 and database_is_sharded:
-        counts = [hi - lo for lo, hi in (shard_bounds_total(xn.shape[0], world, group, r) for r in range(world))]
+        counts = gather_shard_counts(xn.shape[0], world, group)
         n_total = sum(counts)
         pad = max(counts)
         mine = xn if xn.shape[0] == pad else torch.cat([xn, xn.new_zeros((pad - xn.shape[0], xn.shape[1]))])
@@ -194,6 +194,7 @@ def all_pairs_topk(vectors, k: int, *, dtype: str = "bf16", rank: int = 0, world
             keep = torch.cat([torch.arange(r * pad, r * pad + c) for r, c in enumerate(counts)]).to(xn.device)
             full = full[keep]
         db, q = full, xn
+        lo = sum(counts[:rank])
     else:
         n_total = xn.shape[0]
         lo, hi = shard_bounds(n_total, world, rank)
@@ -201,7 +202,6 @@ def all_pairs_topk(vectors, k: int, *, dtype: str = "bf16", rank: int = 0, world
     kk = k + 1 if exclude_self else k
     scores, idx = cosine_topk(q, db, kk)
     if exclude_self:
-        lo, _ = shard_bounds(n_total, world, rank)
         own = torch.arange(lo, lo + q.shape[0], device=idx.device).unsqueeze(1)
         keep = idx != own
         # drop the self column where present, else the last column
@@ -229,7 +229,7 @@ def all_pairs_topk_ring(vectors, k: int, *, dtype: str = "bf16", rank: int = 0, 
     xn = vectors if normalized else l2_normalize(vectors, dtype)
     if world == 1:
         return cosine_topk(xn, xn, k)
-    counts = [hi - lo for lo, hi in (shard_bounds_total(xn.shape[0], world, group, r) for r in range(world))]
+    counts = gather_shard_counts(xn.shape[0], world, group)
     starts = np.concatenate([[0], np.cumsum(counts)])
     if min(counts) < k:
         raise ValueError(f"every shard needs at least k = {k} rows (smallest shard: {min(counts)})")
@@ -258,23 +258,18 @@ def all_pairs_topk_ring(vectors, k: int, *, dtype: str = "bf16", rank: int = 0, 
     return best_s, best_i
 
 
-def shard_bounds_total(local_rows: int, world: int, group, r: int) -> tuple[int, int]:
-    """Row range of rank r when only local row counts are known (all ranks call this)."""
+def gather_shard_counts(local_rows: int, world: int, group=None) -> list[int]:
+    """Row count of every rank's shard.  A collective: EVERY rank of the group must call it, every
+    time (nothing is cached -- a cache keyed on the local count alone lets ranks disagree about
+    whether to enter the all-gather when only a peer's shard changed)."""
     import torch
     import torch.distributed as dist
-    cache = getattr(shard_bounds_total, "_cache", None)
-    key = (local_rows, world, id(group))
-    if cache is None or cache[0] != key:
-        t = torch.tensor([local_rows], dtype=torch.int64)
-        if dist.get_backend(group) == "nccl":
-            t = t.cuda()
-        out = [torch.zeros_like(t) for _ in range(world)]
-        dist.all_gather(out, t, group=group)
-        counts = [int(o.item()) for o in out]
-        starts = np.concatenate([[0], np.cumsum(counts)])
-        shard_bounds_total._cache = cache = (key, starts)
-    starts = cache[1]
-    return int(starts[r]), int(starts[r + 1])
+    t = torch.tensor([int(local_rows)], dtype=torch.int64)
+    if dist.get_backend(group) == "nccl":
+        t = t.cuda()
+    out = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(out, t, group=group)
+    return [int(o.item()) for o in out]
 
 
 def label_metrics(topk_idx, db_labels, query_labels):

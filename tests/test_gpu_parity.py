@@ -564,7 +564,7 @@ def test_fv_fp16x2_path_and_range_guard(api):
 
 @pytest.mark.parametrize("mode", FUSED_MODES)
 def test_fv_fused_posterior_statistics_kernel(api, mode):
-    """Opt-in fused kernels (PVS_FV_FUSED=1 / 2: posterior + statistics in one kernel, the [y^2|y] tile serving as
+    """Fused kernels (PVS_FV_FUSED=2, the default, and =1: posterior + statistics in one kernel, the [y^2|y] tile serving as
     K-major operand of the logit MMA and as MN-major operand of the statistics MMA): ragged images incl.
     T = 1, 127, 128, 129 vs the fp64 oracle and vs the default (unfused) path."""
     import os
@@ -578,6 +578,7 @@ def test_fv_fused_posterior_statistics_kernel(api, mode):
         descs.append((y @ p["components"] + p["mean"]).astype(np.float32))
     enc = api.enc.FisherVectorEncoder(feature_extractor=api.feat.Descriptors(128),
                                       weights=api.enc.GMMWeights.OXFORD102_K256_SIFT_PCA)
+    os.environ["PVS_FV_FUSED"] = "0"                          # the two unfused kernels
     base = enc.encode(descs)
     os.environ["PVS_FV_FUSED"] = mode
     try:
@@ -610,6 +611,7 @@ def test_fv_fused_kernels_many_images_per_cta(api, mode):
     enc = api.enc.FisherVectorEncoder(feature_extractor=api.feat.Descriptors(128),
                                       weights=api.enc.GMMWeights.OXFORD102_K256_SIFT_PCA)
     xd, od = torch.from_numpy(x).cuda(), torch.from_numpy(offs)
+    os.environ["PVS_FV_FUSED"] = "0"                          # the two unfused kernels
     base = enc.encode_descriptors(xd, od, images_per_call=400).cpu().numpy()
     os.environ["PVS_FV_FUSED"] = mode
     try:
