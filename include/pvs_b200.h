@@ -143,7 +143,11 @@ int pvs_cosine_matrix(const float* x_dev, int64_t n, const float* y_dev, int64_t
                       float* s_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* ---- a10 + a11: similarity with fused top-k  (eval.py:37-43, 76-80, 131-132) ----------
- * q_dev [n_q, d], db_dev [n_db, d]: ALREADY row-normalised, dtype fp32 or bf16.
+ * q_dev [n_q, d], db_dev [n_db, d]: ALREADY row-normalised, dtype fp32, bf16 or PVS_F16X2 planes.
+ * bf16: one tensor-core pass, scores within 1e-2.  PVS_F16X2 (and fp32 rows, converted on the fly): three
+ * kind::f16 passes with segmented accumulation, a shortlist of k + 8 candidates per query and an exact
+ * re-evaluation of every candidate the tensor scores cannot order: indices equal the fp64 ranking of the
+ * operands, scores within 1e-4 (tests/test_gpu_sim_exact.py).
  * For every query row the k best database rows by score, ties broken by lowest index
  * (the reference's np.argsort order on exact ties is unspecified).  Scores descending.
  * idx_out = local database row + db_index_offset (global ids for a sharded database).
@@ -155,6 +159,12 @@ size_t pvs_cosine_topk_workspace_bytes(int64_t n_q, int64_t n_db, int64_t d, int
 int pvs_cosine_topk(const void* q_dev, const void* db_dev, int dtype, int64_t n_q, int64_t n_db,
                     int64_t d, int k, int64_t db_index_offset, float* scores_out_dev,
                     int64_t* idx_out_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+/* After a pvs_cosine_topk call that took the fp32-accurate tensor-core path (PVS_F16X2 operands, or PVS_F32 rows
+ * on a device with tcgen05): number of shortlisted candidates whose score was re-evaluated exactly because the
+ * tensor-core scores could not order them (closer than the error bound), and number of query rows whose ambiguous
+ * run reached the end of the shortlist (0 unless many database rows are near-identical).  Synchronises `stream`. */
+int pvs_cosine_topk_exact_stats(const void* workspace_dev, int64_t n_q, int64_t n_db, int k, int64_t* rescored,
+                                int64_t* unresolved, void* stream);
 /* merge `parts` top-k lists per row (scores/idx laid out [parts, n_q, k]) into one
  * [n_q, k] list with the same ordering rule -- used when the DATABASE is sharded. */
 int pvs_topk_merge(const float* scores_dev, const int64_t* idx_dev, int parts, int64_t n_q, int k,

@@ -45,11 +45,11 @@ constexpr int64_t ASSIGN_CHUNK_ROWS = 1 << 18;
 // ---- optional per-stage device timing (CUDA events on the launching stream) -------------
 enum Stage { ST_PCA = 0, ST_KM_SCORES, ST_KM_ARGMIN, ST_VLAD_AGG, ST_GMM_LOGITS, ST_GMM_SOFTMAX, ST_FV_STATS,
              ST_FV_FINALIZE, ST_L2NORM, ST_SIM_GEMM, ST_TOPK_SELECT, ST_TC_VLAD_ASSIGN, ST_TC_FV_POSTERIOR,
-             ST_TC_FV_STATS, ST_TC_SIM_TOPK, ST_TC_FV_PREP, ST_TC_FV_PROJECT, ST_TC_GEMM_PCA, ST_TC_GEMM_LOGITS, ST_TC_FV_FUSED, ST_COUNT };
+             ST_TC_FV_STATS, ST_TC_SIM_TOPK, ST_TC_FV_PREP, ST_TC_FV_PROJECT, ST_TC_GEMM_PCA, ST_TC_GEMM_LOGITS, ST_TC_FV_FUSED, ST_TC_SIM_DENSE, ST_TC_SIM3_TOPK, ST_COUNT };
 static const char* kStageNames[ST_COUNT] = {
     "pca_project", "kmeans_scores", "kmeans_argmin", "vlad_aggregate", "gmm_logits", "gmm_softmax", "fv_stats",
     "fv_finalize", "l2_normalize", "sim_gemm", "topk_select", "tc_vlad_assign", "tc_fv_posterior", "tc_fv_stats",
-    "tc_sim_topk", "tc_fv_prep", "tc_fv_project", "tc_gemm_pca", "tc_gemm_logits", "tc_fv_poststats_fused"};
+    "tc_sim_topk", "tc_fv_prep", "tc_fv_project", "tc_gemm_pca", "tc_gemm_logits", "tc_fv_poststats_fused", "tc_sim3_dense", "tc_sim3_topk"};
 struct StageRec { int stage; cudaEvent_t a, b; };
 static std::mutex g_prof_mu;
 static std::atomic<int> g_prof_on{0};
@@ -536,6 +536,11 @@ extern "C" size_t pvs_cosine_matrix_workspace_bytes(int64_t n, int64_t m, int64_
     return align_up((size_t)n * d * 4, 256) + align_up((size_t)m * d * 4, 256) + 256;
 }
 
+static bool matrix_use_tc(int64_t n, int64_t m, int64_t d)
+{
+    return g_path.load() != PVS_PATH_SIMT && tc_sim3_supported(n, m, d, 1);
+}
+
 extern "C" int pvs_cosine_matrix(const float* x, int64_t n, const float* y, int64_t m, int64_t d, float* s,
                                  void* workspace, size_t workspace_bytes, void* stream)
 {
@@ -550,11 +555,22 @@ extern "C" int pvs_cosine_matrix(const float* x, int64_t n, const float* y, int6
     PVS_CHECK(workspace && workspace_bytes >= need, PVS_ERR_WORKSPACE, "pvs_cosine_matrix: workspace %zu < %zu",
               workspace_bytes, need);
     char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    if (matrix_use_tc(n, m, d)) {
+        // tcgen05: rows normalised straight into fp16 hi + lo planes (the same 4 bytes per element as an fp32 copy),
+        // three kind::f16 passes with segmented accumulation (pvs_tc_sim.cu: SimSplitPolicy<.., DENSE>)
+        void* xp = ws;
+        void* yp = ws + align_up((size_t)n * d * 4, 256);
+        if (int rc = PVS_STAGE(ST_L2NORM, st, launch_l2_normalize(x, n, d, xp, PVS_F16X2, st))) return rc;
+        if (int rc = PVS_STAGE(ST_L2NORM, st, launch_l2_normalize(y, m, d, yp, PVS_F16X2, st))) return rc;
+        return PVS_STAGE(ST_TC_SIM_DENSE, st, tc_sim3_dense(xp, yp, n, m, d, s, m, st));
+    }
+    PVS_CHECK(g_path.load() != PVS_PATH_TENSOR, PVS_ERR_UNSUPPORTED,
+              "pvs_cosine_matrix: the tensor-core path needs d %% 8 == 0 and d >= 64");
     float* xn = (float*)ws;
     float* yn = (float*)(ws + align_up((size_t)n * d * 4, 256));
     if (int rc = launch_l2_normalize(x, n, d, xn, PVS_F32, st)) return rc;
     if (int rc = launch_l2_normalize(y, m, d, yn, PVS_F32, st)) return rc;
-    return launch_gemm_nt(xn, d, yn, d, s, m, n, (int)m, (int)d, 0, 1.f, nullptr, st);
+    return PVS_STAGE(ST_SIM_GEMM, st, launch_gemm_nt(xn, d, yn, d, s, m, n, (int)m, (int)d, 0, 1.f, nullptr, st));
 }
 
 // S[n, n_db] = Q . DB^T for ALREADY normalised fp32 rows (CUDA-core path)
@@ -576,11 +592,22 @@ static bool sim_use_tc(int dtype, int64_t n_q, int64_t n_db, int64_t d, int k)
 {
     return g_path.load() != PVS_PATH_SIMT && tc_sim_supported(dtype, n_q, n_db, d, k);
 }
+// fp32-accurate tensor path (split operands).  Planes always take it; fp32 rows are converted first, which only
+// pays off above a few million multiply-adds (below that the dense CUDA-core block is as fast).
+static bool sim3_use_tc(int dtype, int64_t n_q, int64_t n_db, int64_t d, int k)
+{
+    if (g_path.load() == PVS_PATH_SIMT || !tc_sim3_supported(n_q, n_db, d, k)) return false;
+    if (dtype == PVS_F16X2) return true;
+    return dtype == PVS_F32 && (g_path.load() == PVS_PATH_TENSOR || (double)n_q * (double)n_db * (double)d >= 16777216.0);
+}
 
 extern "C" size_t pvs_cosine_topk_workspace_bytes(int64_t n_q, int64_t n_db, int64_t d, int k, int dtype)
 {
     if (n_q < 0 || n_db <= 0 || d <= 0 || k <= 0) return 0;
     if (sim_use_tc(dtype, n_q, n_db, d, k)) return tc_sim_workspace_bytes(n_q, n_db, k);
+    if (sim3_use_tc(dtype, n_q, n_db, d, k))
+        return tc_sim3_workspace_bytes(n_q, n_db, k) +
+               (dtype == PVS_F32 ? align_up((size_t)n_q * d * 4, 1024) + align_up((size_t)n_db * d * 4, 1024) + 1024 : 0);
     const int64_t qb = topk_block_rows(n_q, n_db);
     size_t b = align_up((size_t)qb * n_db * 4, 256) + 2 * align_up((size_t)qb * 8, 256) + 256;
     if (dtype == PVS_BF16) b += align_up((size_t)n_q * d * 4, 256) + align_up((size_t)n_db * d * 4, 256);
@@ -594,7 +621,7 @@ extern "C" int pvs_cosine_topk(const void* q, const void* db, int dtype, int64_t
     PVS_CHECK(n_q >= 0 && n_db > 0 && d >= 2, PVS_ERR_BAD_SHAPE, "pvs_cosine_topk: bad shape");
     PVS_CHECK(k >= 1 && (k <= PVS_TOPK_MAX || k <= n_db), PVS_ERR_BAD_ARG,
               "k must be in [1, max(%d, n_db = %lld)] (got %d)", PVS_TOPK_MAX, (long long)n_db, k);
-    PVS_CHECK(dtype == PVS_F32 || dtype == PVS_BF16, PVS_ERR_BAD_ARG, "unknown dtype %d", dtype);
+    PVS_CHECK(dtype == PVS_F32 || dtype == PVS_BF16 || dtype == PVS_F16X2, PVS_ERR_BAD_ARG, "unknown dtype %d", dtype);
     if (n_q == 0) return PVS_OK;
     PVS_CHECK(q && db && scores_out && idx_out, PVS_ERR_BAD_ARG, "pvs_cosine_topk: NULL buffer");
     PVS_CHECK(d < 2147483647LL && n_db < 2147483647LL, PVS_ERR_BAD_SHAPE, "pvs_cosine_topk: dimension too large");
@@ -602,8 +629,31 @@ extern "C" int pvs_cosine_topk(const void* q, const void* db, int dtype, int64_t
         return PVS_STAGE(ST_TC_SIM_TOPK, (cudaStream_t)stream,
                          tc_sim_topk(q, db, n_q, n_db, d, k, db_index_offset, scores_out, idx_out, workspace,
                                      workspace_bytes, (cudaStream_t)stream));
+    if (sim3_use_tc(dtype, n_q, n_db, d, k)) {
+        cudaStream_t st = (cudaStream_t)stream;
+        const size_t need = pvs_cosine_topk_workspace_bytes(n_q, n_db, d, k, dtype);
+        PVS_CHECK(workspace && workspace_bytes >= need, PVS_ERR_WORKSPACE, "pvs_cosine_topk: workspace %zu < %zu",
+                  workspace_bytes, need);
+        const void* qp = q;
+        const void* dbp = db;
+        const size_t core = tc_sim3_workspace_bytes(n_q, n_db, k);
+        if (dtype == PVS_F32) {                                 // normalised fp32 rows -> fp16 hi + lo planes behind the core workspace
+            char* base = (char*)(((uintptr_t)workspace + core + 1023) & ~(uintptr_t)1023);
+            void* q2 = base;
+            void* db2 = base + align_up((size_t)n_q * d * 4, 1024);
+            if (int rc = launch_f32_to_split((const float*)q, n_q * d, q2, st)) return rc;
+            if (int rc = launch_f32_to_split((const float*)db, n_db * d, db2, st)) return rc;
+            qp = q2;
+            dbp = db2;
+        }
+        return PVS_STAGE(ST_TC_SIM3_TOPK, st, tc_sim3_topk(qp, dbp, n_q, n_db, d, k, db_index_offset, scores_out, idx_out,
+                                                          workspace, core, st));
+    }
+    PVS_CHECK(dtype != PVS_F16X2, PVS_ERR_UNSUPPORTED,
+              "pvs_cosine_topk: split (PVS_F16X2) operands need the tensor-core path: d %% 8 == 0, d >= 64, k <= %d",
+              PVS_TOPK_MAX - 8);
     PVS_CHECK(g_path.load() != PVS_PATH_TENSOR, PVS_ERR_UNSUPPORTED,
-              "pvs_cosine_topk: the tensor-core path handles d %% 8 == 0, d >= 64, k <= %d only", PVS_TOPK_MAX);
+              "pvs_cosine_topk: the tensor-core paths handle d %% 8 == 0, d >= 64, k <= %d only", PVS_TOPK_MAX - 8);
     const size_t need = pvs_cosine_topk_workspace_bytes(n_q, n_db, d, k, dtype);
     PVS_CHECK(workspace && workspace_bytes >= need, PVS_ERR_WORKSPACE, "pvs_cosine_topk: workspace %zu < %zu",
               workspace_bytes, need);
@@ -636,6 +686,19 @@ extern "C" int pvs_cosine_topk(const void* q, const void* db, int dtype, int64_t
                                                                         done + kk < k ? bound[pass & 1] : nullptr))) return rc;
         }
     }
+    return PVS_OK;
+}
+
+extern "C" int pvs_cosine_topk_exact_stats(const void* workspace, int64_t n_q, int64_t n_db, int k, int64_t* rescored,
+                                           int64_t* unresolved, void* stream)
+{
+    PVS_CHECK(workspace && n_q > 0 && n_db > 0 && k >= 1, PVS_ERR_BAD_ARG, "pvs_cosine_topk_exact_stats: bad arguments");
+    const char* base = (const char*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
+    unsigned long long h[2] = {0, 0};
+    PVS_CUDA(cudaMemcpyAsync(h, base + tc_sim3_stats_offset(n_q, n_db, k), sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    PVS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (rescored) *rescored = (int64_t)h[0];
+    if (unresolved) *unresolved = (int64_t)h[1];
     return PVS_OK;
 }
 
@@ -828,7 +891,8 @@ extern "C" int pvs_cosine_topk_host(const float* q, int64_t n_q, const float* db
     HostCtx& ctx = host_ctx();
     std::lock_guard<std::mutex> lock(ctx.mu);
     Slot& sl = ctx.slot[0];
-    const int dt = use_bf16 ? PVS_BF16 : PVS_F32;
+    // fp32 request: rows are normalised straight into the split operand planes when the tensor path will take them
+    const int dt = use_bf16 ? PVS_BF16 : (sim3_use_tc(PVS_F16X2, n_q, n_db, d, k) && sim3_use_tc(PVS_F32, n_q, n_db, d, k)) ? PVS_F16X2 : PVS_F32;
     const size_t esz = use_bf16 ? 2 : 4;
     const size_t bq = align_up((size_t)n_q * d * 4, 256), bdb = align_up((size_t)n_db * d * 4, 256);
     const size_t bqn = align_up((size_t)n_q * d * esz, 256), bdbn = align_up((size_t)n_db * d * esz, 256);

@@ -35,6 +35,7 @@ int launch_fv_finalize(const float* S, int ld, const float* s0part, int parts, c
 // ---- similarity / top-k --------------------------------------------------------------------
 int launch_l2_normalize(const float* x, int64_t n, int64_t d, void* out, int out_dtype, cudaStream_t st);
 int launch_bf16_to_f32(const void* x, int64_t n, float* out, cudaStream_t st);
+int launch_f32_to_split(const float* x, int64_t n, void* out, cudaStream_t st);
 // s[n, m] = cosine of raw rows, for small n * m (one CTA per pair, no workspace)
 int launch_cosine_small(const float* x, int64_t n, const float* y, int64_t m, int64_t d, float* s, cudaStream_t st);
 // per-row top-k of a dense score block S [rows, n_db] (row stride lds)
@@ -105,5 +106,15 @@ bool tc_sim_supported(int dtype, int64_t n_q, int64_t n_db, int64_t d, int k);
 size_t tc_sim_workspace_bytes(int64_t n_q, int64_t n_db, int k);
 int tc_sim_topk(const void* q, const void* db, int64_t n_q, int64_t n_db, int64_t d, int k, int64_t idx_offset,
                 float* scores_out, int64_t* idx_out, void* ws, size_t ws_bytes, cudaStream_t st);
+
+// fp32-accurate similarity on PVS_F16X2 operand planes (three kind::f16 passes, segmented accumulation):
+// fused top-(k + margin) shortlist + exact re-evaluation of the candidates closer than the error bound, and the
+// dense score matrix
+bool tc_sim3_supported(int64_t n_q, int64_t n_db, int64_t d, int k);
+size_t tc_sim3_workspace_bytes(int64_t n_q, int64_t n_db, int k);
+size_t tc_sim3_stats_offset(int64_t n_q, int64_t n_db, int k);
+int tc_sim3_topk(const void* q, const void* db, int64_t n_q, int64_t n_db, int64_t d, int k, int64_t idx_offset,
+                 float* scores_out, int64_t* idx_out, void* ws, size_t ws_bytes, cudaStream_t st);
+int tc_sim3_dense(const void* q, const void* db, int64_t n_q, int64_t n_db, int64_t d, float* s, int64_t ld, cudaStream_t st);
 
 }  // namespace pvs

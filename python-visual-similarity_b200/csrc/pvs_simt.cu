@@ -921,6 +921,27 @@ int launch_l2_normalize(const float* x, int64_t n, int64_t d, void* out, int out
     return PVS_OK;
 }
 
+// ALREADY normalised fp32 values -> the PVS_F16X2 operand planes (hi plane [n], lo plane [n] right behind it)
+namespace {
+__global__ void f32_to_split_kernel(const float* __restrict__ x, int64_t n, __half* __restrict__ hi, __half* __restrict__ lo)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float v = x[i] * 32768.f;
+        const __half h = __float2half_rn(v);
+        hi[i] = h;
+        lo[i] = __float2half_rn(v - __half2float(h));
+    }
+}
+}  // namespace
+
+int launch_f32_to_split(const float* x, int64_t n, void* out, cudaStream_t st)
+{
+    if (n <= 0) return PVS_OK;
+    PVS_LAUNCH(f32_to_split_kernel, 148 * 8, 256, 0, st, x, n, (__half*)out, (__half*)out + n);
+    return PVS_OK;
+}
+
 int launch_bf16_to_f32(const void* x, int64_t n, float* out, cudaStream_t st)
 {
     if (n <= 0) return PVS_OK;

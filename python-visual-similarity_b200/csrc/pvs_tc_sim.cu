@@ -32,7 +32,11 @@ namespace pvs {
 namespace tc2 {
 
 struct SimParams {
-    CUtensorMap q_map, db_map;
+    CUtensorMap q_map, db_map;     // bf16 rows, or the fp16 hi planes of the split format
+    CUtensorMap q_lo, db_lo;       // fp16 lo planes (PVS_F16X2 operands only)
+    int seg, nseg;                 // split kernel: k-blocks per accumulation segment, segments per tile
+    float* dense;                  // split kernel, dense mode: score matrix [n_q, ld_dense] instead of top-k lists
+    int64_t ld_dense;
     unsigned long long* bufs;      // [grid CTAs, 128 rows, cap] append buffers
     float* part_scores;            // [stripes, n_q, k]
     int64_t* part_idx;             // [stripes, n_q, k]
@@ -284,6 +288,300 @@ struct SimPolicy {
     }
 };
 
+
+// ------------------------------------------------------------------------------------------------
+// fp32-accurate variant: operands are PVS_F16X2 planes (v 2^15 = hi + lo, both fp16), every product
+// is hi*lo + lo*hi + hi*hi (three kind::f16 MMAs, 22 mantissa bits) and the accumulation is SEGMENTED.
+//
+// Why segments: tcgen05.mma adds each K = 16 slice to the TMEM accumulator with truncation, so over a
+// d = 32 768 contraction (6 144 accumulation steps) the sum drifts by up to ~4e-4 relative -- a bias that is
+// useless for "top-k indices exact".  Here a tile's contraction is cut into segments of `seg` k-blocks
+// (64 deep each); the tensor core accumulates one segment from zero, the eight epilogue warps (two per TMEM
+// lane quarter, 128 columns each) add the finished segment into fp32 registers with round-to-nearest while
+// the next segment is already being multiplied into the other TMEM buffer.  The drift is then bounded by
+// (3 * 4 * seg) * 2^-23 of the segment's own partial sums, about 6e-6 of sum|q_i d_i| <= 1 for seg = 4.
+// After the last segment the totals go back into the (now idle) accumulator columns with tcgen05.st and the
+// first warp of each lane quarter runs the same fused top-k scan as the bf16 kernel.  DENSE = true writes the
+// score matrix instead (pvs_cosine_matrix).
+// ------------------------------------------------------------------------------------------------
+struct SimSplitState : SimState {
+    float run[128];                        // running sums of this warp's 128 columns; all zero between tiles
+    __device__ SimSplitState()
+    {
+#pragma unroll
+        for (int j = 0; j < 128; ++j) run[j] = 0.f;
+    }
+};
+
+template <int CAP_, bool DENSE_>
+struct SimSplitPolicy : SimPolicy<CAP_> {
+    using Base = SimPolicy<CAP_>;
+    using Params = SimParams;
+    using EpiState = SimSplitState;
+    struct Tile { int nkb, kb0, qb, dbb, stripe; bool first, last, first_seg, last_seg; };
+    static constexpr bool BF16 = false, F16 = true, MANUAL = false, B_RESIDENT = false, ACC_INIT = false, TILE_SYNC = true, DENSE = DENSE_;
+    static constexpr int CAP = CAP_, PASSES = 3, BLOCK_N = 256, KSTEPS = 4, NKB_RES = 0, PGROUPS = 1, EPI_WARPS = 8;
+    static constexpr int A_BYTES = 128 * 128, B_BYTES = 128 * 128, TMA_BYTES = 2 * (A_BYTES + B_BYTES);
+    static constexpr int SCRATCH_BYTES = (DENSE || CAP <= 512) ? 0 : 4 * CAP * 8;
+    static constexpr int STAGES = (226 * 1024 - 1024 - 256 - SCRATCH_BYTES) / TMA_BYTES;
+    static_assert(STAGES >= 2, "the split kernel needs at least two operand stages");
+    __device__ static void prefetch(const Params& p)
+    {
+        tma_prefetch_desc(&p.q_map); tma_prefetch_desc(&p.db_map); tma_prefetch_desc(&p.q_lo); tma_prefetch_desc(&p.db_lo);
+    }
+    __device__ static int num_tiles(const Params& p) { return p.n_units * p.tiles_per_unit * p.nseg; }
+    // units are dealt round-robin to pairs; the tiles of a unit and the segments of a tile are consecutive
+    __device__ static int tile_at(const Params& p, int it, int pair, int n_pairs, int)
+    {
+        const int per_unit = p.tiles_per_unit * p.nseg;
+        const int j = it / per_unit, w = it - j * per_unit;
+        const long long u = (long long)pair + (long long)j * n_pairs;
+        return u < p.n_units ? (int)(u * per_unit + w) : -1;
+    }
+    __device__ static Tile tile(const Params& p, int i)
+    {
+        const int per_unit = p.tiles_per_unit * p.nseg;
+        const int u = i / per_unit, w2 = i - u * per_unit;
+        const int w = w2 / p.nseg, sg = w2 - w * p.nseg;
+        const int qb = u / p.stripes, s = u - qb * p.stripes;
+        const int dbb = s * p.tiles_per_unit + w;
+        Tile t;
+        t.qb = qb; t.dbb = dbb; t.stripe = s;
+        t.kb0 = sg * p.seg;
+        const int left = p.nkb - t.kb0;
+        t.nkb = dbb < p.db_blocks ? (left < p.seg ? left : p.seg) : 0;     // stripes may overhang the last block
+        t.first_seg = sg == 0;
+        t.last_seg = sg == p.nseg - 1;
+        t.first = w == 0 && t.first_seg;
+        t.last = w == p.tiles_per_unit - 1 && t.last_seg;
+        return t;
+    }
+    __device__ static void load(const Params& p, const Tile& t, int kb, int rank, uint8_t* a_hi, uint8_t* a_lo, uint8_t* b_hi,
+                                uint8_t* b_lo, uint64_t* bar)
+    {
+        const int c = (t.kb0 + kb) * 64, rq = t.qb * 256 + rank * 128, rd = t.dbb * 256 + rank * 128;
+        tma_load_2d_pair(a_hi, &p.q_map, bar, c, rq);
+        tma_load_2d_pair(a_lo, &p.q_lo, bar, c, rq);
+        tma_load_2d_pair(b_hi, &p.db_map, bar, c, rd);
+        tma_load_2d_pair(b_lo, &p.db_lo, bar, c, rd);
+    }
+    // the drift limiter works on database tiles, not on their segments
+    __device__ static void tile_sync(const Params& p, int it, int rank, int n_pairs)
+    {
+        if (it % p.nseg == 0) Base::tile_sync(p, it / p.nseg, rank, n_pairs);
+    }
+    __device__ static void tile_sync_done(const Params& p, int tiles_done, int rank) { Base::tile_sync_done(p, tiles_done / p.nseg, rank); }
+    __device__ static void epi_begin(const Params&, const Tile& t, EpiState& st, int, int, int)
+    {
+        if (t.first) { st.tau = 0ull; st.tau_s = -INFINITY; st.cnt = 0; }
+    }
+    __device__ static void quarter_barrier(int quarter) { asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory"); }
+
+    __device__ __forceinline__ static void epilogue(const Params& p, const Tile& t, int rank, uint32_t tmem, int quarter, int lane,
+                                                    uint8_t* scratch, EpiState& st)
+    {
+        const int half = (((int)threadIdx.x >> 5) - 2) >> 2;       // which 128 of the 256 columns this warp folds
+        const int c0 = half * 128;
+        const int r_in = quarter * 32 + lane;
+        const int64_t row = (int64_t)t.qb * 256 + rank * 128 + r_in;
+        const bool valid = row < p.n_q;
+        constexpr float UNSCALE = 1.f / 1073741824.f;              // operands carry 2^15 each
+        if (t.nkb > 0) {
+            // 8 columns at a time: 128 running sums + one chunk must fit the 168 registers a 320-thread CTA gets
+            if (!t.last_seg) {
+#pragma unroll
+                for (int c = 0; c < 128; c += 8) {
+                    float v[8];
+                    tmem_ld8(tmem + c0 + c, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) st.run[c + j] += v[j];
+                }
+                return;
+            }
+            // last segment: totals
+            if constexpr (DENSE) {
+                float* orow = p.dense + row * p.ld_dense + (int64_t)t.dbb * BLOCK_N + c0;
+                const bool vec = (p.ld_dense & 3) == 0 && ((uintptr_t)p.dense & 15) == 0;
+#pragma unroll
+                for (int c = 0; c < 128; c += 8) {
+                    float v[8];
+                    tmem_ld8(tmem + c0 + c, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { v[j] = (st.run[c + j] + v[j]) * UNSCALE; st.run[c + j] = 0.f; }
+                    const int64_t col0 = (int64_t)t.dbb * BLOCK_N + c0 + c;
+                    if (!valid || col0 >= p.n_db) continue;
+                    if (vec && col0 + 8 <= p.n_db) {
+#pragma unroll
+                        for (int j = 0; j < 8; j += 4) *reinterpret_cast<float4*>(orow + c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (col0 + j < p.n_db) orow[c + j] = v[j];
+                    }
+                }
+                return;
+            } else {
+#pragma unroll
+                for (int c = 0; c < 128; c += 8) {
+                    float v[8];
+                    tmem_ld8(tmem + c0 + c, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    // the sums are zero again from here on: nothing is live across the (out-of-line) scan below, and the
+                    // first segment of the next tile needs no special case
+                    for (int j = 0; j < 8; ++j) { v[j] = (st.run[c + j] + v[j]) * UNSCALE; st.run[c + j] = 0.f; }
+                    tmem_st8(tmem + c0 + c, v);
+                }
+                tmem_st_wait();
+                tcgen05_fence_before();
+                quarter_barrier(quarter);                          // both column halves of these 32 rows are back in TMEM
+                tcgen05_fence_after();
+            }
+        }
+        if constexpr (!DENSE) {
+            if (half != 0) return;                                 // the scan + top-k state belong to the first warp of the quarter
+            // Out of line and on a COPY of the three top-k words: inlined, the scan's registers are added to the 128
+            // running sums of the fold loop (spills in the per-segment path); by reference, the whole state object --
+            // sums included -- is forced into local memory.
+            SimState ts = static_cast<const SimState&>(st);
+            scan_tile(p, t.nkb, t.qb, t.dbb, t.stripe, t.last, rank, tmem, quarter, lane, scratch, ts);
+            static_cast<SimState&>(st) = ts;
+        }
+    }
+
+    // fused top-k over the 256 totals of this warp's 32 rows (now back in TMEM), as in SimPolicy::epilogue
+    __device__ __noinline__ static void scan_tile(const Params& p, int nkb, int qb, int dbb, int stripe, bool last, int rank,
+                                                  uint32_t tmem, int quarter, int lane, uint8_t* scratch, SimState& ts)
+    {
+        const int64_t row = (int64_t)qb * 256 + rank * 128 + quarter * 32 + lane;
+        const bool valid = row < p.n_q;
+        unsigned long long* warp_bufs = p.bufs + ((size_t)blockIdx.x * 128 + quarter * 32) * CAP;
+        unsigned long long* buf = warp_bufs + (size_t)lane * CAP;
+        unsigned long long* sm = reinterpret_cast<unsigned long long*>(scratch) + quarter * CAP;
+        if (nkb > 0) {
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N; c += 32) {
+                __syncwarp();
+                unsigned need = __ballot_sync(0xffffffffu, valid && ts.cnt > CAP - 32);
+                while (need) {
+                    const int owner = __ffs(need) - 1;
+                    need &= need - 1;
+                    Base::prune_row(p, warp_bufs, sm, owner, lane, ts, false, nullptr, nullptr);
+                }
+                float v[32];
+                tmem_ld32(tmem + c, v);
+                tmem_ld_wait();
+                const int64_t col0 = (int64_t)dbb * BLOCK_N + c;
+                if (valid && col0 < p.n_db) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float sc = v[j];
+                        if (sc >= ts.tau_s && col0 + j < p.n_db) {
+                            const unsigned long long key = sim_key(sc, (unsigned)(col0 + j));
+                            if (key > ts.tau) buf[ts.cnt++] = key;
+                        }
+                    }
+                }
+            }
+        }
+        if (last) {
+            __syncwarp();
+            for (int owner = 0; owner < 32; ++owner) {
+                const int64_t orow = (int64_t)qb * 256 + rank * 128 + quarter * 32 + owner;
+                if (orow >= p.n_q) break;
+                float* ps = p.part_scores + ((size_t)stripe * p.n_q + orow) * p.k;
+                int64_t* pi = p.part_idx + ((size_t)stripe * p.n_q + orow) * p.k;
+                Base::prune_row(p, warp_bufs, sm, owner, lane, ts, true, ps, pi);
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Exact re-evaluation of the candidates the tensor scores cannot order.  Input: per query the shortlist of
+// k' = k + margin candidates sorted by tensor score (error <= band).  Two neighbours closer than 2 * band may
+// be in the wrong order, and the k-th / (k+1)-th decide membership; every maximal run of such neighbours that
+// touches the first k positions is re-scored EXACTLY -- sum over d of (hi + lo)(hi + lo) in fp64 from the same
+// operand planes -- and re-ranked (score descending, lowest index first).  One warp per query row; runs are
+// short (a few candidates per query at d = 32 768), so this pass costs a few hundred KB of reads per query.
+// stats[0] += re-scored candidates, stats[1] += rows whose run reached the end of the shortlist (a candidate
+// beyond it could belong to the top-k: the margin was too small; never seen with margin 8 outside degenerate
+// inputs such as many identical rows).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sim_rescue_kernel(const float* __restrict__ s_in, const int64_t* __restrict__ i_in, int kp, int k, int64_t n_q,
+                  const __half* __restrict__ q_hi, const __half* __restrict__ q_lo, const __half* __restrict__ db_hi,
+                  const __half* __restrict__ db_lo, int64_t d, int64_t idx_offset, float band,
+                  float* __restrict__ s_out, int64_t* __restrict__ i_out, unsigned long long* __restrict__ stats)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (q >= n_q) return;
+    const float* s = s_in + q * kp;
+    const int64_t* ix = i_in + q * kp;
+    for (int j = lane; j < k; j += 32) {
+        s_out[q * k + j] = j < kp ? s[j] : -INFINITY;
+        i_out[q * k + j] = j < kp ? ix[j] : -1;
+    }
+    __syncwarp();
+    const float gap = 2.f * band;
+    int i = 0;
+    while (i < k && i < kp) {
+        int j = i;
+        while (j + 1 < kp && ix[j + 1] >= 0 && s[j] - s[j + 1] <= gap) ++j;     // warp-uniform scan (same loads in every lane)
+        if (j == i) { ++i; continue; }
+        const int n = j - i + 1;
+        if (n > 32) {                                              // e.g. many identical rows: bit-equal tensor scores are already in index order
+            if (lane == 0) atomicAdd(&stats[1], 1ull);
+            i = j + 1;
+            continue;
+        }
+        if (j == kp - 1 && kp > k && lane == 0) atomicAdd(&stats[1], 1ull);
+        double mine = 0.0;
+        int64_t my_idx = -1;
+        for (int m = 0; m < n; ++m) {
+            const int64_t id = ix[i + m];
+            const __half* dh = db_hi + (id - idx_offset) * d;
+            const __half* dl = db_lo + (id - idx_offset) * d;
+            const __half* qh = q_hi + q * d;
+            const __half* ql = q_lo + q * d;
+            double acc = 0.0;
+            for (int64_t e = (int64_t)lane * 8; e < d; e += 256) {
+                const uint4 a = *reinterpret_cast<const uint4*>(qh + e), b = *reinterpret_cast<const uint4*>(ql + e);
+                const uint4 c = *reinterpret_cast<const uint4*>(dh + e), f = *reinterpret_cast<const uint4*>(dl + e);
+                const __half2* a2 = reinterpret_cast<const __half2*>(&a);
+                const __half2* b2 = reinterpret_cast<const __half2*>(&b);
+                const __half2* c2 = reinterpret_cast<const __half2*>(&c);
+                const __half2* f2 = reinterpret_cast<const __half2*>(&f);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float2 qa = __half22float2(a2[u]), qb = __half22float2(b2[u]);
+                    const float2 da = __half22float2(c2[u]), db = __half22float2(f2[u]);
+                    acc = fma((double)(qa.x + qb.x), (double)(da.x + db.x), acc);      // hi + lo is exact in fp32
+                    acc = fma((double)(qa.y + qb.y), (double)(da.y + db.y), acc);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == m) { mine = acc; my_idx = id; }
+        }
+        // rank inside the run: score descending, lowest index first
+        int rank = 0;
+        for (int m = 0; m < n; ++m) {
+            const double os = __shfl_sync(0xffffffffu, mine, m);
+            const long long oi = __shfl_sync(0xffffffffu, (long long)my_idx, m);
+            if (lane < n && (os > mine || (os == mine && oi < (long long)my_idx))) ++rank;
+        }
+        if (lane < n && i + rank < k) {
+            s_out[q * k + i + rank] = (float)(mine * (1.0 / 1073741824.0));
+            i_out[q * k + i + rank] = my_idx;
+        }
+        if (lane == 0) atomicAdd(&stats[0], (unsigned long long)n);
+        i = j + 1;
+    }
+}
 }  // namespace tc2
 
 using namespace tc2;
@@ -367,6 +665,133 @@ int tc_sim_topk(const void* q, const void* db, int64_t n_q, int64_t n_db, int64_
     }
     if (rc) return rc;
     return launch_topk_merge(p.part_scores, p.part_idx, pl.stripes, n_q, k, scores_out, idx_out, st);
+}
+
+}  // namespace pvs
+
+// =====================================================================================
+// fp32-accurate similarity on split operands (SimSplitPolicy): fused top-k with exact tie
+// resolution, and the dense score matrix
+// =====================================================================================
+namespace pvs {
+using namespace tc2;
+
+constexpr int SIM3_MARGIN = 8;                                 // shortlist = k + margin candidates per query
+
+static int sim3_seg()
+{
+    int g = 4;
+    if (const char* e = getenv("PVS_SIM_SEG")) { const int v = atoi(e); if (v > 0) g = v; }
+    return g;
+}
+
+// absolute bound on |tensor score - exact score| for unit-norm rows: truncating accumulation inside a segment
+// (3 MMAs x 4 k-steps x seg k-blocks, two ulps each to be safe, of partial sums that add up to <= 1), the
+// round-to-nearest folds of the segments, and the hi + lo split of the operands
+static float sim3_band(int64_t d, int seg)
+{
+    const int nkb = (int)ceil_div(d, 64), nseg = (int)ceil_div(nkb, seg);
+    return 2.f * (12.f * seg) * 1.1920929e-7f + (float)nseg * 5.9604645e-8f + 4.7683716e-7f;
+}
+
+bool tc_sim3_supported(int64_t n_q, int64_t n_db, int64_t d, int k)
+{
+    if (!(tc_available() && d % 8 == 0 && d >= 64 && k >= 1 && k + SIM3_MARGIN <= PVS_TOPK_MAX && n_q > 0 && n_db > 0 &&
+          n_q < 2147483000LL && n_db < 2147483000LL && d < 2147483000LL)) return false;
+    const int64_t nseg = ceil_div(ceil_div(d, 64), sim3_seg());
+    return ceil_div(n_q, 256) * (ceil_div(n_db, 256) + 128) * nseg < 2000000000LL;
+}
+
+struct Sim3Ws { SimPlan pl; int kp; size_t ms, mi, stats, total; };
+static Sim3Ws sim3_ws(int64_t n_q, int64_t n_db, int k)
+{
+    Sim3Ws w{};
+    w.kp = k + SIM3_MARGIN;
+    w.pl = sim_plan(n_q, n_db, w.kp);
+    size_t off = w.pl.total;
+    w.ms = off;    off += align_up((size_t)n_q * w.kp * 4, 1024);
+    w.mi = off;    off += align_up((size_t)n_q * w.kp * 8, 1024);
+    w.stats = off; off += 1024;
+    w.total = off + 1024;
+    return w;
+}
+size_t tc_sim3_workspace_bytes(int64_t n_q, int64_t n_db, int k) { return sim3_ws(n_q, n_db, k).total; }
+
+static int sim3_fill(SimParams& p, const void* q, const void* db, int64_t n_q, int64_t n_db, int64_t d)
+{
+    PVS_CHECK((((uintptr_t)q | (uintptr_t)db) & 15) == 0, PVS_ERR_BAD_ARG, "split operands must be 16-byte aligned");
+    const __half* qh = (const __half*)q;
+    const __half* dh = (const __half*)db;
+    int rc;
+    if ((rc = make_tmap_2d(&p.q_map, qh, true, n_q, d, d, 64, 128))) return rc;
+    if ((rc = make_tmap_2d(&p.q_lo, qh + n_q * d, true, n_q, d, d, 64, 128))) return rc;
+    if ((rc = make_tmap_2d(&p.db_map, dh, true, n_db, d, d, 64, 128))) return rc;
+    if ((rc = make_tmap_2d(&p.db_lo, dh + n_db * d, true, n_db, d, d, 64, 128))) return rc;
+    p.n_q = n_q; p.n_db = n_db;
+    p.nkb = (int)ceil_div(d, 64);
+    p.seg = sim3_seg();
+    p.nseg = (int)ceil_div(p.nkb, p.seg);
+    return PVS_OK;
+}
+
+// q / db: PVS_F16X2 planes ([2, n, d] fp16).  ws[stats] (two uint64 at the START of the aligned workspace's stats
+// slot, returned through stats_out_dev when given): re-scored candidates, rows with an unresolved run.
+int tc_sim3_topk(const void* q, const void* db, int64_t n_q, int64_t n_db, int64_t d, int k, int64_t idx_offset,
+                 float* scores_out, int64_t* idx_out, void* ws, size_t ws_bytes, cudaStream_t st)
+{
+    const Sim3Ws w = sim3_ws(n_q, n_db, k);
+    const SimPlan& pl = w.pl;
+    PVS_CHECK(ws && ws_bytes >= w.total, PVS_ERR_WORKSPACE, "similarity workspace %zu < %zu", ws_bytes, w.total);
+    char* base = (char*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
+    SimParams p{};
+    if (int rc = sim3_fill(p, q, db, n_q, n_db, d)) return rc;
+    p.bufs = (unsigned long long*)(base + pl.bufs);
+    p.part_scores = (float*)(base + pl.ps);
+    p.part_idx = (int64_t*)(base + pl.pi);
+    p.idx_offset = idx_offset; p.k = w.kp; p.cap = pl.cap;
+    p.q_blocks = pl.q_blocks; p.db_blocks = pl.db_blocks; p.stripes = pl.stripes;
+    p.tiles_per_unit = pl.tiles_per_unit; p.n_units = pl.n_units;
+    const int n_tiles = pl.n_units * pl.tiles_per_unit * p.nseg;
+    p.sync_ctr = getenv("PVS_SIM_NOSYNC") ? nullptr : (unsigned*)(base + pl.ctr);
+    p.sync_steps = (int)ceil_div(pl.n_units, pl.pairs) * pl.tiles_per_unit;
+    PVS_CUDA(cudaMemsetAsync(base + pl.ctr, 0, 1024, st));
+    PVS_CUDA(cudaMemsetAsync(base + w.stats, 0, 1024, st));
+    int rc;
+    switch (pl.cap) {
+        case 512: rc = launch_tc2<SimSplitPolicy<512, false>>(p, n_tiles, st, pl.pairs); break;
+        case 1024: rc = launch_tc2<SimSplitPolicy<1024, false>>(p, n_tiles, st, pl.pairs); break;
+        default: rc = launch_tc2<SimSplitPolicy<2048, false>>(p, n_tiles, st, pl.pairs); break;
+    }
+    if (rc) return rc;
+    float* ms = (float*)(base + w.ms);
+    int64_t* mi = (int64_t*)(base + w.mi);
+    if ((rc = launch_topk_merge(p.part_scores, p.part_idx, pl.stripes, n_q, w.kp, ms, mi, st))) return rc;
+    const __half* qh = (const __half*)q;
+    const __half* dh = (const __half*)db;
+    PVS_LAUNCH(sim_rescue_kernel, (unsigned)ceil_div(n_q, 8), 256, 0, st, ms, mi, w.kp, k, n_q, qh, qh + n_q * d, dh, dh + n_db * d, d,
+               idx_offset, sim3_band(d, p.seg), scores_out, idx_out, (unsigned long long*)(base + w.stats));
+    return PVS_OK;
+}
+
+// offset of the two uint64 counters inside a workspace of tc_sim3_workspace_bytes() (after 1024-byte alignment)
+size_t tc_sim3_stats_offset(int64_t n_q, int64_t n_db, int k) { return sim3_ws(n_q, n_db, k).stats; }
+
+// dense score matrix s[n_q, ld] = Q . DB^T from split planes
+int tc_sim3_dense(const void* q, const void* db, int64_t n_q, int64_t n_db, int64_t d, float* s, int64_t ld, cudaStream_t st)
+{
+    SimParams p{};
+    if (int rc = sim3_fill(p, q, db, n_q, n_db, d)) return rc;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    p.dense = s; p.ld_dense = ld; p.k = 1; p.cap = 512;
+    p.q_blocks = (int)ceil_div(n_q, 256); p.db_blocks = (int)ceil_div(n_db, 256);
+    p.stripes = p.db_blocks; p.tiles_per_unit = 1;             // one database block per unit: every (query block, block) pair is a tile
+    p.n_units = p.q_blocks * p.stripes;
+    PVS_CHECK((int64_t)p.q_blocks * p.stripes * p.nseg < 2000000000LL, PVS_ERR_BAD_SHAPE, "score matrix too large for one launch");
+    p.sync_ctr = nullptr;
+    const int pairs = p.n_units < sms / 2 ? p.n_units : sms / 2;
+    return launch_tc2<SimSplitPolicy<512, true>>(p, p.n_units * p.nseg, st, pairs);
 }
 
 }  // namespace pvs

@@ -15,9 +15,9 @@ import numpy as np
 from . import _build
 
 __all__ = ["lib", "check", "PvsError", "NativeLibraryError", "Model", "EXPORTS",
-           "F32", "BF16", "PATH_AUTO", "PATH_SIMT", "PATH_TENSOR"]
+           "F32", "BF16", "F16X2", "PATH_AUTO", "PATH_SIMT", "PATH_TENSOR"]
 
-F32, BF16 = 0, 1
+F32, BF16, F16X2 = 0, 1, 2
 PATH_AUTO, PATH_SIMT, PATH_TENSOR = 0, 1, 2
 KIND_KMEANS, KIND_GMM, KIND_PCA = 1, 2, 3
 
@@ -67,6 +67,7 @@ EXPORTS = {
     "pvs_cosine_matrix": (_i32, [_vp, _i64, _vp, _i64, _i64, _vp, _vp, _sz, _vp]),
     "pvs_cosine_topk_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32, _i32]),
     "pvs_cosine_topk": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _i32, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "pvs_cosine_topk_exact_stats": (_i32, [_vp, _i64, _i64, _i32, C.POINTER(_i64), C.POINTER(_i64), _vp]),
     "pvs_topk_merge": (_i32, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp]),
     "pvs_topk_label_metrics": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "pvs_rows_sub": (_i32, [_vp, _i64, _i32, _vp, _vp]),

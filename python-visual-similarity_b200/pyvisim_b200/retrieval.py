@@ -83,41 +83,86 @@ def shard_bounds(n: int, world: int, rank: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def split_supported(d: int) -> bool:
+    """Shapes the fp32-accurate tensor-core similarity takes (fp16 hi + lo operand planes)."""
+    return d % 8 == 0 and d >= 64
+
+
 def l2_normalize(x, dtype: str = "fp32"):
-    """Row-normalise a CUDA fp32 tensor -> fp32 or bf16 CUDA tensor (zero rows stay zero)."""
+    """Row-normalise a CUDA fp32 tensor (zero rows stay zero).
+
+    ``"fp32"`` -> fp32 ``[n, d]``; ``"bf16"`` -> bf16 ``[n, d]`` (one-pass tensor-core similarity, scores within
+    1e-2); ``"split"`` -> fp16 ``[2, n, d]``: the planes ``hi``, ``lo`` with ``v * 2**15 = hi + lo`` -- the operand
+    format of the fp32-accurate tensor-core similarity (``PVS_F16X2``)."""
     import torch
     x = x.contiguous().float()
-    out = torch.empty_like(x, dtype=torch.bfloat16 if dtype == "bf16" else torch.float32)
+    if dtype == "split":
+        out = torch.empty((2,) + tuple(x.shape), dtype=torch.float16, device=x.device)
+        code = N.F16X2
+    else:
+        out = torch.empty_like(x, dtype=torch.bfloat16 if dtype == "bf16" else torch.float32)
+        code = N.BF16 if dtype == "bf16" else N.F32
     with torch.cuda.device(x.device):
-        N.check(N.lib().pvs_l2_normalize_rows(x.data_ptr(), x.shape[0], x.shape[1], out.data_ptr(),
-                                              N.BF16 if dtype == "bf16" else N.F32,
+        N.check(N.lib().pvs_l2_normalize_rows(x.data_ptr(), x.shape[0], x.shape[1], out.data_ptr(), code,
                                               torch.cuda.current_stream(x.device).cuda_stream))
     return out
 
 
-def cosine_topk(queries_n, database_n, k: int, index_offset: int = 0):
-    """Top-k database rows per query row.  Inputs are ALREADY row-normalised CUDA tensors of
-    the same dtype (fp32 or bf16).  Returns (scores fp32 [nq,k], indices int64 [nq,k]),
-    scores descending, lowest index first on exact ties."""
+def _is_split(t) -> bool:
     import torch
-    if queries_n.dtype != database_n.dtype or queries_n.dtype not in (torch.float32, torch.bfloat16):
-        raise ValueError("queries and database must both be float32 or both bfloat16")
-    if queries_n.shape[1] != database_n.shape[1]:
+    return t.dtype == torch.float16 and t.ndim == 3 and t.shape[0] == 2
+
+
+def take_rows(xn, lo: int, hi: int):
+    """Rows ``lo:hi`` of a normalised matrix in any of the three formats (contiguous)."""
+    return xn[:, lo:hi].contiguous() if _is_split(xn) else xn[lo:hi]
+
+
+def cosine_topk(queries_n, database_n, k: int, index_offset: int = 0, return_stats: bool = False):
+    """Top-k database rows per query row.  Inputs are ALREADY row-normalised CUDA tensors in the same format
+    (fp32, bf16 or split planes, see :func:`l2_normalize`).  Returns (scores fp32 [nq,k], indices int64 [nq,k]),
+    scores descending, lowest index first on exact ties.  With fp32 / split operands on a tcgen05 device the
+    indices are those of the exact (fp64) ranking of the operands; ``return_stats`` adds
+    ``{"rescored": ..., "unresolved": ...}`` of the exact tie resolution."""
+    import ctypes as C
+    import torch
+    split = _is_split(queries_n)
+    if split != _is_split(database_n) or queries_n.dtype != database_n.dtype or \
+            (not split and queries_n.dtype not in (torch.float32, torch.bfloat16)):
+        raise ValueError("queries and database must both be float32, both bfloat16 or both split planes")
+    if queries_n.shape[-1] != database_n.shape[-1]:
         raise ValueError("feature dimensions differ")
     q, db = queries_n.contiguous(), database_n.contiguous()
-    nq, d = q.shape
-    ndb = db.shape[0]
-    dt = N.BF16 if q.dtype == torch.bfloat16 else N.F32
+    nq, d = q.shape[-2:]
+    ndb = db.shape[-2]
+    dt = N.F16X2 if split else (N.BF16 if q.dtype == torch.bfloat16 else N.F32)
     scores = torch.empty((nq, k), dtype=torch.float32, device=q.device)
     idx = torch.empty((nq, k), dtype=torch.int64, device=q.device)
     lib = N.lib()
     need = lib.pvs_cosine_topk_workspace_bytes(nq, ndb, d, k, dt)
     ws = torch.empty((max(int(need), 1),), dtype=torch.uint8, device=q.device)
     with torch.cuda.device(q.device):
+        st = torch.cuda.current_stream(q.device).cuda_stream
         N.check(lib.pvs_cosine_topk(q.data_ptr(), db.data_ptr(), dt, nq, ndb, d, k, int(index_offset),
-                                    scores.data_ptr(), idx.data_ptr(), ws.data_ptr(), ws.numel(),
-                                    torch.cuda.current_stream(q.device).cuda_stream))
+                                    scores.data_ptr(), idx.data_ptr(), ws.data_ptr(), ws.numel(), st))
+        if return_stats:
+            a, b = C.c_int64(0), C.c_int64(0)
+            if dt != N.BF16 and nq > 0:
+                N.check(lib.pvs_cosine_topk_exact_stats(ws.data_ptr(), nq, ndb, k, C.byref(a), C.byref(b), st))
+            return scores, idx, {"rescored": a.value, "unresolved": b.value}
     return scores, idx
+
+
+def _format(dtype: str, d: int) -> str:
+    """Operand format for a requested precision: "fp32" means fp32-ACCURATE scores and exact indices -- split
+    planes on the tensor cores when the shape allows, fp32 rows (CUDA cores) otherwise."""
+    if dtype in ("fp32", "split"):
+        return "split" if split_supported(d) else "fp32"
+    if dtype == "fp32_rows":
+        return "fp32"
+    if dtype != "bf16":
+        raise ValueError(f"dtype must be 'bf16', 'fp32' or 'fp32_rows', got {dtype!r}")
+    return "bf16"
 
 
 def merge_topk(scores, idx, k: int):
@@ -173,7 +218,8 @@ def all_pairs_topk(vectors, k: int, *, dtype: str = "bf16", rank: int = 0, world
                    exclude_self: bool = False):
     """All-pairs cosine similarity + top-k over a set of image vectors.
 
-    ``vectors``: CUDA fp32 tensor.  With ``database_is_sharded=False`` every rank holds the
+    ``vectors``: CUDA fp32 tensor.  ``dtype``: "bf16" (fastest, scores within 1e-2, indices near-optimal) or
+    "fp32" (fp32-accurate tensor-core scores, indices of the exact ranking; about a third of the bf16 rate).  With ``database_is_sharded=False`` every rank holds the
     full ``(N, D)`` set (replicated database) and scores only its own query rows.  With
     ``database_is_sharded=True`` every rank holds only its ``shard_bounds`` rows; the
     normalised shards are all-gathered once (bf16 halves that traffic) and the rank's own
@@ -182,27 +228,35 @@ def all_pairs_topk(vectors, k: int, *, dtype: str = "bf16", rank: int = 0, world
     """
     import torch
     import torch.distributed as dist
-    xn = l2_normalize(vectors, dtype)
+    fmt = _format(dtype, vectors.shape[1])
+    xn = l2_normalize(vectors, fmt)
+    split = fmt == "split"
+    rows = xn.shape[-2]
     if world > 1 and database_is_sharded:
-        counts = gather_shard_counts(xn.shape[0], world, group)
+        counts = gather_shard_counts(rows, world, group)
         n_total = sum(counts)
         pad = max(counts)
-        mine = xn if xn.shape[0] == pad else torch.cat([xn, xn.new_zeros((pad - xn.shape[0], xn.shape[1]))])
-        full = torch.empty((world * pad, xn.shape[1]), dtype=xn.dtype, device=xn.device)
+        mine = xn
+        if rows != pad:
+            z = xn.new_zeros(xn.shape[:-2] + (pad - rows, xn.shape[-1]))
+            mine = torch.cat([xn, z], dim=-2)
+        full = torch.empty((world,) + tuple(mine.shape), dtype=xn.dtype, device=xn.device)
         dist.all_gather_into_tensor(full, mine.contiguous(), group=group)
+        # [world, (2,) pad, d] -> [(2,) world * pad, d]
+        full = full.permute(1, 0, 2, 3).reshape(2, world * pad, -1) if split else full.reshape(world * pad, -1)
         if any(c != pad for c in counts):
             keep = torch.cat([torch.arange(r * pad, r * pad + c) for r, c in enumerate(counts)]).to(xn.device)
-            full = full[keep]
-        db, q = full, xn
+            full = full[:, keep] if split else full[keep]
+        db, q = full.contiguous(), xn
         lo = sum(counts[:rank])
     else:
-        n_total = xn.shape[0]
+        n_total = rows
         lo, hi = shard_bounds(n_total, world, rank)
-        db, q = xn, xn[lo:hi]
+        db, q = xn, take_rows(xn, lo, hi)
     kk = k + 1 if exclude_self else k
     scores, idx = cosine_topk(q, db, kk)
     if exclude_self:
-        own = torch.arange(lo, lo + q.shape[0], device=idx.device).unsqueeze(1)
+        own = torch.arange(lo, lo + q.shape[-2], device=idx.device).unsqueeze(1)
         keep = idx != own
         # drop the self column where present, else the last column
         order = torch.argsort((~keep).to(torch.int8), dim=1, stable=True)[:, :k]
@@ -226,16 +280,17 @@ def all_pairs_topk_ring(vectors, k: int, *, dtype: str = "bf16", rank: int = 0, 
     Returns the rank's ``(scores, indices)`` or, with ``gather=True``, all rows on every rank."""
     import torch
     import torch.distributed as dist
-    xn = vectors if normalized else l2_normalize(vectors, dtype)
+    xn = vectors if normalized else l2_normalize(vectors, _format(dtype, vectors.shape[1]))
     if world == 1:
         return cosine_topk(xn, xn, k)
-    counts = gather_shard_counts(xn.shape[0], world, group)
+    rows = xn.shape[-2]
+    counts = gather_shard_counts(rows, world, group)
     starts = np.concatenate([[0], np.cumsum(counts)])
     if min(counts) < k:
         raise ValueError(f"every shard needs at least k = {k} rows (smallest shard: {min(counts)})")
     pad = max(counts)
-    cur = xn.new_zeros((pad, xn.shape[1]))
-    cur[:xn.shape[0]] = xn
+    cur = xn.new_zeros(xn.shape[:-2] + (pad, xn.shape[-1]))
+    cur[..., :rows, :] = xn
     nxt = torch.empty_like(cur)
     best_s = best_i = None
     left, right = (rank - 1) % world, (rank + 1) % world
@@ -245,7 +300,7 @@ def all_pairs_topk_ring(vectors, k: int, *, dtype: str = "bf16", rank: int = 0, 
         if step + 1 < world:                             # pass it on while it is being scored
             reqs = dist.batch_isend_irecv([dist.P2POp(dist.isend, cur, left, group),
                                            dist.P2POp(dist.irecv, nxt, right, group)])
-        s, i = cosine_topk(xn, cur[:counts[src]], k, index_offset=int(starts[src]))
+        s, i = cosine_topk(xn, take_rows(cur, 0, counts[src]) if counts[src] != pad else cur, k, index_offset=int(starts[src]))
         if best_s is None:
             best_s, best_i = s, i
         else:
