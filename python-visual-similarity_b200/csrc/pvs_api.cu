@@ -477,19 +477,25 @@ extern "C" int pvs_fv_encode(const pvs_model* g, const pvs_model* pca, const flo
         if (int rc = tc_fv_begin(pl, n_images, st)) return rc;
         if (pca)
             if (int rc = PVS_STAGE(ST_TC_FV_PROJECT, st, tc_fv_project(pl, g, pca, desc, total_rows, st))) return rc;
+        float raw1 = 0.f, raw2 = 0.f;
         if (pl.fp16x2 && !argmax_out && tc_fv_fused_enabled()) {
             // posterior + statistics in one kernel (the posteriors never leave the SM); behind it the two
             // 3xTF32 kernels that only run when the projection raised the range flag
-            if (int rc = PVS_STAGE(ST_TC_FV_FUSED, st, tc_fv_fused_mode() == 2 ? tc_fv_poststats_fused_cluster(pl, g, y, offsets, n_images, st)
-                                                                               : tc_fv_poststats_fused(pl, g, y, offsets, n_images, st))) return rc;
+            const int mode = tc_fv_fused_mode();
+            if (mode == 2) { raw1 = ldexpf(1.f, g->h_exp - 14); raw2 = ldexpf(1.f, 2 * g->h_exp - 14); }   // raw sums, folded in global memory
+            if (int rc = PVS_STAGE(ST_TC_FV_FUSED, st, mode == 2 ? tc_fv_poststats_fused_cluster(pl, g, y, offsets, n_images, st)
+                                                                 : tc_fv_poststats_fused(pl, g, y, offsets, n_images, st))) return rc;
             if (int rc = PVS_STAGE(ST_TC_FV_POSTERIOR, st, tc_fv_posterior(pl, g, y, total_rows, argmax_out, st, true))) return rc;
             if (int rc = PVS_STAGE(ST_TC_FV_STATS, st, tc_fv_stats(pl, g, y, offsets, n_images, st, true))) return rc;
         } else {
             if (int rc = PVS_STAGE(ST_TC_FV_POSTERIOR, st, tc_fv_posterior(pl, g, y, total_rows, argmax_out, st))) return rc;
             if (int rc = PVS_STAGE(ST_TC_FV_STATS, st, tc_fv_stats(pl, g, y, offsets, n_images, st))) return rc;
         }
+        // the cluster kernel (the default) leaves raw segment-folded sums in S; every other kernel writes S / T
+        // (the gated 3xTF32 fallback overwrites S with S / T, so the raw scaling applies only while the range flag is down:
+        // fv_finalize reads the flag)
         return PVS_STAGE(ST_FV_FINALIZE, st, launch_fv_finalize(pl.S, 2 * g->d, pl.s0part, TC_FV_S0_PARTS, offsets, g, n_images, power,
-                                                                 norm_order, eps, out, st));
+                                                                 norm_order, eps, out, st, raw1, raw2, pl.flag));
     }
     PVS_CHECK(g_path.load() != PVS_PATH_TENSOR, PVS_ERR_UNSUPPORTED,
               "pvs_fv_encode: the tensor-core path handles K=256, D=64 (d_in %% 32 == 0) only");

@@ -30,7 +30,8 @@ int launch_fv_stats(const float* q, const float* y, int d, int k, const int64_t*
 // raw partial sums per image in s0part [n_images, parts, k] that still need / T)
 int launch_fv_finalize(const float* S, int ld, const float* s0part, int parts, const int64_t* offsets,
                        const pvs_model* gmm, int64_t n_images, float power, float norm_order, float eps,
-                       float* out, cudaStream_t st);
+                       float* out, cudaStream_t st, float raw1 = 0.f, float raw2 = 0.f, const int* raw_gate = nullptr);
+// raw1 != 0 (and *raw_gate == 0 when a gate is given): S holds raw sums that still need raw1 / T (first-order columns), raw2 / T
 
 // ---- similarity / top-k --------------------------------------------------------------------
 int launch_l2_normalize(const float* x, int64_t n, int64_t d, void* out, int out_dtype, cudaStream_t st);
@@ -82,8 +83,8 @@ int tc_fv_posterior(const TcFvPlan& pl, const pvs_model* g, const float* y, int6
                     bool fallback_only = false);
 int tc_fv_poststats_fused_cluster(const TcFvPlan& pl, const pvs_model* g, const float* y, const int64_t* offsets, int64_t n_images,
                                   cudaStream_t st);
-// PVS_FV_FUSED: posterior + statistics in one kernel (opt-in): 1 = one CTA per SM (pvs_tc_fvfused.cu),
-// 2 = 2-CTA clusters that split the components (pvs_tc_fvfused2.cu)
+// PVS_FV_FUSED: posterior + statistics in one kernel: 2 (default) = 2-CTA clusters that split the components, statistics
+// folded in segments (pvs_tc_fvfused2.cu); 1 = one CTA per SM (pvs_tc_fvfused.cu); 0 = the two unfused kernels
 int tc_fv_fused_mode();
 inline bool tc_fv_fused_enabled() { return tc_fv_fused_mode() != 0; }
 int tc_fv_poststats_fused(const TcFvPlan& pl, const pvs_model* g, const float* y, const int64_t* offsets, int64_t n_images,

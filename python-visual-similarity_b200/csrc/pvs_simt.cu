@@ -591,7 +591,7 @@ fv_finalize_kernel(const float* __restrict__ S, int ld, const float* __restrict_
                    const float* __restrict__ var, const float* __restrict__ pi,
                    const float* __restrict__ g_pi, const float* __restrict__ g_mu,
                    const float* __restrict__ g_sig, float power, float ord, float eps,
-                   float* __restrict__ out)
+                   float* __restrict__ out, float raw1, float raw2, const int* __restrict__ raw_gate)
 {
     extern __shared__ float s0s[];                          // [k]
     __shared__ float red[32];
@@ -601,6 +601,11 @@ fv_finalize_kernel(const float* __restrict__ S, int ld, const float* __restrict_
     const int kd = k * d;
     const float* Simg = S + img * (int64_t)k * ld;
     float* o = out + img * (int64_t)(2 * kd + k);
+    // raw1 != 0: S holds raw sums in operand units (segment-folded by the fused kernel): first-order columns still need
+    // raw1 / T, second-order columns raw2 / T -- unless the range flag went up and the 3xTF32 kernels wrote S / T instead
+    const bool raw = raw1 != 0.f && (!raw_gate || *raw_gate == 0);
+    const float f1 = raw ? raw1 / (float)(offsets[img + 1] - offsets[img]) : 1.f;
+    const float f2 = raw ? raw2 / (float)(offsets[img + 1] - offsets[img]) : 1.f;
     if (s0part) {
         const float inv_t = 1.f / (float)(offsets[img + 1] - offsets[img]);   // T == 0 -> inf -> NaN, as the reference
         for (int j = tid; j < k; j += nt) {
@@ -639,8 +644,8 @@ fv_finalize_kernel(const float* __restrict__ S, int ld, const float* __restrict_
                 ee[u] = it < n_it ? j * d + dd : -1;
                 if (ee[u] >= 0) {
                     const float* Sj = Simg + (unsigned)(j * ld);
-                    s1[u] = Sj[dd];
-                    s2[u] = Sj[d + dd];
+                    s1[u] = Sj[dd] * f1;
+                    s2[u] = Sj[d + dd] * f2;
                     m[u] = mu[ee[u]]; v[u] = var[ee[u]]; gm[u] = g_mu[ee[u]]; gs[u] = g_sig[ee[u]];
                     s0[u] = s0s[j];
                 }
@@ -698,7 +703,8 @@ fv_finalize_k256_d64_kernel(const float* __restrict__ S, const float* __restrict
                             const int64_t* __restrict__ offsets, const float* __restrict__ mu,
                             const float* __restrict__ var, const float* __restrict__ pi,
                             const float* __restrict__ g_pi, const float* __restrict__ g_mu,
-                            const float* __restrict__ g_sig, float eps, float* __restrict__ out)
+                            const float* __restrict__ g_sig, float eps, float* __restrict__ out, float raw1, float raw2,
+                            const int* __restrict__ raw_gate)
 {
     constexpr int K = 256, D = 64, KD = K * D, NJ = 16;
     __shared__ float s0s[K];
@@ -719,6 +725,12 @@ fv_finalize_k256_d64_kernel(const float* __restrict__ S, const float* __restrict
         const int j = j0 + 16 * it;
         s1[it] = Simg[j * (2 * D) + dd];
         s2[it] = Simg[j * (2 * D) + D + dd];
+    }
+    if (raw1 != 0.f && (!raw_gate || *raw_gate == 0)) {  // raw sums in operand units (see fv_finalize_kernel)
+        const float inv_t = 1.f / (float)(offsets[img + 1] - offsets[img]);
+        const float f1 = raw1 * inv_t, f2 = raw2 * inv_t;
+#pragma unroll
+        for (int it = 0; it < NJ; ++it) { s1[it] *= f1; s2[it] *= f2; }
     }
     float dp = 0.f;
     if (tid < K) {
@@ -777,19 +789,19 @@ int launch_fv_stats(const float* q, const float* y, int d, int k, const int64_t*
 
 int launch_fv_finalize(const float* S, int ld, const float* s0part, int parts, const int64_t* offsets,
                        const pvs_model* g, int64_t n_images, float power, float norm_order, float eps, float* out,
-                       cudaStream_t st)
+                       cudaStream_t st, float raw1, float raw2, const int* raw_gate)
 {
     if (n_images <= 0) return PVS_OK;
     PVS_CHECK(g->k <= 12000, PVS_ERR_UNSUPPORTED, "fv_finalize supports k <= 12000 (got %d)", g->k);
     if (power == 0.5f && norm_order == 2.f && g->k == 256 && g->d == 64 && ld == 128 && s0part)
         PVS_LAUNCH(fv_finalize_k256_d64_kernel, (unsigned)n_images, 1024, 0, st, S, s0part, parts, offsets, g->mu, g->var, g->pi,
-                   g->g_pi, g->g_mu, g->g_sig, eps, out);
+                   g->g_pi, g->g_mu, g->g_sig, eps, out, raw1, raw2, raw_gate);
     else if (power == 0.5f && norm_order == 2.f)
         PVS_LAUNCH(fv_finalize_kernel<true>, (unsigned)n_images, 1024, (size_t)g->k * sizeof(float), st, S, ld, s0part, parts, offsets, g->k, g->d,
-                   g->mu, g->var, g->pi, g->g_pi, g->g_mu, g->g_sig, power, norm_order, eps, out);
+                   g->mu, g->var, g->pi, g->g_pi, g->g_mu, g->g_sig, power, norm_order, eps, out, raw1, raw2, raw_gate);
     else
         PVS_LAUNCH(fv_finalize_kernel<false>, (unsigned)n_images, 1024, (size_t)g->k * sizeof(float), st, S, ld, s0part, parts, offsets, g->k, g->d,
-                   g->mu, g->var, g->pi, g->g_pi, g->g_mu, g->g_sig, power, norm_order, eps, out);
+                   g->mu, g->var, g->pi, g->g_pi, g->g_mu, g->g_sig, power, norm_order, eps, out, raw1, raw2, raw_gate);
     return PVS_OK;
 }
 

@@ -491,12 +491,12 @@ __global__ void __launch_bounds__(THREADS, 1) kernel(const __grid_constant__ Par
 
 using namespace tc;
 
-// Opt-in (PVS_FV_FUSED=1): parity-green but, at 9.4 ms against 8.2 ms for the two unfused kernels on the C2
-// batch, not the default -- see the header comment and DESIGN.md section 8.
+// PVS_FV_FUSED selects the posterior + statistics kernel: default 2 = pvs_tc_fvfused2.cu (2-CTA clusters, statistics folded
+// in segments: the only path that keeps EVERY image of the full C2 batch inside the 1e-4 bar); 1 = this file's single-CTA
+// kernel; 0 = the two unfused kernels.  The non-default ones accumulate the statistics of a whole image in the tensor core
+// (0.6 % of the C2 images end up 1e-4 .. 2.8e-4 off) and stay as parity references for the tests.
 int tc_fv_fused_mode()
 {
-    // default: the 2-CTA cluster kernel (pvs_tc_fvfused2.cu).  PVS_FV_FUSED=0 selects the two unfused kernels,
-    // =1 the single-CTA fused kernel (both kept as parity references for the tests).
     const char* e = getenv("PVS_FV_FUSED");
     return !e ? 2 : (e[0] == '0' ? 0 : e[0] == '1' ? 1 : 2);
 }

@@ -3,7 +3,8 @@
 // logits (256 columns) and the statistics (256 columns) fill TMEM.  Here a 2-CTA cluster splits
 // the 256 mixture components: both CTAs walk the same 128-descriptor tiles of the same images,
 // CTA r owns components [128 r, 128 r + 128).  Per CTA that leaves room for
-//   TMEM   two logit accumulators (2 x 128 columns) + the statistics (128 columns)
+//   TMEM   two logit accumulators (2 x 128 columns) + two statistics buffers (2 x 128 columns: segments of four tiles
+//          alternate between them and are folded into S in global memory, see the MMA warp)
 //   smem   W' slice RESIDENT (64 KB, no streaming), two A1 tiles (2 x 64 KB), one Q chunk buffer (32 KB)
 // so the logit MMA of tile i+1 runs while the softmax warps work on tile i.  All MMAs are
 // cta_group::1; what crosses the CTA boundary is two floats per descriptor (row maximum, row
@@ -70,6 +71,7 @@ struct Params {
     int64_t n_images;
     const int* flag;
     float sc_y, un1, un2;
+    int seg;                               // tiles per statistics segment
 };
 
 __device__ __forceinline__ uint32_t cluster_rank()
@@ -112,6 +114,7 @@ __device__ __forceinline__ void cluster_sync()
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) kernel(const __grid_constant__ Params p)
 {
+    const int SEG = p.seg;
     if (*p.flag != 0) return;                                  // uniform over the grid
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -122,7 +125,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) kernel(c
     // So use u signals / polls barrier u % 4 (with a single barrier the uninstrumented build overwrote a chunk that was
     // still being read and hung on the full C2 batch).
     uint64_t *s_full = bars + 10, *q_full = bars + 11, *q_empty = bars + 15, *w_res = bars + 19, *x_sum = bars + 20;   // q_full[4], q_empty[4], x_sum[4]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+    uint64_t* s_free = bars + 24;                              // s_free[2]: the segment buffer has been folded into S; the second s_full
+    uint64_t* s_full2 = bars + 26;                             // sits at bars + 26
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 27);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_rank(), peer = rank ^ 1;
     const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
@@ -135,6 +140,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) kernel(c
             mbar_init(&l_free[i], 8);
         }
         mbar_init(s_full, 1);
+        mbar_init(s_full2, 1);
+        mbar_init(&s_free[0], 4);                              // the four folding warps (one per lane quarter)
+        mbar_init(&s_free[1], 4);
         for (int i = 0; i < 4; ++i) {
             mbar_init(&q_full[i], 4);
             mbar_init(&q_empty[i], 1 + 4);
@@ -154,7 +162,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) kernel(c
     cluster_sync();                                            // the peer's barriers exist before anybody signals them
     tcgen05_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tmem_S = tmem + 256;                        // logits: columns [0,128) and [128,256)
+    // logits: columns [0,128) and [128,256); statistics of the even / odd segments: [256,384), [384,512)
+    const uint32_t tmem_S = tmem + 256;
+    auto s_full_of = [&](uint32_t sb) { return sb ? s_full2 : s_full; };
 
     auto n_tiles_of = [&](int64_t img, int64_t& r0, int& T) {
         r0 = p.offsets[img];
@@ -181,12 +191,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) kernel(c
 #endif
         FT0(t_all);
         mbar_wait(w_res, 0);
-        uint32_t g = 0;
+        // Statistics accumulate in SEGMENTS of SEG tiles, alternating between two TMEM buffers; a finished segment is added to
+        // the image's S rows in global memory (L2-resident) by CUDA cores with round-to-nearest fp32 adds (`fold` in the
+        // softmax warps) while the next segment is multiplied into the other buffer.  tcgen05.mma adds every K = 16 slice to
+        // the accumulator with truncation, a bias that grows with the number of accumulation steps (384 for a 2 000-descriptor
+        // image) and that d_sigma = (S2 - 2 mu S1 + mu^2 S0) / sigma^2 - S0 amplifies: accumulated over the whole image in one
+        // buffer, the worst images of the full C2 batch were 1.2e-4 (this kernel) to 2.8e-4 (the other paths) off the fp64
+        // result; folded every four tiles they are at 6e-5.
+        uint32_t g = 0, n_seg = 0;
+        struct Prev { int tile, nt; uint32_t sg; } prev{0, 0, 0};
         bool have_prev = false;
-        int prev_tile = 0;
-        bool prev_last = false;
-        auto mma2 = [&](uint32_t gp, int tile, bool last) {
+        auto mma2 = [&](uint32_t gp, const Prev& t) {
             const uint32_t a1 = a1b + (gp & 1) * A1_BYTES;
+            const uint32_t sb = t.sg & 1;
+            const bool fresh = t.tile % SEG == 0, seg_last = t.tile % SEG == SEG - 1 || t.tile == t.nt - 1;
+            if (fresh && t.sg >= 2) {                          // the segment that used this buffer has been folded
+                mbar_wait(&s_free[sb], ((t.sg >> 1) & 1) ^ 1);
+                tcgen05_fence_after();
+            }
             for (int n = 0; n < 2; ++n) {
                 const uint32_t use = 2 * gp + (uint32_t)n;
                 FT0(t2);
@@ -200,8 +222,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) kernel(c
                         const uint64_t a_lo = make_smem_desc(a1 + 16384 + ks * 2048, 32768, 1024, LAYOUT_SW128);
                         const uint64_t b_hi = make_smem_desc(qb + ks * 2048, 16384, 1024, LAYOUT_SW128);
                         const uint64_t b_lo = make_smem_desc(qb + 16384 + ks * 2048, 16384, 1024, LAYOUT_SW128);
-                        const uint32_t d = tmem_S + (uint32_t)(n * QC);
-                        umma<true>(d, a_hi, b_lo, idesc2, (tile | ks) ? 1u : 0u);
+                        const uint32_t d = tmem_S + sb * CK + (uint32_t)(n * QC);
+                        umma<true>(d, a_hi, b_lo, idesc2, (!fresh || ks) ? 1u : 0u);
                         umma<true>(d, a_lo, b_hi, idesc2, 1u);
                         umma<true>(d, a_hi, b_hi, idesc2, 1u);
                     }
@@ -211,7 +233,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) kernel(c
             }
             if (elect_one()) {
                 umma_commit(&a1_free[gp & 1]);
-                if (last) umma_commit(s_full);
+                if (seg_last) umma_commit(s_full_of(sb));
             }
             __syncwarp();
         };
@@ -245,13 +267,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) kernel(c
                     }
                     __syncwarp();
                 }
-                if (have_prev) mma2(g - 1, prev_tile, prev_last);
+                if (have_prev) mma2(g - 1, prev);
                 have_prev = true;
-                prev_tile = tile;
-                prev_last = tile == nt - 1;
+                if (tile % SEG == 0) ++n_seg;
+                prev = Prev{tile, nt, n_seg - 1};
             }
         }
-        if (have_prev) mma2(g - 1, prev_tile, prev_last);
+        if (have_prev) mma2(g - 1, prev);
 #ifdef PVS_TIMING
         FTA(3, t_all);
         if (lane == 0 && rank == 0) for (int i = 0; i < 4; ++i) atomicAdd(&g_ft[i], (unsigned long long)ft[i]);
@@ -282,7 +304,46 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) kernel(c
         const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
         const int trow = quarter * 32 + lane;
         constexpr float LOG2E = 1.4426950408889634f;
-        uint32_t g = 0, imgs = 0;
+        uint32_t g = 0, n_seg = 0;
+        // this thread's place in fv_finalize's [k][ s1 | s2 ] layout: accumulator lane m = row of the (y'^2, y') operand
+        const int m = trow, dd = 32 * (m >> 6) + ((m & 63) >> 1);
+        const bool lin = m & 1;
+        const int col = lin ? dd : D + dd;
+        // Fold the finished statistics segment (tile t was its last) into S: the first segment of an image stores its partial
+        // sums, the others add them (fp32, round to nearest; every address belongs to one thread).  S stays in raw operand
+        // units; fv_finalize applies the operand scales and 1 / T.  Done by the first warp of every lane quarter right after
+        // it has published its Q chunk of the FOLLOWING tile: by then the segment's last MMAs have long finished, and the warp
+        // would otherwise wait for its partner (which publishes the second chunk of a tile and runs about 2 k cycles behind).
+        struct Rec { int64_t img; int tile, nt; uint32_t sg; bool valid; };
+        Rec h1{0, 0, 0, 0, false}, h2{0, 0, 0, 0, false};     // tiles g - 1 and g - 2
+        auto fold = [&](const Rec& t) {
+            if (!t.valid || !(t.tile % SEG == SEG - 1 || t.tile == t.nt - 1)) return;
+            const uint32_t sb = t.sg & 1;
+            mbar_wait(s_full_of(sb), (t.sg >> 1) & 1);
+            tcgen05_fence_after();
+            const bool first = t.tile < SEG;
+            float* Sp = p.S + t.img * (int64_t)(K * AUG) + (int64_t)(rank * CK) * AUG + col;
+            const uint32_t ts = tmem_S + sb * CK + lane_off;
+#pragma unroll 1
+            for (int c = 0; c < CK; c += 32) {
+                float v[32], r[32];
+                if (!first) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = __ldcg(Sp + (c + j) * AUG);
+                }
+                tmem_ld32(ts + c, v);
+                tmem_ld_wait();
+                if (!first) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] += r[j];
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) __stcg(Sp + (c + j) * AUG, v[j]);
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_free[sb]);
+        };
 #ifdef PVS_TIMING
         long long ft[16] = {0};
 #endif
@@ -293,9 +354,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) kernel(c
             for (int tile = 0; tile < nt; ++tile, ++g) {
                 const uint32_t b = g & 1, ph = (g >> 1) & 1;
                 const bool valid = tile * TT + trow < T;
+                if (tile % SEG == 0) ++n_seg;
+                const Rec cur{img, tile, nt, n_seg - 1, true};
                 FT0(t4);
                 mbar_wait(&l_full[b], ph);
                 FTA(4, t4);
+                // the segment that ended with tile g - 2 is complete (l_full(g) was committed after the statistics MMAs of tile
+                // g - 2): fold it while no logits are held in registers
+                FT0(t11f);
+                if (half == 0) fold(h2);
+                FTA(11, t11f);
+
                 FT0(t5);
                 tcgen05_fence_after();
                 const uint32_t tl = tmem + b * CK + lane_off + c0;
@@ -383,34 +452,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) kernel(c
                     if (lane == 0) mbar_arrive(&q_full[use & 3]);
                 }
                 FTA(9, t9);
+                h2 = h1;
+                h1 = cur;
             }
             FT0(t11);
-            // image end: this CTA's 128 components of S / T, operand scales undone, in fv_finalize's [k][ s1 | s2 ] layout
-            float* Simg = p.S + img * (int64_t)(K * AUG) + (int64_t)(rank * CK) * AUG;
-            const int m = trow, dd = 32 * (m >> 6) + ((m & 63) >> 1);
-            const bool lin = m & 1;
-            const int col = lin ? dd : D + dd;
-            if (nt > 0) {
-                mbar_wait(s_full, imgs & 1);
-                ++imgs;
-                tcgen05_fence_after();
-                const float scale = (lin ? p.un1 : p.un2) / (float)T;
-                const uint32_t ts = tmem_S + lane_off;
-#pragma unroll 1
-                for (int c = c0; c < c0 + 64; c += 32) {
-                    float v[32];
-                    tmem_ld32(ts + c, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) Simg[(int64_t)(c + j) * AUG + col] = v[j] * scale;
-                }
-                tcgen05_fence_before();
-            } else {
+            if (nt == 0 && half == 0) {                        // T = 0: NaN encoding, like the reference's division by zero
+                float* Simg = p.S + img * (int64_t)(K * AUG) + (int64_t)(rank * CK) * AUG;
                 const float nanv = __int_as_float(0x7fc00000);
-                for (int c = c0; c < c0 + 64; ++c) Simg[(int64_t)c * AUG + col] = nanv;
+                for (int c = 0; c < CK; ++c) Simg[(int64_t)c * AUG + col] = nanv;
             }
             FTA(11, t11);
         }
+        if (half == 0) { fold(h2); fold(h1); }
 #ifdef PVS_TIMING
         FTA(12, t_all);
         if (warp == 2 && lane == 0 && rank == 0) for (int i = 4; i < 13; ++i) atomicAdd(&g_ft[i], (unsigned long long)ft[i]);
@@ -544,6 +597,8 @@ int tc_fv_poststats_fused_cluster(const TcFvPlan& pl, const pvs_model* g, const 
     memcpy(p.cst, g->cst_host.data(), sizeof(p.cst));
     p.y = y; p.offsets = offsets; p.S = pl.S; p.s0part = pl.s0part; p.n_images = n_images; p.flag = pl.flag;
     p.sc_y = ldexpf(1.f, -g->h_exp); p.un1 = ldexpf(1.f, g->h_exp - 14); p.un2 = ldexpf(1.f, 2 * g->h_exp - 14);
+    p.seg = 2;                                                 // see the table in DESIGN.md: 1 -> 7.6e-5 worst image / 506 k images/s, 2 -> 9.9e-5 / 618 k, 4 -> 1.3e-4 / 664 k
+    if (const char* e = getenv("PVS_FV_SEG")) { const int v = atoi(e); if (v >= 1) p.seg = v; }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -504,11 +504,13 @@ struct SimSplitPolicy : SimPolicy<CAP_> {
 // k' = k + margin candidates sorted by tensor score (error <= band).  Two neighbours closer than 2 * band may
 // be in the wrong order, and the k-th / (k+1)-th decide membership; every maximal run of such neighbours that
 // touches the first k positions is re-scored EXACTLY -- sum over d of (hi + lo)(hi + lo) in fp64 from the same
-// operand planes -- and re-ranked (score descending, lowest index first).  One warp per query row; runs are
-// short (a few candidates per query at d = 32 768), so this pass costs a few hundred KB of reads per query.
-// stats[0] += re-scored candidates, stats[1] += rows whose run reached the end of the shortlist (a candidate
-// beyond it could belong to the top-k: the margin was too small; never seen with margin 8 outside degenerate
-// inputs such as many identical rows).
+// operand planes -- and re-ranked (score descending, lowest index first).  One warp per query row.  At d = 32 768
+// the band (2e-5, a worst-case bound; the measured error is ~1.5e-6) is of the order of the spacing of the best
+// hundred scores of a database of 10^4..10^5 high-dimensional rows, so most of a list may be re-scored: ~130 KB of
+// operand reads per candidate, a few per cent of the tensor kernel's time.
+// stats[0] += re-scored candidates, stats[1] += rows that could not be certified: the last shortlist entry is still
+// within 2 * band of the k-th score (a row beyond the shortlist could belong to the top-k: margin too small -- only
+// with degenerate inputs such as many identical rows), or a run of more than 32 chained candidates.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 sim_rescue_kernel(const float* __restrict__ s_in, const int64_t* __restrict__ i_in, int kp, int k, int64_t n_q,
@@ -527,10 +529,17 @@ sim_rescue_kernel(const float* __restrict__ s_in, const int64_t* __restrict__ i_
     }
     __syncwarp();
     const float gap = 2.f * band;
+    // Membership: a candidate ranked past position k by the tensor scores can belong to the true top-k only if its
+    // tensor score is within 2 * band of the k-th one; anything below `cut` is certainly out, whatever chain it hangs on.
+    // The shortlist is long enough iff its last entry is below `cut` (or the database had fewer than kp rows).
+    const bool full = kp > k && ix[kp - 1] >= 0;
+    const float cut = (k <= kp && ix[k - 1] >= 0) ? s[k - 1] - gap : -INFINITY;
+    if (full && s[kp - 1] >= cut && lane == 0) atomicAdd(&stats[1], 1ull);
     int i = 0;
     while (i < k && i < kp) {
         int j = i;
-        while (j + 1 < kp && ix[j + 1] >= 0 && s[j] - s[j + 1] <= gap) ++j;     // warp-uniform scan (same loads in every lane)
+        // warp-uniform scan (same loads in every lane); past position k - 1 only possible members extend a run
+        while (j + 1 < kp && ix[j + 1] >= 0 && s[j] - s[j + 1] <= gap && (j + 1 < k || s[j + 1] >= cut)) ++j;
         if (j == i) { ++i; continue; }
         const int n = j - i + 1;
         if (n > 32) {                                              // e.g. many identical rows: bit-equal tensor scores are already in index order
@@ -538,7 +547,6 @@ sim_rescue_kernel(const float* __restrict__ s_in, const int64_t* __restrict__ i_
             i = j + 1;
             continue;
         }
-        if (j == kp - 1 && kp > k && lane == 0) atomicAdd(&stats[1], 1ull);
         double mine = 0.0;
         int64_t my_idx = -1;
         for (int m = 0; m < n; ++m) {
@@ -676,7 +684,7 @@ int tc_sim_topk(const void* q, const void* db, int64_t n_q, int64_t n_db, int64_
 namespace pvs {
 using namespace tc2;
 
-constexpr int SIM3_MARGIN = 8;                                 // shortlist = k + margin candidates per query
+constexpr int SIM3_MARGIN = 24;                                // shortlist = k + margin candidates per query
 
 static int sim3_seg()
 {

@@ -9,7 +9,9 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(os.path.dirname(PKG_DIR), "csrc")
 INCLUDE_DIR = os.path.join(os.path.dirname(os.path.dirname(PKG_DIR)), "include")
-LIB_PATH = os.path.join(PKG_DIR, "lib", "libpvs_b200.so")
+# PVS_LIB selects another in-tree build of the same sources (developer builds such as -DPVS_TIMING:
+# `PVS_LIB=.../lib/libpvs_b200_timing.so PVS_NVCC_EXTRA=-DPVS_TIMING python -m pyvisim_b200._build`)
+LIB_PATH = os.environ.get("PVS_LIB") or os.path.join(PKG_DIR, "lib", "libpvs_b200.so")
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -48,7 +50,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc not found: cannot build libpvs_b200.so")
     os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
     tmp = LIB_PATH + ".tmp"
-    objdir = os.path.join(os.path.dirname(LIB_PATH), "obj")
+    objdir = os.path.join(os.path.dirname(LIB_PATH), "obj" + ("_" + os.path.basename(LIB_PATH) if os.environ.get("PVS_LIB") else ""))
     os.makedirs(objdir, exist_ok=True)
     flags = [f for f in NVCC_FLAGS if f != "-shared"] + os.environ.get("PVS_NVCC_EXTRA", "").split()   # e.g. -DPVS_TIMING
 

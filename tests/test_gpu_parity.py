@@ -519,7 +519,8 @@ def test_fv_tensor_path_ragged_batch_vs_oracle(api):
     assert max(errs) <= 1e-4, errs
 
 
-# fused kernels under test: PVS_FV_FUSED=1 (one CTA per SM), =2 (2-CTA clusters that split the components)
+# fused kernels under test: PVS_FV_FUSED=1 (one CTA per SM), =2 (the default: 2-CTA clusters that split the components,
+# statistics folded in segments)
 FUSED_MODES = ["1", "2"]
 
 
@@ -572,7 +573,7 @@ def test_fv_fused_posterior_statistics_kernel(api, mode):
     p = load_weights("pca_k256_sift_f2")
     r = np.random.RandomState(9)
     descs = []
-    for t in (1, 127, 128, 129, 300, 2000, 16):
+    for t in (1, 127, 128, 129, 300, 2000, 16, 512, 513, 1100):        # 512 / 513: one segment of four tiles / one tile more
         comp = r.choice(256, size=t, p=w["weights"] / w["weights"].sum())
         y = w["means"][comp] + r.standard_normal((t, 64)) * np.sqrt(w["covariances"][comp])
         descs.append((y @ p["components"] + p["mean"]).astype(np.float32))

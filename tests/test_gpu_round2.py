@@ -171,7 +171,7 @@ def test_deepconv_feature_batched_on_device(api):
 
 def test_fv_fused_default_full_c2_batch(api):
     """BASELINE.json configs[1] at full size (8 189 images x 2 000 SIFT-like descriptors) through the default
-    (fused cluster) kernel: every image against the unfused kernels, a sample against the fp64 oracle, unit norms,
+    (fused cluster) kernel: every image against the fp32 CUDA-core path, a sample against the fp64 oracle, unit norms,
     and bit-identical results when the batch is encoded a second time (no race in the fused pipeline)."""
     import os
     from conftest import load_weights
@@ -192,17 +192,30 @@ def test_fv_fused_default_full_c2_batch(api):
     assert torch.equal(a, b)
     assert torch.isfinite(a).all()
     assert (a.norm(dim=1) - 1).abs().max().item() <= 1e-5
-    os.environ["PVS_FV_FUSED"] = "0"
+    # every image against the fp32 CUDA-core path (no tensor-core accumulation: 0.2e-5 .. 0.9e-5 of the fp64 result), the
+    # ones that differ most -- that is where the tensor path has its largest error -- and the chunk boundaries against the
+    # fp64 oracle.  (The statistics are accumulated in segments of four tiles precisely because of this tail: over whole
+    # images the worst of the 8 189 were 1.2e-4 .. 2.8e-4 off.)
+    api.nat.set_path(api.nat.PATH_SIMT)
     try:
-        u = enc.encode_descriptors(x, offs)
+        u = torch.empty_like(a)
+        for i0 in range(0, n, 1024):                           # the CUDA-core path materialises the posteriors: keep the workspace small
+            i1 = min(n, i0 + 1024)
+            u[i0:i1] = enc.encode_descriptors(x[i0 * T:i1 * T], offs[i0:i1 + 1] - offs[i0])
     finally:
-        os.environ.pop("PVS_FV_FUSED", None)
-    rel = ((a - u).norm(dim=1) / u.norm(dim=1)).max().item()
-    assert rel <= 5e-5 and not torch.equal(a, u), rel
+        api.nat.set_path(api.nat.PATH_AUTO)
+    per_image = (a - u).norm(dim=1) / u.norm(dim=1)
+    rel = per_image.max().item()
+    assert rel <= 1e-4 and not torch.equal(a, u), rel
+    worst = per_image.topk(4).indices.tolist()
     w, p = load_weights("gmm_k256_sift_pca"), load_weights("pca_k256_sift_f2")
-    pick = [0, 1, 591, 592, 4095, 8188]                       # chunk boundaries of the 592-image calls included
+    pick = [0, 1, 591, 592, 4095, 8188] + worst               # chunk boundaries of the 592-image calls included
     descs = [x[i * T:(i + 1) * T].cpu().numpy() for i in pick]
     ref = O.fv_encode(descs, w["weights"], w["means"], w["covariances"], w["precisions_cholesky"],
                       pca=(p["components"], p["mean"]))
-    got = a[pick].cpu().numpy()
-    assert max(rel_l2(got[i], ref[i]) for i in range(len(pick))) <= 1e-4
+    got, got_u = a[pick].cpu().numpy(), u[pick].cpu().numpy()
+    e_f = [rel_l2(got[i], ref[i]) for i in range(len(pick))]
+    e_u = [rel_l2(got_u[i], ref[i]) for i in range(len(pick))]
+    print(f"\n[fv c2 full] tensor path vs CUDA-core path: max {rel:.2e}, median {per_image.median().item():.2e}; vs fp64 oracle on {pick}: "
+          f"tensor {max(e_f):.2e}, CUDA cores {max(e_u):.2e}")
+    assert max(e_f) <= 1e-4 and max(e_u) <= 1e-4, (e_f, e_u)
