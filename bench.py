@@ -1,12 +1,16 @@
 #!/usr/bin/env python
 """bench.py -- BASELINE.json's metric on its configuration, B200 path vs the reference path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4]
 
-Workload at N=1 (and per rank at N>1, weak scaling): BASELINE.json configs[1] --
-Fisher-vector encode, GMM K=256 (diag) on SIFT-PCA-64 (bundled
-gmm_k256_sift_pca + pca_k256_sift_f2), 8,189 synthetic images x 2,000 SIFT-like 128-D fp32
-descriptors.  One step = one pass of the encode path over that batch.
+Default workload (the one BASELINE.json's metric is quoted on), at N=1 and per rank at N>1 (weak scaling):
+configs[1] -- Fisher-vector encode, GMM K=256 (diag) on SIFT-PCA-64 (bundled gmm_k256_sift_pca +
+pca_k256_sift_f2), 8,189 synthetic images x 2,000 SIFT-like 128-D fp32 descriptors.  One step = one pass of the
+encode path over that batch.  --workload c3: configs[2], VLAD on 100,000 images x 196 x 514-D (sharded over the
+ranks, strong scaling); --workload c4: configs[3], all-pairs cosine + top-100 over 262,144 VLAD-32768 vectors
+(database replicated in bf16, query rows sharded, top-k lists all-gathered; strong scaling).  At every N the c2
+line also carries `extra.retrieval_allgather`: a 65,536-row instance of configs[3] through the same sharded path,
+so the one collective of the hot path is exercised by the scaling run.
 
 value  : images/s, whole job, descriptors already resident in HBM, timed with CUDA events
          on the launching stream, max over ranks.  Inputs (8.4 GB) >> L2 (126 MB), so no
@@ -33,7 +37,40 @@ WORKLOADS = {
     # name: (n_images, T, d_in, description)
     "c2": (8189, 2000, 128, "FV encode, GMM K=256 diag, SIFT-128 -> PCA-64, 8189 images x 2000 descriptors"),
     "c3": (100000, 196, 514, "VLAD encode, K=256, VGG16 conv 514-D, 196 descriptors/image, 100k images"),
+    "c4": (262144, 0, 32768, "all-pairs cosine + top-100 over 262144 VLAD vectors (256 x 128 = 32768-D)"),
 }
+# algorithmic work per image of the FV C2 path (PCA + logits + statistics; descriptors in,
+# fp32 encoding out)
+C2_FLOP_PER_IMAGE = 2 * 2000 * 128 * 64 + 2 * (2 * 2000 * 256 * 128)       # 294.9 MFLOP
+C2_BYTES_PER_IMAGE = 2000 * 128 * 4 + 33024 * 4                              # 1 156 096 B
+
+
+def host_threads():
+    """(threads the BLAS pools will use now, vendor string) via threadpoolctl."""
+    try:
+        from threadpoolctl import threadpool_info
+        info = [i for i in threadpool_info() if i.get("user_api") == "blas"]
+        if info:
+            return max(i.get("num_threads", 1) for i in info), ", ".join(sorted({f"{i.get('internal_api')} {i.get('version')}" for i in info}))
+    except Exception:
+        pass
+    return os.cpu_count(), "unknown"
+
+
+class blas_threads:
+    """All host cores for the CPU legs (torchrun exports OMP_NUM_THREADS=1, which would cripple the reference arm), or 1."""
+    def __init__(self, n):
+        self.n, self.ctx = n, None
+    def __enter__(self):
+        try:
+            from threadpoolctl import threadpool_limits
+            self.ctx = threadpool_limits(limits=self.n)
+            self.ctx.__enter__()
+        except Exception:
+            self.ctx = None
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
 
 
 def peaks():
@@ -67,31 +104,93 @@ def oracle_fv_rate(descs, seconds_hint=None):
     return len(descs) / dt, dt, out
 
 
+def vlad_like_rows(rng, n, d=32768):
+    """VLAD-shaped unit rows: 256 unit blocks of 128, ~15 % of the blocks empty."""
+    b = rng.standard_normal((n, d // 128, 128)).astype(np.float32)
+    b /= np.linalg.norm(b, axis=2, keepdims=True)
+    b *= (rng.random((n, d // 128, 1)) > 0.15)
+    b = b.reshape(n, d)
+    return b / np.maximum(np.linalg.norm(b, axis=1, keepdims=True), 1e-30)
+
+
+def cpu_legs(sample_fv, sample_vlad=16, sim_rows=(256, 8192)):
+    """The reference's CPU path (oracle port) for the three BASELINE.json metrics on bounded samples: all host threads
+    and one thread (BASELINE.md section 3 asks for both and for the BLAS vendor)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pvs_oracle as O
+    rng = np.random.default_rng(0)
+    T = 2000
+    descs = [sift_like_host(rng, T, 128) for _ in range(sample_fv)]
+    a = np.abs(rng.standard_normal((sample_vlad * T, 128))).astype(np.float32)
+    a = np.sqrt(a / (a.sum(1, keepdims=True) + 1e-7))
+    cen = a[rng.choice(a.shape[0], 256, replace=False)]
+    vl = [a[i * T:(i + 1) * T] for i in range(sample_vlad)]
+    q, db = vlad_like_rows(rng, sim_rows[0]), vlad_like_rows(rng, sim_rows[1])
+    out = {}
+    for tag, n in (("all_threads", os.cpu_count()), ("one_thread", 1)):
+        with blas_threads(n):
+            used, vendor = host_threads()
+            fv_descs = descs if n > 1 else descs[:max(2, sample_fv // 8)]
+            oracle_fv_rate(fv_descs[:2]); O.vlad_encode(vl[:2], cen); O.cosine_topk(q[:8], db, 100)     # warm-up (file loads, pools)
+            fv_rate = max(oracle_fv_rate(fv_descs)[0] for _ in range(2))
+            t_v = t_s = 1e30
+            for _ in range(2):
+                t0 = time.perf_counter(); O.vlad_encode(vl, cen); t_v = min(t_v, time.perf_counter() - t0)
+                t0 = time.perf_counter(); O.cosine_topk(q, db, 100); t_s = min(t_s, time.perf_counter() - t0)
+        out[tag] = {"threads": used, "fv_c2_images_per_s": fv_rate, "vlad_c1_images_per_s": sample_vlad / t_v,
+                    "cosine_top100_queries_per_s_at_8192_rows": sim_rows[0] / t_s,
+                    "cosine_top100_tflops": 2.0 * sim_rows[0] * sim_rows[1] * 32768 / t_s / 1e12}
+        out["blas"] = vendor
+    return out
+
+
 def run_reference(args):
+    """The reference's own CPU implementation of the path (the oracle port: the reference is Python on scikit-learn /
+    NumPy and cannot travel to the GPU box) on all host threads, same metric and config."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_img, T, d_in, desc = WORKLOADS["c2"]
-    sample = 32
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pvs_oracle as O
+    n_img, T, d_in, desc = WORKLOADS[args.workload]
     rng = np.random.default_rng(0)
-    descs = [sift_like_host(rng, T, d_in) for _ in range(sample)]
-    for _ in range(args.warmup):
-        oracle_fv_rate(descs[:4])
-    times = []
-    for _ in range(args.steps):
-        _, dt, _ = oracle_fv_rate(descs)
-        times.append(dt)
+    with blas_threads(os.cpu_count()):                    # torchrun exports OMP_NUM_THREADS=1
+        used, vendor = host_threads()
+        if args.workload == "c2":
+            sample, metric, unit = 32, METRIC, UNIT
+            descs = [sift_like_host(rng, T, d_in) for _ in range(sample)]
+            fn = lambda: oracle_fv_rate(descs)
+            what = f"{sample} of {n_img} images x {T} descriptors per step"
+        elif args.workload == "c3":
+            sample, metric, unit = 512, "vlad_encode_images_per_s_k256", UNIT
+            x = rng.standard_normal((sample * T, d_in)).astype(np.float32)
+            cen = x[rng.choice(x.shape[0], 256, replace=False)]
+            descs = [x[i * T:(i + 1) * T] for i in range(sample)]
+            fn = lambda: O.vlad_encode(descs, cen)
+            what = f"{sample} of {n_img} images x {T} descriptors per step"
+        else:
+            sample, metric, unit = 128, "cosine_top100_queries_per_s", "queries/s"
+            q, db = vlad_like_rows(rng, sample), vlad_like_rows(rng, 16384)
+            fn = lambda: O.cosine_topk(q, db, 100)
+            what = f"{sample} queries against 16384 of {n_img} database rows per step (scaled by 16384 / {n_img})"
+        for _ in range(max(1, min(args.warmup, 2))):
+            fn()
+        times = []
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            fn()
+            times.append(time.perf_counter() - t0)
     ms = 1e3 * float(np.mean(times))
     value = sample / (ms / 1e3)
-    cores = os.cpu_count()
+    if args.workload == "c4":
+        value *= 16384 / n_img                             # queries/s against the full database
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "sample": f"{sample} images x {T} descriptors per step"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} of {n_img} images per step, NumPy/OpenBLAS default threads"},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "scaling": "weak" if args.workload == "c2" else "strong", "vs_baseline": None, "dtype": "f64" if args.workload == "c2" else "f32",
+        "data": "synthetic", "config": {"workload": desc, "sample": what},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": used, "kind": "port", "blas": vendor, "sample": what},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
@@ -232,20 +331,74 @@ def run_extras(dev, pk):
                                                "label_flips_vs_fp32_oracle": int(bad.size), "rel_score_gap_of_flips": gaps,
                                                "descriptors": [2000, 1900]}
     del enc
-    n, d, k = 16384, 32768, 100
-    v = torch.empty((n, d), dtype=torch.bfloat16, device=dev)
-    for r in range(0, n, 4096):                           # VLAD-shaped rows: 256 unit blocks of 128, ~15 % empty
-        b = torch.randn((4096, d // 128, 128), device=dev, generator=g)
-        b = b / b.norm(dim=2, keepdim=True)
-        b = b * (torch.rand((4096, d // 128, 1), device=dev, generator=g) > 0.15)
-        b = b.reshape(4096, -1)
-        v[r:r + 4096] = (b / b.norm(dim=1, keepdim=True).clamp_min(1e-30)).bfloat16()
-    ms, _ = timed(lambda: retrieval.cosine_topk(v, v, k), 2)
-    tf = 2.0 * n * n * d / ms / 1e9
-    out["all_pairs_cosine_top100"] = {"tflops": tf, "queries_per_s": n / ms * 1e3, "n": n, "d": d, "k": k, "dtype": "bf16",
-                                      "frac_of_bf16_sustained_peak": tf / pk["bf16_tflops_sustained"],
-                                      "frac_of_bf16_burst_peak": tf / pk["bf16_tflops"]}
     return out
+
+# --------------------------------------------------------------------------------------
+# BASELINE.json configs[3]: all-pairs cosine + top-k, database replicated in bf16, query rows sharded over the ranks,
+# top-k lists all-gathered (pvs_allgather_topk through the library's NCCL communicator).  Used by --workload c4 and, with
+# a smaller database, as the retrieval leg of every c2 line.
+# --------------------------------------------------------------------------------------
+def vlad_like_device(n, d, dev, gen, dtype):
+    import torch
+    v = torch.empty((n, d), dtype=dtype, device=dev)
+    for r in range(0, n, 4096):                           # VLAD-shaped rows: 256 unit blocks of 128, ~15 % empty
+        m = min(4096, n - r)
+        b = torch.randn((m, d // 128, 128), device=dev, generator=gen)
+        b = b / b.norm(dim=2, keepdim=True)
+        b = b * (torch.rand((m, d // 128, 1), device=dev, generator=gen) > 0.15)
+        b = b.reshape(m, -1)
+        v[r:r + m] = (b / b.norm(dim=1, keepdim=True).clamp_min(1e-30)).to(dtype)
+    return v
+
+
+def run_retrieval(dev, rank, world, n, d, k, steps, warmup, pk, comm=None):
+    import torch
+    import torch.distributed as dist
+    from pyvisim_b200 import _native as N, retrieval
+    gen = torch.Generator(device=dev).manual_seed(4321)   # same seed on every rank: the database is replicated
+    db = vlad_like_device(n, d, dev, gen, torch.bfloat16)
+    lo, hi = retrieval.shard_bounds(n, world, rank)
+    q = db[lo:hi]
+
+    def step():
+        s_, i_ = retrieval.cosine_topk(q, db, k)
+        if world > 1:
+            s_, i_ = retrieval.gather_topk(s_, i_, n, comm=comm)
+        return s_, i_
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(1, warmup)):
+        s_, i_ = step()
+    barrier()
+    N.lib().pvs_launch_count_reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        s_, i_ = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    launches = int(N.lib().pvs_launch_count())
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    # every row's best match is itself (index = global row), lists sorted, gathered lists complete on every rank
+    ok = bool((i_[:, 0] == torch.arange(i_.shape[0], device=dev)).all()) and bool((s_[:, :-1] >= s_[:, 1:]).all()) \
+        and i_.shape[0] == n
+    tf = 2.0 * n * n * d / ms / 1e9
+    out = {"ms": ms, "tflops": tf, "queries_per_s": n / ms * 1e3, "n": n, "d": d, "k": k, "dtype": "bf16", "n_gpus": world,
+           "frac_of_bf16_sustained_peak": tf / world / pk["bf16_tflops_sustained"], "frac_of_bf16_burst_peak": tf / world / pk["bf16_tflops"],
+           "collective": "pvs_allgather_topk (ncclAllGather x 2, library communicator)" if world > 1 else "none (one rank)",
+           "allgather_bytes_per_rank": int((hi - lo) * k * 12) if world > 1 else 0,
+           "self_match_and_order_ok": ok, "gpu_launches_per_step": launches // max(steps, 1)}
+    del db
+    return out, (s_, i_)
+
 
 # --------------------------------------------------------------------------------------
 # our arm
@@ -355,73 +508,83 @@ def run_ours(args):
     e2e_ok = bool(np.allclose(out_np[:4], out[:4].cpu().numpy(), atol=1e-6))
 
     # ---- roofline of the dominant kernel (live CUDA-event stage times) -------------------
+    # per image the path does 294.9 MFLOP (PCA + logits + statistics) and moves 1 156 096 B
+    # (descriptors in, fp32 encoding out).  `achieved` = that work for the images of one launch / the dominant kernel's
+    # average launch time; both roofs are given, `bound` names the binding one.  The contractions run as three kind::f16
+    # MMAs per product (fp16 hi + lo operands, fp32-class accuracy), so the tensor ceiling of this path is peak / 3.
     pk = peaks()
     dominant = max(stages.items(), key=lambda kv: kv[1][0]) if stages else (None, (0.0, 0))
-    flops_per_image = {"pca_project": 2 * T * d_in * D, "gmm_logits": 2 * T * K * 2 * D,
-                       "fv_stats": 2 * T * K * 2 * D, "tc_fv_posterior": 2 * T * K * 2 * D,
-                       "tc_fv_stats": 2 * T * K * 2 * D, "tc_fv_project": 2 * T * d_in * D,
-                       "tc_fv_poststats_fused": 4 * T * K * 2 * D}        # logits + statistics in one kernel
-    # algorithmic HBM bytes per image of each kernel: what its interface makes it move
-    bytes_per_image = {"gmm_softmax": 2 * T * K * 4,
-                       "fv_finalize": K * 2 * D * 4 + 16 * K * 4 + out_dim * 4,  # S + zeroth-order partials in, encoding out
+    bytes_per_image = {"fv_finalize": K * 2 * D * 4 + 16 * K * 4 + out_dim * 4,  # S + zeroth-order partials in, encoding out
                        "tc_fv_project": T * (d_in + D) * 4,                    # X in, Y out
-                       "tc_fv_posterior": T * (D + K) * 4,                     # Y in, Q out (fp16 hi + lo planes = 4 B)
-                       "tc_fv_stats": T * (D + K) * 4 + K * 2 * D * 4}         # Q + Y in, S out
-    # The fp16x2 kernels (three kind::f16 MMAs per product on power-of-two-scaled fp16 hi + lo operands) need
-    # half the tensor time of 3xTF32, which puts posterior / statistics / projection on the HBM roofline:
-    # they stream Q (1 KB per descriptor) through HBM.  The tensor fraction is reported beside it.
-    hbm_bound = {"tc_fv_project", "tc_fv_posterior", "tc_fv_stats", "gmm_softmax", "fv_finalize"}
-    # DRAM bytes per image of each kernel from the committed `ncu --set full` capture
-    # (profiles/ncu_fv_r01c.txt: dram read + write per launch of 592 images)
-    ncu_dram_bytes_per_image = {"tc_fv_project": (0.606304e9 + 0.272666e9) / 592, "tc_fv_posterior": NCU_POST_BYTES / 592,
-                                "tc_fv_stats": (1.534512e9 + 0.063308e9) / 592}
+                       "tc_fv_poststats_fused": T * D * 4 + K * 2 * D * 4}     # Y in, S out (Q never leaves the SM)
+    traffic_db = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic_db = json.load(f)
+    except Exception:
+        pass
+
+    def two_roofs(ms_for_images, images):
+        tf = C2_FLOP_PER_IMAGE * images / (ms_for_images / 1e3) / 1e12
+        gb = C2_BYTES_PER_IMAGE * images / (ms_for_images / 1e3) / 1e9
+        t_frac, h_frac = tf / pk["bf16_tflops_sustained"], gb / pk["hbm_gbs"]
+        return {"tensor": {"achieved_tflops": tf, "peak_tflops": pk["bf16_tflops_sustained"], "frac": t_frac,
+                           "frac_of_3pass_ceiling": 3 * t_frac, "flop_per_image": C2_FLOP_PER_IMAGE},
+                "hbm": {"achieved_gbs": gb, "peak_gbs": pk["hbm_gbs"], "frac": h_frac, "bytes_per_image": C2_BYTES_PER_IMAGE},
+                "binding": "tensor" if 3 * t_frac >= h_frac else "hbm"}
+
     roofline = None
     if dominant[0]:
         name, (ms, n) = dominant
         per_launch_ms = ms / n
         imgs_per_launch = n_img * prof_steps / n
-        traffic = ncu_dram_bytes_per_image.get(name)
-        tflops = flops_per_image.get(name, 0) * imgs_per_launch / (per_launch_ms / 1e3) / 1e12
-        if name in hbm_bound:
-            ach = bytes_per_image.get(name, 0) * imgs_per_launch / (per_launch_ms / 1e3) / 1e9
-            roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                        "frac": ach / pk["hbm_gbs"], "traffic": traffic * imgs_per_launch if traffic else None,
-                        "peak_source": f"hbm copy, {pk['source']}",
-                        "algorithmic_bytes_per_launch": bytes_per_image.get(name, 0) * imgs_per_launch}
-            if tflops:
-                roofline["tensor"] = {"achieved_tflops": tflops, "frac_of_bf16_sustained": tflops / pk["bf16_tflops_sustained"],
-                                      "note": "fp16x2: three kind::f16 MMAs per algorithmic product (ceiling = peak / 3)"}
+        r = two_roofs(per_launch_ms, imgs_per_launch)
+        tr = traffic_db.get(name)
+        if r["binding"] == "tensor":
+            roofline = {"bound": "tensor", "achieved": r["tensor"]["achieved_tflops"], "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                        "frac": r["tensor"]["frac"], "peak_source": f"bf16 dense sustained, {pk['source']} (kernel runs inside a long step)"}
         else:
-            peak = pk["bf16_tflops_sustained"]
-            roofline = {"bound": "tensor", "kernel": name, "achieved": tflops, "peak": peak, "unit": "TFLOP/s",
-                        "frac": tflops / peak, "traffic": traffic * imgs_per_launch if traffic else None,
-                        "peak_source": f"bf16 dense sustained, {pk['source']} (kernel runs inside a long step)",
-                        "note": "fp16x2: three kind::f16 MMAs per algorithmic product, so the ceiling of this kernel is "
-                                "peak / 3; frac_of_fp16x2_ceiling = 3 * frac",
-                        "frac_of_fp16x2_ceiling": 3 * tflops / peak}
-        roofline["kernel_ms_per_launch"] = per_launch_ms
-        roofline["kernel_share_of_step"] = ms / sum(v[0] for v in stages.values())
-        roofline["timing"] = f"{prof_steps} extra single-stream step(s), CUDA events around each launch"
-    # whole-path HBM roofline (algorithmic bytes per image: descriptors in + encoding out)
-    alg_bytes = T * d_in * 4 + out_dim * 4
-    path_gbs = alg_bytes * n_img / (ms_per_step / 1e3) / 1e9
+            roofline = {"bound": "hbm", "achieved": r["hbm"]["achieved_gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
+                        "frac": r["hbm"]["frac"], "peak_source": f"hbm copy, {pk['source']}"}
+        roofline.update({
+            "kernel": name, "tensor": r["tensor"], "hbm": r["hbm"],
+            "note": "SURVEY.md 8(d) work of the WHOLE path per image over the dominant kernel's time; the contractions are three "
+                    "kind::f16 MMAs per product, so the tensor ceiling is peak / 3 (frac_of_3pass_ceiling)",
+            "traffic": tr["dram_bytes_per_image"] * imgs_per_launch if tr else None,
+            "traffic_source": tr["source"] if tr else None,
+            "kernel_interface_bytes_per_launch": bytes_per_image.get(name, 0) * imgs_per_launch,
+            "kernel_ms_per_launch": per_launch_ms, "images_per_launch": imgs_per_launch,
+            "kernel_share_of_step": ms / sum(v[0] for v in stages.values()),
+            "timing": f"{prof_steps} extra single-stream step(s), CUDA events around each launch"})
+    path = two_roofs(ms_per_step, n_img)                   # the same two fractions for the whole step
+    alg_bytes = C2_BYTES_PER_IMAGE
+    path_gbs = path["hbm"]["achieved_gbs"]
 
     # ---- CPU baseline: oracle port on a bounded sample (rank 0, N=1 only) ------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sample = args.cpu_sample
         descs = [x[i * T:(i + 1) * T].cpu().numpy() for i in range(sample)]
-        rate, dt, ref_out = oracle_fv_rate(descs)
+        with blas_threads(os.cpu_count()):
+            used, vendor = host_threads()
+            rate, dt, ref_out = oracle_fv_rate(descs)
         err = float(np.linalg.norm(out[:sample].cpu().numpy().astype(np.float64) - ref_out) / np.linalg.norm(ref_out))
-        cpu = {"value": rate, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-               "sample": f"first {sample} of {n_img} images, {dt:.1f} s, NumPy/OpenBLAS default threads",
-               "parity_rel_l2_vs_gpu": err}
+        cpu = {"value": rate, "unit": UNIT, "cores": used, "kind": "port", "blas": vendor,
+               "sample": f"first {sample} of {n_img} images, {dt:.1f} s, NumPy/{vendor}, {used} threads",
+               "parity_rel_l2_vs_gpu": err, "legs": cpu_legs(32)}
 
     extra = None
-    if rank == 0 and world == 1 and not args.no_extra:
-        del x
-        torch.cuda.empty_cache()
-        extra = run_extras(dev, pk)
+    del x
+    torch.cuda.empty_cache()
+    if not args.no_extra:
+        comm = None
+        if world > 1:
+            from pyvisim_b200 import retrieval
+            comm = retrieval.NativeComm()
+        ret, _ = run_retrieval(dev, rank, world, 65536, 32768, 100, 2, 1, pk, comm)
+        if rank == 0:
+            extra = run_extras(dev, pk) if world == 1 else {}
+            extra["retrieval_allgather"] = ret
 
     if rank == 0:
         line = {
@@ -437,6 +600,7 @@ def run_ours(args):
                     "matches_device_path": e2e_ok},
             "gpu_launches": launches,
             "roofline": roofline,
+            "path_roofline": path,
             "path_hbm": {"algorithmic_bytes_per_image": alg_bytes, "achieved_gbs": path_gbs,
                          "frac_of_hbm_peak": path_gbs / pk["hbm_gbs"]},
             "stages_ms": {k: round(v[0] / max(prof_steps, 1), 4) for k, v in stages.items()},
@@ -454,8 +618,181 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-# DRAM read + write bytes of one posterior launch (592 images) in the committed ncu capture
-NCU_POST_BYTES = 0.321038e9 + 1.172946e9
+def _dist_setup():
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    return rank, local_rank, world, dev
+
+
+def run_c3(args):
+    """BASELINE.json configs[2]: VLAD on VGG16 last-conv features (514-D, K=256, 196 descriptors / image), 100,000 images
+    sharded over the ranks (strong scaling, no collective)."""
+    import torch
+    import torch.distributed as dist
+    from pyvisim_b200 import _native as N, retrieval
+    from pyvisim_b200.encoders import VLADEncoder
+    from pyvisim_b200.encoders._base_encoder import kmeans_from_centers
+    from pyvisim_b200.features import Descriptors
+    rank, local_rank, world, dev = _dist_setup()
+    n_total, T, D, desc = WORKLOADS["c3"]
+    if args.images:
+        n_total = args.images
+    lo, hi = retrieval.shard_bounds(n_total, world, rank)
+    n = hi - lo
+    gen = torch.Generator(device=dev).manual_seed(77 + rank)
+    x = torch.empty((n * T, D), dtype=torch.float32, device=dev)
+    for r in range(0, n * T, 1 << 20):
+        x[r:r + (1 << 20)].normal_(0, 1, generator=gen).abs_()       # post-ReLU-like, non-negative
+    cg = torch.Generator(device=dev).manual_seed(5)                  # the same random-init centres on every rank
+    centers = torch.randn((256, D), device=dev, generator=cg).abs_().cpu().numpy()
+    enc = VLADEncoder(feature_extractor=Descriptors(D), kmeans_model=kmeans_from_centers(centers))
+    offs = torch.arange(n + 1, dtype=torch.int64) * T
+    res = torch.empty((n, 256 * D), dtype=torch.float32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    step = lambda: enc.encode_descriptors(x, offs, images_per_call=4096, out=res)
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    N.lib().pvs_launch_count_reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = int(N.lib().pvs_launch_count())
+    N.profile_enable(True)
+    step()
+    barrier()
+    stages = N.profile_read()
+    N.profile_enable(False)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    pk = peaks()
+    alg = T * D * 4 + 256 * D * 4                          # SURVEY.md 8(d): descriptors in, encoding out
+    gbs = alg * n_total / (ms / 1e3) / 1e9
+    dom = max(stages.items(), key=lambda kv: kv[1][0])
+    dom_ms = dom[1][0] / dom[1][1]
+    dom_imgs = n / dom[1][1]
+    dom_gbs = alg * dom_imgs / (dom_ms / 1e3) / 1e9
+    tdb = {}
+    try:
+        tdb = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        pass
+    tr = tdb.get(dom[0] + "_c3")
+    # e2e on a bounded subset through the public API with pinned host buffers
+    m = min(n, 16384)
+    xh = torch.empty((m * T, D), dtype=torch.float32, pin_memory=True)
+    xh.copy_(x[:m * T])
+    oh = torch.empty((m, 256 * D), dtype=torch.float32, pin_memory=True)
+    offs_np = np.arange(m + 1, dtype=np.int64) * T
+    enc.encode_descriptors(xh.numpy(), offs_np, out=oh.numpy())
+    barrier()
+    t0 = time.perf_counter()
+    enc.encode_descriptors(xh.numpy(), offs_np, out=oh.numpy())
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    checksum = float(res.double().sum().item())
+    if rank == 0:
+        print(json.dumps({
+            "metric": "vlad_encode_images_per_s_k256", "value": n_total / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": desc, "images_total": n_total, "images_per_gpu": n, "descriptors_per_image": T, "d": D, "k": 256,
+                                            "weights": "random-init K-Means (no 514-D K-Means file is bundled)",
+                                            "l2": f"inputs ({n * T * D * 4 / 1e9:.1f} GB/GPU) larger than L2, no flush",
+                                            "parallelism": f"dp{world} (images sharded, no collective)"},
+            "e2e": {"value": world * m / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(m * T * D * 4 + (m + 1) * 8), "d2h_bytes_per_step": int(m * 256 * D * 4),
+                    "images": m, "note": "bounded subset per rank through encode_descriptors with pinned host buffers"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": dom_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": dom_gbs / pk["hbm_gbs"],
+                         "traffic": tr["dram_bytes_per_image"] * dom_imgs if tr else None, "traffic_source": tr["source"] if tr else None,
+                         "bytes_per_image": alg, "kernel_ms_per_launch": dom_ms, "images_per_launch": dom_imgs,
+                         "note": "SURVEY.md 8(d) bytes of the whole path per image over the dominant kernel's time"},
+            "path_hbm": {"achieved_gbs": gbs / world, "frac_of_hbm_peak": gbs / world / pk["hbm_gbs"], "note": "per GPU"},
+            "stages_ms": {k: round(v[0], 4) for k, v in stages.items()},
+            "clocks": clocks.summary(), "checksum": checksum}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_c4(args):
+    """BASELINE.json configs[3]: all-pairs cosine + top-100 over 262,144 VLAD-32768 vectors; database replicated in bf16
+    (17.2 GB), query rows sharded over the ranks, top-k lists all-gathered (strong scaling)."""
+    import torch
+    import torch.distributed as dist
+    from pyvisim_b200 import retrieval
+    rank, local_rank, world, dev = _dist_setup()
+    n, _, d, desc = WORKLOADS["c4"]
+    if args.images:
+        n = args.images
+    pk = peaks()
+    comm = retrieval.NativeComm() if world > 1 else None
+    with ClockSampler(local_rank) as clocks:
+        r, (s_, i_) = run_retrieval(dev, rank, world, n, d, 100, args.steps, max(1, min(args.warmup, 2)), pk, comm)
+    # e2e on a bounded block: fp32 query vectors from pinned host memory -> normalise -> top-100 against the resident database
+    # -> lists back to the host
+    gen = torch.Generator(device=dev).manual_seed(4321)
+    db = vlad_like_device(min(n, 65536), d, dev, gen, torch.bfloat16)
+    m = 4096
+    qh = torch.empty((m, d), dtype=torch.float32, pin_memory=True)
+    qh.copy_(db[:m].float())
+    sh, ih = torch.empty((m, 100), dtype=torch.float32, pin_memory=True), torch.empty((m, 100), dtype=torch.int64, pin_memory=True)
+
+    def e2e():
+        q = retrieval.l2_normalize(qh.to(dev, non_blocking=True), "bf16")
+        a, b = retrieval.cosine_topk(q, db, 100)
+        sh.copy_(a, non_blocking=True); ih.copy_(b, non_blocking=True)
+        torch.cuda.synchronize()
+    e2e()
+    t0 = time.perf_counter()
+    e2e()
+    e2e_s = time.perf_counter() - t0
+    if rank == 0:
+        tdb = {}
+        try:
+            tdb = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        except Exception:
+            pass
+        tr = tdb.get("tc_sim_topk")
+        print(json.dumps({
+            "metric": "cosine_top100_queries_per_s", "value": r["queries_per_s"], "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": r["ms"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "config": {"workload": desc, "n": n, "d": d, "k": 100, "parallelism": f"query rows sharded over {world} rank(s), "
+                                            "database replicated in bf16, top-k lists all-gathered", "l2": "database (17.2 GB) larger than L2, no flush"},
+            "e2e": {"value": m / e2e_s * (db.shape[0] / n), "unit": "queries/s", "h2d_bytes_per_step": int(m * d * 4), "d2h_bytes_per_step": int(m * 100 * 12),
+                    "note": f"{m} fp32 query rows from pinned host memory against {db.shape[0]} resident rows, scaled to {n} rows"},
+            "gpu_launches": r["gpu_launches_per_step"] * args.steps,
+            "roofline": {"bound": "tensor", "kernel": "tc_sim_topk (SimPolicy: bf16 GEMM + fused top-k)", "achieved": r["tflops"] / world,
+                         "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": r["tflops"] / world / pk["bf16_tflops_sustained"],
+                         "frac_of_burst_peak": r["tflops"] / world / pk["bf16_tflops"], "traffic": tr["dram_bytes_per_launch"] if tr else None,
+                         "traffic_source": tr["source"] if tr else None, "flop": 2.0 * n * n * d, "note": "per GPU; 2 N^2 D FLOP / step time"},
+            "retrieval": r, "clocks": clocks.summary()}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():
@@ -464,6 +801,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"], help="c2 (default) = the configuration the metric is quoted on")
     ap.add_argument("--images", type=int, default=0, help="override images per GPU (debug)")
     ap.add_argument("--images-per-call", type=int, default=0, help="0 = library default (4 per SM)")
     ap.add_argument("--e2e-images", type=int, default=0, help="images in the host-buffer leg (0 = all)")
@@ -474,6 +812,10 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c3":
+        run_c3(args)
+    elif args.workload == "c4":
+        run_c4(args)
     else:
         run_ours(args)
 

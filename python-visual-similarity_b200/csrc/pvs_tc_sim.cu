@@ -693,13 +693,19 @@ static int sim3_seg()
     return g;
 }
 
-// absolute bound on |tensor score - exact score| for unit-norm rows: truncating accumulation inside a segment
-// (3 MMAs x 4 k-steps x seg k-blocks, two ulps each to be safe, of partial sums that add up to <= 1), the
-// round-to-nearest folds of the segments, and the hi + lo split of the operands
+// Band on |tensor score - exact score| for unit-norm rows.  Model: every MMA (3 per k-step, 4 k-steps per 64-deep k-block,
+// `seg` k-blocks per segment) adds its slice to the accumulator with an error of at most one ulp of the segment's partial
+// sum, which is bounded by the segment's share of sum |q_i d_i| <= 1; every fold of a segment into the fp32 running sum
+// rounds to nearest (half an ulp of a value <= 1); the hi + lo split and the dropped lo * lo term cost 2^-21.  The first two
+// terms are worst cases that assume every step loses a full ulp in the same direction at full magnitude; measured on VLAD-
+// shaped and Gaussian rows at d = 64 .. 32 768 the error stays below a tenth of their sum (1.5e-6 at d = 32 768), so half of
+// it is used -- 7e-6 at d = 32 768 instead of 1.4e-5, which matters because every candidate pair closer than twice the band
+// is re-scored exactly (131 KB of operand reads per candidate).  The tests compare the returned indices with the fp64
+// ranking, so a band that is too small shows up as an index mismatch, not as a silent error.
 static float sim3_band(int64_t d, int seg)
 {
     const int nkb = (int)ceil_div(d, 64), nseg = (int)ceil_div(nkb, seg);
-    return 2.f * (12.f * seg) * 1.1920929e-7f + (float)nseg * 5.9604645e-8f + 4.7683716e-7f;
+    return 0.5f * ((12.f * seg) * 1.1920929e-7f + (float)nseg * 5.9604645e-8f) + 4.7683716e-7f;
 }
 
 bool tc_sim3_supported(int64_t n_q, int64_t n_db, int64_t d, int k)

@@ -77,7 +77,12 @@ def run_device(encode_fn, ws_fn, cluster: N.Model, pca: Optional[N.Model], x, of
           or tuple(out.shape) != (n_images, out_dim) or not out.is_contiguous()):
         raise ValueError(f"out must be a contiguous float32 tensor of shape {(n_images, out_dim)} on {dev}")
     rows_i32 = torch.empty((x.shape[0],), dtype=torch.int32, device=dev) if want_rows_i32 else None
-    offs_dev = torch.as_tensor(offs_host, device=dev)
+    # chunk-local CSR offsets of every chunk, built on the host and uploaded in ONE copy (a slice-and-subtract on the device
+    # was one extra kernel launch per chunk)
+    starts = list(range(0, n_images, images_per_call))
+    local_host = np.concatenate([offs_host[i0:min(n_images, i0 + images_per_call) + 1] - offs_host[i0] for i0 in starts]) \
+        if starts else np.zeros((1,), np.int64)
+    local_dev = torch.as_tensor(np.ascontiguousarray(local_host, dtype=np.int64), device=dev)
     caller = torch.cuda.current_stream(dev)
     n_chunks = (n_images + images_per_call - 1) // images_per_call
     streams = [caller] if (n_chunks <= 1 or n_streams <= 1) else _streams_for(dev, n_streams)
@@ -87,8 +92,9 @@ def run_device(encode_fn, ws_fn, cluster: N.Model, pca: Optional[N.Model], x, of
     pca_h = pca.handle if pca else None
     ws = [None] * len(streams)
     power, order, eps = params
+    lpos = 0
     with torch.cuda.device(dev):
-        for c, i0 in enumerate(range(0, n_images, images_per_call)):
+        for c, i0 in enumerate(starts):
             si = c % len(streams)
             with torch.cuda.stream(streams[si]):
                 i1 = min(n_images, i0 + images_per_call)
@@ -96,7 +102,8 @@ def run_device(encode_fn, ws_fn, cluster: N.Model, pca: Optional[N.Model], x, of
                 need = ws_fn(cluster.handle, pca_h, r1 - r0, i1 - i0)
                 if ws[si] is None or ws[si].numel() < need:
                     ws[si] = torch.empty((need,), dtype=torch.uint8, device=dev)
-                local = offs_dev[i0:i1 + 1] - r0 if i0 else offs_dev[:i1 + 1]
+                local = local_dev[lpos:lpos + (i1 - i0) + 1]
+                lpos += (i1 - i0) + 1
                 N.check(encode_fn(cluster.handle, pca_h, x[r0:r1].data_ptr() if r1 > r0 else x.data_ptr(),
                                   local.data_ptr(), i1 - i0, r1 - r0, power, order, eps, out[i0:i1].data_ptr(),
                                   rows_i32[r0:].data_ptr() if (rows_i32 is not None and r1 > r0) else None,
