@@ -318,17 +318,28 @@ def run_extras(dev, pk):
     ref = O.similarity_score(O.vlad_encode([d1], cen), O.vlad_encode([d2], cen))
     cpu_s = time.perf_counter() - t0
     _, lab = enc.encode_descriptors([d1, d2], return_labels=True)
+    lab = np.asarray(lab)
     xs = np.vstack([d1, d2])
-    gold = O.kmeans_predict(xs, cen)
+    gold = O.kmeans_predict(xs, cen)                      # fp32, this host's BLAS: sub-1e-6 ties fall by its rounding noise
+    s64 = (cen.astype(np.float64) ** 2).sum(1)[None, :] - 2.0 * (xs.astype(np.float64) @ cen.astype(np.float64).T)
+    exact = s64.argmin(1).astype(np.int32)                # what the device resolves near-ties to (fp64 re-evaluation)
     bad = np.flatnonzero(lab != gold)
-    gaps = []
-    if bad.size:
-        sc = O.kmeans_scores(xs[bad], cen)
-        gaps = (np.abs(sc[np.arange(bad.size), lab[bad]] - sc[np.arange(bad.size), gold[bad]]) / np.abs(sc).max(axis=1)).tolist()
+    gaps = (np.abs(s64[bad, lab[bad]] - s64[bad, gold[bad]]) / np.abs(s64[bad]).max(axis=1)).tolist()
+
+    def vlad_from_labels(x, lb):                          # vlad.py:98-111 with given labels (oracle arithmetic)
+        v = np.zeros((256, 128), dtype=np.float32)
+        np.add.at(v, lb, x - cen[lb])
+        return (v / (np.linalg.norm(v, axis=1, ord=2, keepdims=True) + 1e-9)).flatten()
+    ref_exact = float(np.asarray(O.similarity_score(vlad_from_labels(d1, exact[:2000])[None], vlad_from_labels(d2, exact[2000:])[None])).ravel()[0])
+    sc = float(np.asarray(score).ravel()[0])
     out["quickstart_vlad_similarity_score"] = {"latency_ms_median": 1e3 * float(np.median(lat)), "latency_ms_min": 1e3 * float(np.min(lat)),
-                                               "cpu_oracle_ms": 1e3 * cpu_s, "score": float(np.asarray(score).ravel()[0]),
-                                               "abs_diff_vs_oracle": float(abs(np.asarray(score).ravel()[0] - np.asarray(ref).ravel()[0])),
-                                               "label_flips_vs_fp32_oracle": int(bad.size), "rel_score_gap_of_flips": gaps,
+                                               "cpu_oracle_ms": 1e3 * cpu_s, "score": sc,
+                                               "rel_diff_vs_oracle_with_exact_labels": abs(sc - ref_exact) / abs(ref_exact),
+                                               "label_mismatches_vs_exact_argmin": int((lab != exact).sum()),
+                                               "rel_diff_vs_fp32_oracle": float(abs(sc - np.asarray(ref).ravel()[0]) / abs(np.asarray(ref).ravel()[0])),
+                                               "label_mismatches_vs_fp32_oracle": int(bad.size), "rel_score_gap_of_those": gaps,
+                                               "note": "near-ties below 1e-6 are resolved by exact (fp64) scores on the device; the fp32 reference "
+                                                       "resolves them by the rounding noise of its BLAS kernel",
                                                "descriptors": [2000, 1900]}
     del enc
     return out
@@ -714,7 +725,7 @@ def run_c3(args):
         t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    checksum = float(res.double().sum().item())
+    checksum = float(sum(res[r:r + 4096].double().sum().item() for r in range(0, n, 4096)))
     if rank == 0:
         print(json.dumps({
             "metric": "vlad_encode_images_per_s_k256", "value": n_total / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,

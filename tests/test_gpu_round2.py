@@ -219,3 +219,51 @@ def test_fv_fused_default_full_c2_batch(api):
     print(f"\n[fv c2 full] tensor path vs CUDA-core path: max {rel:.2e}, median {per_image.median().item():.2e}; vs fp64 oracle on {pick}: "
           f"tensor {max(e_f):.2e}, CUDA cores {max(e_u):.2e}")
     assert max(e_f) <= 1e-4 and max(e_u) <= 1e-4, (e_f, e_u)
+
+
+def test_vlad_near_ties_resolved_exactly(api):
+    """BASELINE.json configs[0] (README quick start: two images of ~2 000 RootSIFT-128 descriptors).  Hard-assignment
+    near-ties -- score gaps at the 1e-7 level, below the accuracy of any fp32 evaluation: the reference's own answer
+    depends on the summation order of its BLAS kernel -- are re-evaluated in fp64 on the device, so the labels equal
+    the EXACT arg-min on every row, every mismatch with the fp32 oracle is a sub-1e-6 tie, and the similarity score
+    equals the one computed from the exact labels to 1e-6."""
+    from pyvisim_b200.encoders._base_encoder import kmeans_from_centers
+    rng = np.random.default_rng(0)
+
+    def rootsift_like(t):
+        a = np.abs(rng.standard_normal((t, 128))).astype(np.float32)
+        a /= a.sum(axis=1, keepdims=True) + 1e-7
+        return np.sqrt(a)
+
+    def exact_labels(x, c):
+        x64, c64 = x.astype(np.float64), c.astype(np.float64)
+        s = (c64 * c64).sum(1)[None, :] - 2.0 * (x64 @ c64.T)
+        return s.argmin(1).astype(np.int32), s
+
+    d1, d2 = rootsift_like(2000), rootsift_like(1900)
+    xs = np.vstack([d1, d2])
+    cen = xs[rng.choice(3900, 256, replace=False)]
+    cen2 = cen.copy()                                       # 128 near-duplicate centres: every row has a near-tie
+    cen2[128:] = cen[:128] * np.float32(1 + 3e-7)
+    for c in (cen, cen2):
+        enc = api.enc.VLADEncoder(feature_extractor=api.feat.Descriptors(128), kmeans_model=kmeans_from_centers(c))
+        _, lab = enc.encode_descriptors([d1, d2], return_labels=True)
+        lab = np.asarray(lab)
+        gold64, s64 = exact_labels(xs, c)
+        assert np.array_equal(lab, gold64), f"rows {np.flatnonzero(lab != gold64)} differ from the exact arg-min"
+        gold32 = O.kmeans_predict(xs, c)                    # fp32, host BLAS: may differ, but only at near-ties
+        bad = np.flatnonzero(lab != gold32)
+        gap = np.abs(s64[bad, lab[bad]] - s64[bad, gold32[bad]]) / np.abs(s64[bad]).max(axis=1)
+        assert np.all(gap < 1e-6), gap
+    enc = api.enc.VLADEncoder(feature_extractor=api.feat.Descriptors(128), kmeans_model=kmeans_from_centers(cen))
+    score = float(np.asarray(enc.similarity_score([d1], [d2])).ravel()[0])
+
+    def vlad_from_labels(x, lab):                           # vlad.py:98-111 (as oracle/pvs_oracle.py) with the given labels
+        v = np.zeros((256, 128), dtype=np.float32)
+        np.add.at(v, lab, x - cen[lab])
+        v = O._signed_power(v, 1)
+        return (v / (np.linalg.norm(v, axis=1, ord=2, keepdims=True) + 1e-9)).flatten()
+
+    g1, g2 = exact_labels(d1, cen)[0], exact_labels(d2, cen)[0]
+    ref = float(np.asarray(O.similarity_score(vlad_from_labels(d1, g1)[None], vlad_from_labels(d2, g2)[None])).ravel()[0])
+    assert abs(score - ref) <= 1e-5 * abs(ref), (score, ref)
