@@ -57,6 +57,18 @@ def host_threads():
     return os.cpu_count(), "unknown"
 
 
+class stdout_to_stderr:
+    """NCCL prints its version banner on stdout when a communicator is created; the contract is ONE JSON line there."""
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 class blas_threads:
     """All host cores for the CPU legs (torchrun exports OMP_NUM_THREADS=1, which would cripple the reference arm), or 1."""
     def __init__(self, n):
@@ -427,7 +439,9 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        with stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
 
     n_img, T, d_in, desc = WORKLOADS["c2"]
     if args.images:
@@ -591,7 +605,9 @@ def run_ours(args):
         comm = None
         if world > 1:
             from pyvisim_b200 import retrieval
-            comm = retrieval.NativeComm()
+            with stdout_to_stderr():
+                comm = retrieval.NativeComm()
+                torch.cuda.synchronize()
         ret, _ = run_retrieval(dev, rank, world, 65536, 32768, 100, 2, 1, pk, comm)
         if rank == 0:
             extra = run_extras(dev, pk) if world == 1 else {}
@@ -638,7 +654,9 @@ def _dist_setup():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        with stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
     return rank, local_rank, world, dev
 
 
@@ -760,7 +778,11 @@ def run_c4(args):
     if args.images:
         n = args.images
     pk = peaks()
-    comm = retrieval.NativeComm() if world > 1 else None
+    comm = None
+    if world > 1:
+        with stdout_to_stderr():
+            comm = retrieval.NativeComm()
+            torch.cuda.synchronize()
     with ClockSampler(local_rank) as clocks:
         r, (s_, i_) = run_retrieval(dev, rank, world, n, d, 100, args.steps, max(1, min(args.warmup, 2)), pk, comm)
     # e2e on a bounded block: fp32 query vectors from pinned host memory -> normalise -> top-100 against the resident database

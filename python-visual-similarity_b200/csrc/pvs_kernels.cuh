@@ -83,8 +83,9 @@ int tc_fv_posterior(const TcFvPlan& pl, const pvs_model* g, const float* y, int6
                     bool fallback_only = false);
 int tc_fv_poststats_fused_cluster(const TcFvPlan& pl, const pvs_model* g, const float* y, const int64_t* offsets, int64_t n_images,
                                   cudaStream_t st);
-// PVS_FV_FUSED: posterior + statistics in one kernel: 2 (default) = 2-CTA clusters that split the components, statistics
-// folded in segments (pvs_tc_fvfused2.cu); 1 = one CTA per SM (pvs_tc_fvfused.cu); 0 = the two unfused kernels
+// PVS_FV_FUSED: 0 (default) = posterior kernel + statistics kernel, statistics folded in segments (pvs_tc_fv.cu);
+// 2 = both in one kernel, 2-CTA clusters that split the components, same fold (pvs_tc_fvfused2.cu); 1 = one CTA per SM
+// (pvs_tc_fvfused.cu, whole-image accumulation: test reference only)
 int tc_fv_fused_mode();
 inline bool tc_fv_fused_enabled() { return tc_fv_fused_mode() != 0; }
 int tc_fv_poststats_fused(const TcFvPlan& pl, const pvs_model* g, const float* y, const int64_t* offsets, int64_t n_images,

@@ -317,6 +317,8 @@ struct Stats16Params {
     StatsParams b;
     const float* rinv;                        // [rows + 16, 4]: per-descriptor softmax normaliser (slot 0 of 16 bytes)
     const int* flag;                          // != 0: operands out of fp16 range -> this kernel does nothing
+    const int* smax;                          // segments per image slot: max over the images of ceil(k-blocks / segk), >= 1 (device)
+    int segk;                                 // k-blocks (16 descriptors each) per statistics segment
     float sc_y, un1, un2;                     // 2^-e, 2^(e-14), 2^(2e-14)
 };
 
@@ -332,7 +334,14 @@ struct Stats16Params {
 struct Stats16Policy {
     using Params = Stats16Params;
     struct EpiState { float2 s0; };
-    struct Tile { int nkb; int t; int64_t img, r0; };
+    // A tile of the skeleton is one SEGMENT of an image: `segk` k-blocks accumulated from zero in one of the two TMEM
+    // accumulators and folded into the image's S rows (global memory, L2-resident, fp32 round-to-nearest adds) by the
+    // epilogue warps while the next segment is being multiplied into the other accumulator.  tcgen05.mma adds every K = 16
+    // slice to the accumulator with truncation; accumulated over a whole 2 000-descriptor image that bias, amplified by the
+    // cancellation in d_sigma, put 46 of the 8 189 images of the C2 batch 1e-4 .. 2.6e-4 off the fp64 result.
+    // Every image gets *p.smax consecutive tiles on ONE CTA (the folds of an image are ordered: same threads, same
+    // addresses); tiles past the image's last segment are empty and skipped.
+    struct Tile { int nkb; int t; int64_t img, r0; int kb0; bool first, last, skip; };
     static constexpr bool BF16 = false, F16 = true, A_MN = true, B_MN = true, EPI_READS_STAGES = true, MANUAL = true;
     static constexpr bool TMA_OWN_BARRIER = true;
     static constexpr int KT = 16;             // descriptors per stage = one K=16 step
@@ -347,19 +356,35 @@ struct Stats16Policy {
     __device__ static bool enabled(const Params& p) { return *p.flag == 0; }
     __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.qh_map); tma_prefetch_desc(&p.ql_map); tma_prefetch_desc(&p.y_map); }
     __device__ static void init_stage(uint8_t* extra) { mbar_init(reinterpret_cast<uint64_t*>(extra + BAR_OFF), 1); }
-    __device__ static int num_tiles(const Params& p) { return (int)p.b.n_images; }
-    __device__ static int tile_at(const Params&, int it, int n) { return strided_tile(it, n); }
+    __device__ static int num_tiles(const Params& p) { return (int)p.b.n_images * *p.smax; }
+    __device__ static int tile_at(const Params& p, int it, int)
+    {
+        const int smax = *p.smax;
+        const long long img = (long long)blockIdx.x + (long long)(it / smax) * gridDim.x;
+        return img < p.b.n_images ? (int)(img * smax + it % smax) : -1;
+    }
     __device__ static Tile tile(const Params& p, int i)
     {
-        const int64_t r0 = p.b.offsets[i];
-        const int t = (int)(p.b.offsets[i + 1] - r0);
-        return {(t + KT - 1) / KT, t, (int64_t)i, r0};
+        const int smax = *p.smax;
+        const int64_t img = i / smax;
+        const int seg = i - (int)img * smax;
+        const int64_t r0 = p.b.offsets[img];
+        const int t = (int)(p.b.offsets[img + 1] - r0);
+        const int total = (t + KT - 1) / KT, kb0 = seg * p.segk;
+        const int left = total - kb0;
+        Tile tl;
+        tl.nkb = left <= 0 ? 0 : (left < p.segk ? left : p.segk);
+        tl.t = t; tl.img = img; tl.r0 = r0; tl.kb0 = kb0;
+        tl.first = seg == 0;
+        tl.last = left <= p.segk;                          // also true for an empty image (its only tile writes NaN)
+        tl.skip = seg > 0 && left <= 0;
+        return tl;
     }
     __device__ static void load(const Params& p, const Tile& t, int kb, uint8_t*, uint8_t*, uint8_t* b_hi, uint8_t* b_lo, uint64_t*)
     {
         uint8_t* extra = b_lo + B_BYTES;
         uint64_t* bar = reinterpret_cast<uint64_t*>(extra + BAR_OFF);
-        const int row = (int)(t.r0 + (int64_t)kb * KT);
+        const int row = (int)(t.r0 + (int64_t)(t.kb0 + kb) * KT);
         mbar_expect_tx(bar, TMA_BYTES);
         bulk_load_1d(extra + R_OFF, p.rinv + (int64_t)row * 4, KT * 16, bar);     // (the array is padded by 16 rows)
 #pragma unroll
@@ -379,7 +404,7 @@ struct Stats16Policy {
         uint8_t* extra = b_lo + B_BYTES;
         mbar_wait(reinterpret_cast<uint64_t*>(extra + BAR_OFF), (ps.uses / STAGES) & 1u);
         ++ps.uses;
-        const int valid = t.t - kb * KT;                   // rows of this stage that belong to the image
+        const int valid = t.t - (t.kb0 + kb) * KT;         // rows of this stage that belong to the image
         // a lane owns 8 dims of one row: row r = 4 pw + lane / 8, dims [8 (lane % 8), +8)
         const int r = pw * 4 + (lane >> 3);
         const int blk = (lane & 7) >> 2, c0 = (lane & 3) * 2;
@@ -413,7 +438,7 @@ struct Stats16Policy {
         }
     }
     __device__ static void epi_init(const Params&, uint8_t*, int) {}
-    __device__ static void epi_begin(const Params&, const Tile&, EpiState& st, int, int) { st.s0 = make_float2(0.f, 0.f); }
+    __device__ static void epi_begin(const Params&, const Tile& t, EpiState& st, int, int) { if (t.first) st.s0 = make_float2(0.f, 0.f); }
     // zeroth-order sums: thread (quarter, lane) owns components 2e, 2e + 1 (e = 32 quarter + lane) = one
     // 4-byte word of every row in column block `quarter`; a warp reads one 128-B row per instruction
     __device__ static void consume(const Params&, const Tile&, int, uint8_t*, uint8_t*, uint8_t* b_hi, uint8_t* b_lo,
@@ -442,23 +467,36 @@ struct Stats16Policy {
     __device__ static void epilogue(const Params& p, const Tile& t, uint32_t tmem, int quarter, int lane, uint8_t*,
                                     EpiState& st)
     {
+        if (t.skip) return;                                // past the image's last segment
         const int e = quarter * 32 + lane;                 // operand row: [0,64) = y'^2, [64,128) = y'
         const int n = e < FV_D ? FV_D + e : e - FV_D;      // column in the [ s1 | s2 ] layout
-        float* Simg = p.b.S + t.img * (int64_t)FV_K * FV_2D;
-        const float scale = (e < FV_D ? p.un2 : p.un1) / (float)t.t;   // undo the operand scales; T == 0 -> NaN below
-        const bool empty = t.nkb == 0;
+        float* Simg = p.b.S + t.img * (int64_t)FV_K * FV_2D + n;
+        const float scale = t.last ? (e < FV_D ? p.un2 : p.un1) / (float)t.t : 1.f;   // undo the operand scales; T == 0 -> NaN below
+        const bool empty = t.t == 0;
         const float nanv = __int_as_float(0x7fc00000);
         // raw zeroth-order sums go into partial slot 0 (the other slots stay zero, fv_finalize adds them up and divides by T)
-        reinterpret_cast<float2*>(p.b.s0part + t.img * (int64_t)(TC_FV_S0_PARTS * FV_K))[e] =
-            make_float2(st.s0.x * (1.f / 16384.f), st.s0.y * (1.f / 16384.f));
+        if (t.last)
+            reinterpret_cast<float2*>(p.b.s0part + t.img * (int64_t)(TC_FV_S0_PARTS * FV_K))[e] =
+                make_float2(st.s0.x * (1.f / 16384.f), st.s0.y * (1.f / 16384.f));
+        // fold: 64 columns per round trip to L2 (the running sums of the earlier segments come back while the accumulator
+        // is read).  Measured alternatives: 16-column slices between the stages of the next segment (the epilogue warps also
+        // have to release every stage after reading it for the zeroth-order sums) made the kernel slower, 6.0 -> 6.7 ms.
 #pragma unroll 1
-        for (int c = 0; c < FV_K; c += 32) {
-            float v[32];
+        for (int c = 0; c < FV_K; c += 64) {
+            float v[64], r[64];
+            if (!t.first) {
+#pragma unroll
+                for (int jj = 0; jj < 64; ++jj) r[jj] = __ldcg(Simg + (int64_t)(c + jj) * FV_2D);
+            }
             __syncwarp();
-            tmem_ld32(tmem + c, v);
+            tmem_ld32(tmem + c, *reinterpret_cast<float (*)[32]>(v));
+            tmem_ld32(tmem + c + 32, *reinterpret_cast<float (*)[32]>(v + 32));
             tmem_ld_wait();
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) Simg[(int64_t)(c + jj) * FV_2D + n] = empty ? nanv : v[jj] * scale;
+            for (int jj = 0; jj < 64; ++jj) {
+                const float x = t.first ? v[jj] : v[jj] + r[jj];
+                __stcg(Simg + (int64_t)(c + jj) * FV_2D, empty ? nanv : x * scale);
+            }
         }
     }
 };
@@ -1184,6 +1222,26 @@ int tc_fv_posterior(const TcFvPlan& pl, const pvs_model* g, const float* y, int6
     return tc2::launch_tc2<tc2::PostPairPolicy>(p, p.m_blocks, st);
 }
 
+// segments per image slot of the fp16x2 statistics kernel: max over the images of ceil(k-blocks / segk), at least 1
+__global__ void fv_smax_kernel(const int64_t* __restrict__ offsets, int64_t n_images, int segk, int* __restrict__ smax)
+{
+    int m = 1;
+    for (int64_t i = threadIdx.x; i < n_images; i += blockDim.x) {
+        const int t = (int)(offsets[i + 1] - offsets[i]);
+        const int nkb = (t + Stats16Policy::KT - 1) / Stats16Policy::KT;
+        m = max(m, (nkb + segk - 1) / segk);
+    }
+    m = __reduce_max_sync(0xffffffffu, m);
+    __shared__ int part[32];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 1;
+        m = __reduce_max_sync(0xffffffffu, m);
+        if (threadIdx.x == 0) *smax = m;
+    }
+}
+
 int tc_fv_stats(const TcFvPlan& pl, const pvs_model* g, const float* y, const int64_t* offsets, int64_t n_images, cudaStream_t st,
                 bool fallback_only)
 {
@@ -1200,7 +1258,15 @@ int tc_fv_stats(const TcFvPlan& pl, const pvs_model* g, const float* y, const in
     if ((rc = make_tmap_2d(&h.qh_map, pl.q, true, rows, FV_K, FV_K, 64, Stats16Policy::KT))) return rc;
     if ((rc = make_tmap_2d(&h.ql_map, (const __half*)pl.q + (size_t)rows * FV_K, true, rows, FV_K, FV_K, 64, Stats16Policy::KT))) return rc;
     if ((rc = make_tmap_2d(&h.y_map, y, false, rows, FV_D, FV_D, 32, Stats16Policy::KT))) return rc;
-    if (!fallback_only && (rc = launch_tc<Stats16Policy>(h, (int)n_images, st))) return rc;
+    if (!fallback_only) {
+        int seg = 2;                                           // 128-descriptor tiles per segment, as in the fused kernel
+        if (const char* e = getenv("PVS_FV_SEG")) { const int v = atoi(e); if (v >= 1) seg = v; }
+        h.segk = seg * 8;
+        h.smax = pl.flag + 1;                                  // the int behind the range flag (cleared by tc_fv_begin)
+        fv_smax_kernel<<<1, 1024, 0, st>>>(offsets, n_images, h.segk, pl.flag + 1);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if ((rc = launch_tc<Stats16Policy>(h, (int)n_images, st))) return rc;
+    }
     return launch_tc<StatsGatedPolicy>(h, (int)n_images, st);
 }
 

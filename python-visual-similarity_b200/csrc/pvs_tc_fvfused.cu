@@ -491,14 +491,16 @@ __global__ void __launch_bounds__(THREADS, 1) kernel(const __grid_constant__ Par
 
 using namespace tc;
 
-// PVS_FV_FUSED selects the posterior + statistics kernel: default 2 = pvs_tc_fvfused2.cu (2-CTA clusters, statistics folded
-// in segments: the only path that keeps EVERY image of the full C2 batch inside the 1e-4 bar); 1 = this file's single-CTA
-// kernel; 0 = the two unfused kernels.  The non-default ones accumulate the statistics of a whole image in the tensor core
-// (0.6 % of the C2 images end up 1e-4 .. 2.8e-4 off) and stay as parity references for the tests.
+// PVS_FV_FUSED selects how posterior + statistics run.  Default 0: the posterior kernel and the statistics kernel
+// (pvs_tc_fv.cu), the statistics folded in segments of 256 descriptors -- on the full C2 batch the fastest variant that
+// keeps EVERY image inside the 1e-4 bar (658 k images/s, worst image 8.9e-5; table in DESIGN.md).  2: the 2-CTA cluster
+// kernel of pvs_tc_fvfused2.cu (Q never leaves the SM; same segment fold, but the fold sits on its softmax chain: 560-620 k
+// images/s, worst image 9.9e-5).  1: this file's single-CTA kernel (statistics of a whole image accumulated in the tensor
+// core: 712 k images/s but 58 of the 8 189 images 1e-4 .. 2.8e-4 off; kept as a reference for the tests only).
 int tc_fv_fused_mode()
 {
     const char* e = getenv("PVS_FV_FUSED");
-    return !e ? 2 : (e[0] == '0' ? 0 : e[0] == '1' ? 1 : 2);
+    return !e ? 0 : (e[0] == '1' ? 1 : e[0] == '2' ? 2 : 0);
 }
 
 int tc_fv_poststats_fused(const TcFvPlan& pl, const pvs_model* g, const float* y, const int64_t* offsets, int64_t n_images,

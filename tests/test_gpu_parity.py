@@ -519,8 +519,8 @@ def test_fv_tensor_path_ragged_batch_vs_oracle(api):
     assert max(errs) <= 1e-4, errs
 
 
-# fused kernels under test: PVS_FV_FUSED=1 (one CTA per SM), =2 (the default: 2-CTA clusters that split the components,
-# statistics folded in segments)
+# fused kernels under test: PVS_FV_FUSED=1 (one CTA per SM), =2 (2-CTA clusters that split the components, statistics folded
+# in segments like the default two-kernel path)
 FUSED_MODES = ["1", "2"]
 
 
@@ -565,7 +565,7 @@ def test_fv_fp16x2_path_and_range_guard(api):
 
 @pytest.mark.parametrize("mode", FUSED_MODES)
 def test_fv_fused_posterior_statistics_kernel(api, mode):
-    """Fused kernels (PVS_FV_FUSED=2, the default, and =1: posterior + statistics in one kernel, the [y^2|y] tile serving as
+    """Fused kernels (PVS_FV_FUSED=2 and =1: posterior + statistics in one kernel, the [y^2|y] tile serving as
     K-major operand of the logit MMA and as MN-major operand of the statistics MMA): ragged images incl.
     T = 1, 127, 128, 129 vs the fp64 oracle and vs the default (unfused) path."""
     import os

@@ -35,7 +35,7 @@ def run(tag):
     print(json.dumps({"variant": tag, "ms": round(e0.elapsed_time(e1) / 3, 3), "images_per_s": round(n / (e0.elapsed_time(e1) / 3) * 1e3),
                       "err_max": float(per.max()), "err_median": float(per.median()), "n_gt_1e-4": int((per > 1e-4).sum()),
                       "n_gt_5e-5": int((per > 5e-5).sum()), "worst": per.topk(3).indices.tolist()}), flush=True)
-for mode, segs in (("2", ("1", "2", "4", "8", "16")), ("0", ("",)), ("1", ("",))):
+for mode, segs in (("0", ("1", "2", "4", "16")), ("2", ("2", "4")), ("1", ("",))):
     for seg in segs:
         os.environ["PVS_FV_FUSED"] = mode
         if seg: os.environ["PVS_FV_SEG"] = seg
