@@ -541,6 +541,8 @@ def run_ours(args):
     dominant = max(stages.items(), key=lambda kv: kv[1][0]) if stages else (None, (0.0, 0))
     bytes_per_image = {"fv_finalize": K * 2 * D * 4 + 16 * K * 4 + out_dim * 4,  # S + zeroth-order partials in, encoding out
                        "tc_fv_project": T * (d_in + D) * 4,                    # X in, Y out
+                       "tc_fv_posterior": T * (D + K) * 4,                     # Y in, Q out (fp16 hi + lo planes = 4 B)
+                       "tc_fv_stats": T * (D + K) * 4 + K * 2 * D * 4,         # Q + Y in, S out
                        "tc_fv_poststats_fused": T * D * 4 + K * 2 * D * 4}     # Y in, S out (Q never leaves the SM)
     traffic_db = {}
     try:
