@@ -204,9 +204,11 @@ struct AssignPolicy {
         const float* c2 = reinterpret_cast<const float*>(scratch);
         const int64_t row = (int64_t)t.mb * 256 + rank * 128 + quarter * 32 + lane;
         const float m2 = H_ ? p.neg2s : -2.f;                  // fp16x2: the accumulator holds x.c / 4^e
-        // best and runner-up (strict <: the lowest index wins exact ties, like sklearn's scan)
+        // best (strict <: the lowest index wins exact ties, like sklearn's scan) and the VALUE of the runner-up, branch-free:
+        // min over the elements of max(score, best so far) -- two FMNMX per element; tracking the runner-up's index as well
+        // made the epilogue the bottleneck of the 128-D kernel (VLAD C1 1.67 M -> 1.15 M images/s)
         float best = INFINITY, second = INFINITY;
-        int bi = 0, si = 0;
+        int bi = 0;
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N; c += 32) {
             float v[32];
@@ -215,27 +217,58 @@ struct AssignPolicy {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const float s = fmaf(m2, v[j], c2[c + j]);
-                if (s < best) { second = best; si = bi; best = s; bi = c + j; }
-                else if (s < second) { second = s; si = c + j; }
+#ifndef PVS_ASSIGN_NO_TIE
+                second = fminf(second, fmaxf(s, best));
+#endif
+                if (s < best) { best = s; bi = c + j; }
             }
         }
-        // Near-tie: the split-operand scores carry ~1e-6 of relative error (22-bit products, truncating accumulation), so
-        // two centres closer than 1e-5 of their squared norms are re-evaluated EXACTLY (||c||^2 - 2 x.c in fp64 from the fp32
-        // inputs) and the strict-< rule is applied to the exact scores.  The reference (vlad.py:95 -> sklearn's fp32 sgemm)
-        // resolves gaps below ~1e-6 by the rounding noise of its BLAS kernel's summation order, which differs between CPUs;
-        // the exact order is the only reproducible choice, and every remaining mismatch with an fp32 reference run is such a
-        // sub-1e-6 tie (tests: assert_labels).  One or two rows in ten thousand take this branch.
-        if (row < p.rows && si < p.k && second - best <= 1e-5f * 0.5f * (c2[bi] + c2[si])) {
-            const float* xr = p.x + row * (int64_t)p.d;
-            const float* ca = p.centers + (int64_t)bi * p.d;
-            const float* cb = p.centers + (int64_t)si * p.d;
-            double sa = 0.0, sb = 0.0;
-            for (int i = 0; i < p.d; ++i) {
-                const double xv = (double)xr[i], a = (double)ca[i], b = (double)cb[i];
-                sa = fma(a, a - 2.0 * xv, sa);                 // c^2 - 2 x c, term by term
-                sb = fma(b, b - 2.0 * xv, sb);
+        // Near-tie: the split-operand scores carry up to ~1e-6 of relative error (22-bit products, 24 truncating accumulation
+        // steps at D = 128), so when the runner-up is closer than 2e-6 of (||c||^2 + |score|) the two are re-evaluated EXACTLY
+        // (||c||^2 - 2 x.c in fp64 from the fp32 inputs) and the strict-< rule is applied to the exact scores.  The reference
+        // (vlad.py:95 -> sklearn's fp32 sgemm) resolves gaps below ~1e-6 by the rounding noise of its BLAS kernel's summation
+        // order, which differs between CPUs; the exact order is the only reproducible choice, and every remaining mismatch
+        // with an fp32 reference run is such a sub-1e-6 tie (tests: assert_labels).  A warp with a flagged row scans the
+        // accumulator a second time for the runner-up's index (tcgen05.ld is warp-collective) and then works the flagged rows
+        // off together: 32 lanes share the two 2 D-long fp64 dot products.  (A 1e-5 threshold flagged a row in nearly every
+        // warp of the RootSIFT benchmark and doubled the kernel's time.)
+        const bool tie = row < p.rows && second - best <= 2e-6f * (c2[bi] + fabsf(best));
+        unsigned need = __ballot_sync(0xffffffffu, tie);
+        if (need) {
+            float sec = INFINITY;
+            int si = -1;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N; c += 32) {
+                float v[32];
+                tmem_ld32(tmem + c, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float s = fmaf(m2, v[j], c2[c + j]);
+                    if (c + j != bi && s < sec) { sec = s; si = c + j; }
+                }
             }
-            if (sb < sa || (sb == sa && si < bi)) bi = si;
+            while (need) {
+                const int owner = __ffs(need) - 1;
+                need &= need - 1;
+                const int a_i = __shfl_sync(0xffffffffu, bi, owner), b_i = __shfl_sync(0xffffffffu, si, owner);
+                if (b_i < 0 || b_i >= p.k) continue;           // warp-uniform
+                const float* xr = p.x + (row - lane + owner) * (int64_t)p.d;
+                const float* ca = p.centers + (int64_t)a_i * p.d;
+                const float* cb = p.centers + (int64_t)b_i * p.d;
+                double sa = 0.0, sb = 0.0;
+                for (int i = lane; i < p.d; i += 32) {
+                    const double xv = (double)xr[i], a = (double)ca[i], b = (double)cb[i];
+                    sa = fma(a, a - 2.0 * xv, sa);             // c^2 - 2 x c, term by term
+                    sb = fma(b, b - 2.0 * xv, sb);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    sa += __shfl_xor_sync(0xffffffffu, sa, o);
+                    sb += __shfl_xor_sync(0xffffffffu, sb, o);
+                }
+                if (lane == owner && (sb < sa || (sb == sa && b_i < a_i))) bi = b_i;
+            }
         }
         if (row < p.rows) p.labels[row] = bi;
     }
