@@ -294,6 +294,12 @@ template <class P> struct policy_extra<P, decltype((void)P::STAGE_EXTRA)> { stat
 //                                      it inside store(), post-process the tiles and only then arrive on full[s]
 template <class P, class = void> struct policy_own_tx { static constexpr bool value = false; };
 template <class P> struct policy_own_tx<P, decltype((void)P::TMA_OWN_BARRIER)> { static constexpr bool value = P::TMA_OWN_BARRIER; };
+//   static constexpr bool FOLD_WARPS = true   (with MANUAL) four more warps behind the producers own the accumulator read-out:
+//                                      they wait for tfull, run fold(prm, tile, tmem, quarter, lane, FoldState&) and
+//                                      release the accumulator; the epilogue warps then only consume() stages and call
+//                                      epilogue_host(prm, tile, EpiState&) (no TMEM access, no accumulator hand-shake)
+template <class P, class = void> struct policy_foldwarps { static constexpr bool value = false; };
+template <class P> struct policy_foldwarps<P, decltype((void)P::FOLD_WARPS)> { static constexpr bool value = P::FOLD_WARPS; };
 template <class P, class = void> struct policy_gated { static constexpr bool value = false; };
 template <class P> struct policy_gated<P, decltype((void)&P::enabled)> { static constexpr bool value = true; };
 
@@ -359,7 +365,9 @@ struct Layout {
     // threads: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue,
     // warps 6-9 (only with P::MANUAL) operand producers that load fp32 from global memory,
     // split it into tf32 hi/lo parts and store the swizzled tiles themselves
-    static constexpr int THREADS = P::MANUAL ? 192 + 128 * P::PGROUPS : 192;
+    static constexpr bool FOLD = policy_foldwarps<P>::value;
+    static_assert(!FOLD || P::MANUAL, "fold warps sit behind the producer warps");
+    static constexpr int THREADS = (P::MANUAL ? 192 + 128 * P::PGROUPS : 192) + (FOLD ? 128 : 0);
     static constexpr bool OWN_TX = policy_own_tx<P>::value;
     static constexpr uint32_t FULL_COUNT = (P::TMA_BYTES > 0 && !OWN_TX ? 1 : 0) + (P::MANUAL ? 4 : 0);
     static_assert(2 * P::BLOCK_N <= 512, "accumulator does not fit TMEM twice");
@@ -486,6 +494,24 @@ __global__ void __launch_bounds__(Layout<P>::THREADS, 1) tc_kernel(const __grid_
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
+    } else if (L::FOLD && warp >= 6 + 4 * P::PGROUPS) {
+        if constexpr (L::FOLD) {
+            // accumulator read-out by dedicated warps (one per TMEM lane quarter)
+            const int quarter = warp & 3;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            typename P::FoldState fs;
+            for (int it = 0, t; (t = P::tile_at(prm, it, n_tiles)) >= 0; ++it) {
+                const typename P::Tile tl = P::tile(prm, t);
+                mbar_wait(&tfull[acc], acc_phase);
+                tcgen05_fence_after();
+                P::fold(prm, tl, tmem_base + (uint32_t)(acc * P::BLOCK_N) + ((uint32_t)(quarter * 32) << 16), quarter, lane, fs);
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
     } else if (warp >= 6) {
         if constexpr (P::MANUAL) {
             // P::PGROUPS groups of four producer warps; group g fills the k-blocks whose
@@ -552,18 +578,22 @@ __global__ void __launch_bounds__(Layout<P>::THREADS, 1) tc_kernel(const __grid_
                     if (++stage == P::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
-            PVS1_T0(t_tf);
-            mbar_wait(&tfull[acc], acc_phase);
-            PVS1_ADD(3, t_tf, warp == 2 && lane == 0);
-            tcgen05_fence_after();
-            PVS1_T0(t_body);
-            P::epilogue(prm, tl, tmem_base + (uint32_t)(acc * P::BLOCK_N) + ((uint32_t)(quarter * 32) << 16), quarter,
-                        lane, scratch, st);
-            PVS1_ADD(4, t_body, warp == 2 && lane == 0);
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if constexpr (L::FOLD) {
+                P::epilogue_host(prm, tl, st, quarter, lane);    // the fold warps own the accumulator
+            } else {
+                PVS1_T0(t_tf);
+                mbar_wait(&tfull[acc], acc_phase);
+                PVS1_ADD(3, t_tf, warp == 2 && lane == 0);
+                tcgen05_fence_after();
+                PVS1_T0(t_body);
+                P::epilogue(prm, tl, tmem_base + (uint32_t)(acc * P::BLOCK_N) + ((uint32_t)(quarter * 32) << 16), quarter,
+                            lane, scratch, st);
+                PVS1_ADD(4, t_body, warp == 2 && lane == 0);
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
         }
     }
     tcgen05_fence_before();

@@ -343,6 +343,10 @@ struct Stats16Policy {
     // addresses); tiles past the image's last segment are empty and skipped.
     struct Tile { int nkb; int t; int64_t img, r0; int kb0; bool first, last, skip; };
     static constexpr bool BF16 = false, F16 = true, A_MN = true, B_MN = true, EPI_READS_STAGES = true, MANUAL = true;
+    // The fold of a finished segment belongs to four warps of its own: the epilogue warps have to release every operand stage
+    // after reading it for the zeroth-order sums, and with the fold on them the ring stalled (4.6 -> 5.9 ms for the kernel).
+    static constexpr bool FOLD_WARPS = true;
+    struct FoldState {};
     static constexpr bool TMA_OWN_BARRIER = true;
     static constexpr int KT = 16;             // descriptors per stage = one K=16 step
     static constexpr int PASSES = 3, BLOCK_N = FV_K, STAGES = 7, KSTEPS = 1, PGROUPS = 1;
@@ -464,8 +468,18 @@ struct Stats16Policy {
         }
         st.s0 = acc;
     }
-    __device__ static void epilogue(const Params& p, const Tile& t, uint32_t tmem, int quarter, int lane, uint8_t*,
-                                    EpiState& st)
+    // epilogue warps: only the zeroth-order sums (collected stage by stage in consume())
+    __device__ static void epilogue_host(const Params& p, const Tile& t, EpiState& st, int quarter, int lane)
+    {
+        if (t.skip || !t.last) return;
+        const int e = quarter * 32 + lane;
+        // raw zeroth-order sums go into partial slot 0 (the other slots stay zero, fv_finalize adds them up and divides by T)
+        reinterpret_cast<float2*>(p.b.s0part + t.img * (int64_t)(TC_FV_S0_PARTS * FV_K))[e] =
+            make_float2(st.s0.x * (1.f / 16384.f), st.s0.y * (1.f / 16384.f));
+    }
+    // fold warps: add the finished segment to the image's S rows.  32 columns per round trip to L2 (the running sums of the
+    // earlier segments come back while the accumulator is read); the last segment applies the operand scales and 1 / T.
+    __device__ static void fold(const Params& p, const Tile& t, uint32_t tmem, int quarter, int lane, FoldState&)
     {
         if (t.skip) return;                                // past the image's last segment
         const int e = quarter * 32 + lane;                 // operand row: [0,64) = y'^2, [64,128) = y'
@@ -474,31 +488,24 @@ struct Stats16Policy {
         const float scale = t.last ? (e < FV_D ? p.un2 : p.un1) / (float)t.t : 1.f;   // undo the operand scales; T == 0 -> NaN below
         const bool empty = t.t == 0;
         const float nanv = __int_as_float(0x7fc00000);
-        // raw zeroth-order sums go into partial slot 0 (the other slots stay zero, fv_finalize adds them up and divides by T)
-        if (t.last)
-            reinterpret_cast<float2*>(p.b.s0part + t.img * (int64_t)(TC_FV_S0_PARTS * FV_K))[e] =
-                make_float2(st.s0.x * (1.f / 16384.f), st.s0.y * (1.f / 16384.f));
-        // fold: 64 columns per round trip to L2 (the running sums of the earlier segments come back while the accumulator
-        // is read).  Measured alternatives: 16-column slices between the stages of the next segment (the epilogue warps also
-        // have to release every stage after reading it for the zeroth-order sums) made the kernel slower, 6.0 -> 6.7 ms.
 #pragma unroll 1
-        for (int c = 0; c < FV_K; c += 64) {
-            float v[64], r[64];
+        for (int c = 0; c < FV_K; c += 32) {
+            float v[32], r[32];
             if (!t.first) {
 #pragma unroll
-                for (int jj = 0; jj < 64; ++jj) r[jj] = __ldcg(Simg + (int64_t)(c + jj) * FV_2D);
+                for (int jj = 0; jj < 32; ++jj) r[jj] = __ldcg(Simg + (int64_t)(c + jj) * FV_2D);
             }
             __syncwarp();
-            tmem_ld32(tmem + c, *reinterpret_cast<float (*)[32]>(v));
-            tmem_ld32(tmem + c + 32, *reinterpret_cast<float (*)[32]>(v + 32));
+            tmem_ld32(tmem + c, v);
             tmem_ld_wait();
 #pragma unroll
-            for (int jj = 0; jj < 64; ++jj) {
+            for (int jj = 0; jj < 32; ++jj) {
                 const float x = t.first ? v[jj] : v[jj] + r[jj];
                 __stcg(Simg + (int64_t)(c + jj) * FV_2D, empty ? nanv : x * scale);
             }
         }
     }
+    __device__ static void epilogue(const Params&, const Tile&, uint32_t, int, int, uint8_t*, EpiState&) {}   // unused (FOLD_WARPS)
 };
 // the 3xTF32 kernel behind the opposite gate
 struct StatsGatedPolicy : StatsPolicy {
