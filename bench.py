@@ -573,10 +573,18 @@ def run_ours(args):
         else:
             roofline = {"bound": "hbm", "achieved": r["hbm"]["achieved_gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
                         "frac": r["hbm"]["frac"], "peak_source": f"hbm copy, {pk['source']}"}
+        own_flop = {"tc_fv_project": 2 * T * d_in * D, "tc_fv_posterior": 2 * T * K * 2 * D, "tc_fv_stats": 2 * T * K * 2 * D,
+                    "tc_fv_poststats_fused": 4 * T * K * 2 * D}.get(name)
+        if own_flop:                                       # the kernel's OWN share of the work, for orientation
+            own_tf = own_flop * imgs_per_launch / (per_launch_ms / 1e3) / 1e12
+            roofline["kernel_own"] = {"flop_per_image": own_flop, "achieved_tflops": own_tf,
+                                      "frac_of_3pass_ceiling": 3 * own_tf / pk["bf16_tflops_sustained"],
+                                      "hbm_frac_on_interface_bytes": bytes_per_image.get(name, 0) * imgs_per_launch / (per_launch_ms / 1e3) / 1e9 / pk["hbm_gbs"]}
         roofline.update({
             "kernel": name, "tensor": r["tensor"], "hbm": r["hbm"],
-            "note": "SURVEY.md 8(d) work of the WHOLE path per image over the dominant kernel's time; the contractions are three "
-                    "kind::f16 MMAs per product, so the tensor ceiling is peak / 3 (frac_of_3pass_ceiling)",
+            "note": "SURVEY.md 8(d) work of the WHOLE path per image over the dominant kernel's time (so it can exceed the ceiling "
+                    "when the step is spread over several kernels: path_roofline is the whole step, kernel_own the kernel's own "
+                    "share); the contractions are three kind::f16 MMAs per product, so the tensor ceiling is peak / 3",
             "traffic": tr["dram_bytes_per_image"] * imgs_per_launch if tr else None,
             "traffic_source": tr["source"] if tr else None,
             "kernel_interface_bytes_per_launch": bytes_per_image.get(name, 0) * imgs_per_launch,
