@@ -477,7 +477,7 @@ struct Stats16Policy {
         reinterpret_cast<float2*>(p.b.s0part + t.img * (int64_t)(TC_FV_S0_PARTS * FV_K))[e] =
             make_float2(st.s0.x * (1.f / 16384.f), st.s0.y * (1.f / 16384.f));
     }
-    // fold warps: add the finished segment to the image's S rows.  32 columns per round trip to L2 (the running sums of the
+    // fold warps: add the finished segment to the image's S rows.  64 columns per round trip to L2 (the running sums of the
     // earlier segments come back while the accumulator is read); the last segment applies the operand scales and 1 / T.
     __device__ static void fold(const Params& p, const Tile& t, uint32_t tmem, int quarter, int lane, FoldState&)
     {
@@ -489,19 +489,22 @@ struct Stats16Policy {
         const bool empty = t.t == 0;
         const float nanv = __int_as_float(0x7fc00000);
 #pragma unroll 1
-        for (int c = 0; c < FV_K; c += 32) {
-            float v[32], r[32];
+        for (int c = 0; c < FV_K; c += 64) {               // 64 running sums in flight per trip to L2, the accumulator in two halves
+            float v[32], r[64];
             if (!t.first) {
 #pragma unroll
-                for (int jj = 0; jj < 32; ++jj) r[jj] = __ldcg(Simg + (int64_t)(c + jj) * FV_2D);
+                for (int jj = 0; jj < 64; ++jj) r[jj] = __ldcg(Simg + (int64_t)(c + jj) * FV_2D);
             }
-            __syncwarp();
-            tmem_ld32(tmem + c, v);
-            tmem_ld_wait();
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) {
-                const float x = t.first ? v[jj] : v[jj] + r[jj];
-                __stcg(Simg + (int64_t)(c + jj) * FV_2D, empty ? nanv : x * scale);
+            for (int h = 0; h < 2; ++h) {
+                __syncwarp();
+                tmem_ld32(tmem + c + 32 * h, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) {
+                    const float x = t.first ? v[jj] : v[jj] + r[32 * h + jj];
+                    __stcg(Simg + (int64_t)(c + 32 * h + jj) * FV_2D, empty ? nanv : x * scale);
+                }
             }
         }
     }
