@@ -38,6 +38,7 @@ WORKLOADS = {
     "c2": (8189, 2000, 128, "FV encode, GMM K=256 diag, SIFT-128 -> PCA-64, 8189 images x 2000 descriptors"),
     "c3": (100000, 196, 514, "VLAD encode, K=256, VGG16 conv 514-D, 196 descriptors/image, 100k images"),
     "c4": (262144, 0, 32768, "all-pairs cosine + top-100 over 262144 VLAD vectors (256 x 128 = 32768-D)"),
+    "c5": (1048576, 0, 164608, "Pipeline VLAD(RootSIFT-128) + FV(VGG16-PCA 514 -> 257) encode (164608-D) + retrieval top-100 / mAP over 1M synthetic images"),
 }
 # algorithmic work per image of the FV C2 path (PCA + logits + statistics; descriptors in,
 # fp32 encoding out)
@@ -180,8 +181,14 @@ def run_reference(args):
             descs = [x[i * T:(i + 1) * T] for i in range(sample)]
             fn = lambda: O.vlad_encode(descs, cen)
             what = f"{sample} of {n_img} images x {T} descriptors per step"
+        elif args.workload == "c5":
+            sample, metric, unit, db_rows = 32, "pipeline_retrieval_queries_per_s", "queries/s", 2048
+            q = rng.standard_normal((sample, d_in)).astype(np.float32)
+            db = rng.standard_normal((db_rows, d_in)).astype(np.float32)
+            fn = lambda: O.cosine_topk(q, db, 100)
+            what = f"{sample} queries against {db_rows} of {n_img} database rows of {d_in}-D per step (scaled by {db_rows} / {n_img}); retrieval only"
         else:
-            sample, metric, unit = 128, "cosine_top100_queries_per_s", "queries/s"
+            sample, metric, unit, db_rows = 128, "cosine_top100_queries_per_s", "queries/s", 16384
             q, db = vlad_like_rows(rng, sample), vlad_like_rows(rng, 16384)
             fn = lambda: O.cosine_topk(q, db, 100)
             what = f"{sample} queries against 16384 of {n_img} database rows per step (scaled by 16384 / {n_img})"
@@ -194,8 +201,8 @@ def run_reference(args):
             times.append(time.perf_counter() - t0)
     ms = 1e3 * float(np.mean(times))
     value = sample / (ms / 1e3)
-    if args.workload == "c4":
-        value *= 16384 / n_img                             # queries/s against the full database
+    if args.workload in ("c4", "c5"):
+        value *= db_rows / n_img                           # queries/s against the full database
     line = {
         "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -838,13 +845,114 @@ def run_c4(args):
         dist.destroy_process_group()
 
 
+def run_c5(args):
+    """BASELINE.json configs[4]: Pipeline VLAD(RootSIFT) + FV(VGG16-PCA) concatenated encode, then all-pairs retrieval with
+    top-100 lists and mAP / top-k accuracy over the whole set, images sharded over the ranks.  The encodings (164,608-D,
+    bf16 after row normalisation: 329 GB for 1 M images) never exist in one place: every rank keeps its shard and the
+    shards travel around a ring (`retrieval.all_pairs_topk_ring`); label metrics are evaluated on the device
+    (`pvs_topk_label_metrics`) and reduced with one all-reduce.  Synthetic images: every class has a prototype descriptor
+    for each extractor, an image is its class prototype plus noise (so that retrieval has something to find)."""
+    import torch
+    import torch.distributed as dist
+    from pyvisim_b200 import _native as N, retrieval
+    from pyvisim_b200.encoders import FisherVectorEncoder, VLADEncoder, GMMWeights, Pipeline
+    from pyvisim_b200.encoders._base_encoder import kmeans_from_centers
+    from pyvisim_b200.features import Descriptors
+    rank, local_rank, world, dev = _dist_setup()
+    n_total, _, dim, desc = WORKLOADS["c5"]
+    if args.images:
+        n_total = args.images
+    lo, hi = retrieval.shard_bounds(n_total, world, rank)
+    n = hi - lo
+    T1, T2, k = 2000, 196, 100
+    per_class = 64
+    classes = max(2, n_total // per_class)
+    pg = torch.Generator(device=dev).manual_seed(2024)               # prototypes and centres: the same on every rank
+    proto1 = torch.randn((classes, 128), device=dev, generator=pg).abs_()
+    proto2 = torch.randn((classes, 514), device=dev, generator=pg)
+    cen = torch.randn((256, 128), device=dev, generator=pg).abs_()
+    cen = (cen / cen.sum(1, keepdim=True)).sqrt_().cpu().numpy()
+    pipe = Pipeline([VLADEncoder(feature_extractor=Descriptors(128), kmeans_model=kmeans_from_centers(cen)),
+                     FisherVectorEncoder(feature_extractor=Descriptors(514), weights=GMMWeights.OXFORD102_K256_VGG16_PCA,
+                                         output_dtype=np.float32)])
+    shard = torch.empty((n, dim), dtype=torch.bfloat16, device=dev)
+    gen = torch.Generator(device=dev).manual_seed(99 + rank)
+    chunk = 1024
+    enc_ms = 0.0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    N.lib().pvs_launch_count_reset()
+    with ClockSampler(local_rank) as clocks:
+        for c0 in range(0, n, chunk):
+            m = min(chunk, n - c0)
+            cls = (torch.arange(lo + c0, lo + c0 + m, device=dev) % classes)
+            x1 = (proto1[cls][:, None, :] + 2.0 * torch.randn((m, T1, 128), device=dev, generator=gen)).abs_()
+            x1 = (x1 / (x1.sum(2, keepdim=True) + 1e-7)).sqrt_().reshape(m * T1, 128)
+            x2 = (proto2[cls][:, None, :] + 3.0 * torch.randn((m, T2, 514), device=dev, generator=gen)).clamp_min_(0).reshape(m * T2, 514)
+            o1, o2 = torch.arange(m + 1, dtype=torch.int64) * T1, torch.arange(m + 1, dtype=torch.int64) * T2
+            torch.cuda.synchronize()
+            e0.record()
+            enc = pipe.encode_descriptors([x1, x2], [o1, o2])
+            shard[c0:c0 + m] = retrieval.l2_normalize(enc, "bf16")
+            e1.record()
+            torch.cuda.synchronize()
+            enc_ms += e0.elapsed_time(e1)
+            del x1, x2, enc
+        enc_launches = int(N.lib().pvs_launch_count())
+        torch.cuda.empty_cache()
+        # warm-up on a 512-row slice per rank (NCCL point-to-point channels, workspaces), not timed
+        retrieval.all_pairs_topk_ring(shard[:min(n, 512)], k + 1, rank=rank, world=world, normalized=True, gather=False)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        s_, i_ = retrieval.all_pairs_topk_ring(shard, k + 1, rank=rank, world=world, normalized=True, gather=False)
+        labels = (torch.arange(n_total, device=dev) % classes).to(torch.int32)
+        hits, ap = retrieval.label_metrics(i_[:, 1:].contiguous(), labels, labels[lo:hi])
+        agg = torch.stack([ap.double().sum(), (hits > 0).double().sum(),
+                           (i_[:, 0] == torch.arange(lo, hi, device=dev)).double().sum()])
+        if world > 1:
+            dist.all_reduce(agg)
+        r1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    ret_ms = r0.elapsed_time(r1)
+    t = torch.tensor([enc_ms, ret_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    enc_ms, ret_ms = float(t[0]), float(t[1])
+    pk = peaks()
+    flop = 2.0 * n_total * n_total * dim
+    if rank == 0:
+        print(json.dumps({
+            "metric": "pipeline_retrieval_queries_per_s", "value": n_total / (ret_ms / 1e3), "unit": "queries/s", "n_gpus": world, "steps": 1, "warmup": 0,
+            "ms_per_step": ret_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 encode, bf16 similarity",
+            "data": "synthetic", "config": {"workload": desc, "images_total": n_total, "images_per_gpu": n, "dim": dim, "k": k, "classes": classes,
+                                            "descriptors_per_image": {"rootsift128": T1, "vgg16_514": T2},
+                                            "weights": "VLAD: random-init K-Means (no RootSIFT K-Means file is bundled); FV: bundled gmm_k256_deep_features_vgg16_pca + PCA",
+                                            "parallelism": f"images sharded over {world} rank(s); shards of the bf16 encodings travel around a ring; mAP all-reduced"},
+            "encode": {"images_per_s": n_total / (enc_ms / 1e3), "ms": enc_ms, "gpu_launches": enc_launches,
+                       "note": "Pipeline.encode_descriptors + row normalisation, descriptors generated on the device chunk by chunk (generation not timed)"},
+            "retrieval": {"ms": ret_ms, "pflops": flop / ret_ms / 1e12, "frac_of_bf16_sustained_peak": flop / ret_ms / 1e9 / world / pk["bf16_tflops_sustained"],
+                          "shard_gb_per_rank": n * dim * 2 / 1e9},
+            "quality": {"map_at_100": float(agg[0]) / n_total, "top100_accuracy": float(agg[1]) / n_total, "self_is_first": float(agg[2]) / n_total,
+                        "chance_precision": per_class / n_total},
+            "e2e": {"value": n_total / ((enc_ms + ret_ms) / 1e3), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 16,
+                    "note": "encode + retrieval + mAP; descriptors are synthesised on the device (1.4 MB per image would be 1.5 TB of host traffic)"},
+            "clocks": clocks.summary()}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"], help="c2 (default) = the configuration the metric is quoted on")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"], help="c2 (default) = the configuration the metric is quoted on")
     ap.add_argument("--images", type=int, default=0, help="override images per GPU (debug)")
     ap.add_argument("--images-per-call", type=int, default=0, help="0 = library default (4 per SM)")
     ap.add_argument("--e2e-images", type=int, default=0, help="images in the host-buffer leg (0 = all)")
@@ -859,6 +967,8 @@ def main():
         run_c3(args)
     elif args.workload == "c4":
         run_c4(args)
+    elif args.workload == "c5":
+        run_c5(args)
     else:
         run_ours(args)
 
