@@ -229,6 +229,16 @@ int pvs_vlad_encode_host(const pvs_model* kmeans, const pvs_model* pca, const fl
 int pvs_fv_encode_host(const pvs_model* gmm, const pvs_model* pca, const float* desc_host,
                        const int64_t* offsets_host, int64_t n_images, float power, float norm_order,
                        float eps, float* out_host, int64_t chunk_rows);
+/* uint8 transport (a declared option, not the reference's dtype): descriptors whose values are integers in 0..255 --
+ * what OpenCV's SIFT produces (features/_features.py:96-110 returns them as float32) and how they are usually stored --
+ * may be passed as uint8 rows.  They cross PCIe in a quarter of the bytes, are widened to float32 on the device and then
+ * take exactly the path of the float32 entry points: results are bit-identical to passing the same values as float32. */
+int pvs_vlad_encode_host_u8(const pvs_model* kmeans, const pvs_model* pca, const uint8_t* desc_host,
+                            const int64_t* offsets_host, int64_t n_images, float power, float norm_order,
+                            float eps, float* out_host, int32_t* labels_out_host, int64_t chunk_rows);
+int pvs_fv_encode_host_u8(const pvs_model* gmm, const pvs_model* pca, const uint8_t* desc_host,
+                          const int64_t* offsets_host, int64_t n_images, float power, float norm_order,
+                          float eps, float* out_host, int64_t chunk_rows);
 int pvs_cosine_matrix_host(const float* x_host, int64_t n, const float* y_host, int64_t m, int64_t d,
                            float* s_host);
 int pvs_cosine_topk_host(const float* q_host, int64_t n_q, const float* db_host, int64_t n_db, int64_t d,

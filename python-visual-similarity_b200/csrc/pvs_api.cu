@@ -768,9 +768,11 @@ int slot_reserve(Slot& s, size_t bytes, size_t n_offs)
 }
 
 // shared driver for the two encoders: chunk images so a chunk has <= chunk_rows rows
+// desc_u8 != NULL: uint8 transport -- the chunk crosses PCIe as bytes into a staging area and is widened on the device
 template <typename EncodeFn, typename WsFn>
 int encode_host(const float* desc_host, const int64_t* offsets_host, int64_t n_images, int d_in, int64_t out_dim,
-                float* out_host, int32_t* rows_i32_out_host, int64_t chunk_rows, WsFn ws_bytes, EncodeFn encode)
+                float* out_host, int32_t* rows_i32_out_host, int64_t chunk_rows, WsFn ws_bytes, EncodeFn encode,
+                const uint8_t* desc_u8 = nullptr)
 {
     PVS_CHECK(n_images >= 0, PVS_ERR_BAD_ARG, "negative n_images");
     if (n_images == 0) return PVS_OK;
@@ -778,7 +780,7 @@ int encode_host(const float* desc_host, const int64_t* offsets_host, int64_t n_i
     PVS_CHECK(offsets_host[0] == 0, PVS_ERR_BAD_ARG, "offsets[0] must be 0");
     for (int64_t i = 0; i < n_images; ++i)
         PVS_CHECK(offsets_host[i + 1] >= offsets_host[i], PVS_ERR_BAD_ARG, "offsets must be non-decreasing");
-    PVS_CHECK(offsets_host[n_images] == 0 || desc_host, PVS_ERR_BAD_ARG, "NULL descriptor buffer");
+    PVS_CHECK(offsets_host[n_images] == 0 || desc_host || desc_u8, PVS_ERR_BAD_ARG, "NULL descriptor buffer");
     if (int s = require_device()) return s;
     if (chunk_rows <= 0) chunk_rows = 1 << 19;
     HostCtx& ctx = host_ctx();
@@ -799,16 +801,21 @@ int encode_host(const float* desc_host, const int64_t* offsets_host, int64_t n_i
         const size_t b_out = align_up((size_t)n * out_dim * 4, 256);
         const size_t b_lab = rows_i32_out_host ? align_up((size_t)rows * 4, 256) : 0;
         const size_t b_ws = ws_bytes(rows, n);
+        const size_t b_u8 = desc_u8 ? align_up((size_t)rows * d_in, 256) : 0;
         if (s.stream) PVS_CUDA(cudaStreamSynchronize(s.stream));      // previous use of this slot finished
-        if ((rc = slot_reserve(s, b_desc + b_offs + b_out + b_lab + b_ws + 256, (size_t)n + 1))) break;
+        if ((rc = slot_reserve(s, b_desc + b_offs + b_out + b_lab + b_ws + b_u8 + 256, (size_t)n + 1))) break;
         char* p = (char*)s.buf;
         float* d_desc = (float*)p;            p += b_desc;
         int64_t* d_offs = (int64_t*)p;        p += b_offs;
         float* d_out = (float*)p;             p += b_out;
         int32_t* d_lab = rows_i32_out_host ? (int32_t*)p : nullptr; p += b_lab;
-        void* d_ws = p;
+        void* d_ws = p;                       p += b_ws;
+        uint8_t* d_u8 = (uint8_t*)p;
         for (int64_t i = 0; i <= n; ++i) s.offs_pinned[i] = offsets_host[i0 + i] - offsets_host[i0];
-        if (rows > 0)
+        if (rows > 0 && desc_u8) {
+            PVS_CUDA(cudaMemcpyAsync(d_u8, desc_u8 + offsets_host[i0] * (int64_t)d_in, (size_t)rows * d_in, cudaMemcpyHostToDevice, s.stream));
+            if ((rc = launch_u8_to_f32(d_u8, d_desc, (size_t)rows * d_in, s.stream))) break;
+        } else if (rows > 0)
             PVS_CUDA(cudaMemcpyAsync(d_desc, desc_host + offsets_host[i0] * (int64_t)d_in, (size_t)rows * d_in * 4,
                                      cudaMemcpyHostToDevice, s.stream));
         PVS_CUDA(cudaMemcpyAsync(d_offs, s.offs_pinned, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, s.stream));
@@ -860,6 +867,40 @@ extern "C" int pvs_fv_encode_host(const pvs_model* g, const pvs_model* pca, cons
             cudaStream_t st) {
             return pvs_fv_encode(g, pca, dd, doff, n, rows, power, norm_order, eps, dout, nullptr, ws, wsb, st);
         });
+}
+
+extern "C" int pvs_vlad_encode_host_u8(const pvs_model* km, const pvs_model* pca, const uint8_t* desc_host,
+                                       const int64_t* offsets_host, int64_t n_images, float power, float norm_order,
+                                       float eps, float* out_host, int32_t* labels_out_host, int64_t chunk_rows)
+{
+    if (int s = check_chain(km, PVS_MODEL_KMEANS, pca, "pvs_vlad_encode_host_u8")) return s;
+    PVS_CHECK(norm_order > 0.f, PVS_ERR_UNSUPPORTED, "norm_order must be > 0 (or inf), got %g", (double)norm_order);
+    const int d_in = pca ? pca->d_in : km->d;
+    return encode_host(
+        nullptr, offsets_host, n_images, d_in, (int64_t)km->k * km->d, out_host, labels_out_host, chunk_rows,
+        [&](int64_t rows, int64_t n) { return pvs_vlad_workspace_bytes(km, pca, rows, n); },
+        [&](const float* dd, const int64_t* doff, int64_t n, int64_t rows, float* dout, int32_t* dlab, void* ws, size_t wsb,
+            cudaStream_t st) {
+            return pvs_vlad_encode(km, pca, dd, doff, n, rows, power, norm_order, eps, dout, dlab, ws, wsb, st);
+        },
+        desc_host);
+}
+
+extern "C" int pvs_fv_encode_host_u8(const pvs_model* g, const pvs_model* pca, const uint8_t* desc_host,
+                                     const int64_t* offsets_host, int64_t n_images, float power, float norm_order,
+                                     float eps, float* out_host, int64_t chunk_rows)
+{
+    if (int s = check_chain(g, PVS_MODEL_GMM_DIAG, pca, "pvs_fv_encode_host_u8")) return s;
+    PVS_CHECK(norm_order > 0.f, PVS_ERR_UNSUPPORTED, "norm_order must be > 0 (or inf), got %g", (double)norm_order);
+    const int d_in = pca ? pca->d_in : g->d;
+    return encode_host(
+        nullptr, offsets_host, n_images, d_in, (int64_t)2 * g->k * g->d + g->k, out_host, nullptr, chunk_rows,
+        [&](int64_t rows, int64_t n) { return pvs_fv_workspace_bytes(g, pca, rows, n); },
+        [&](const float* dd, const int64_t* doff, int64_t n, int64_t rows, float* dout, int32_t*, void* ws, size_t wsb,
+            cudaStream_t st) {
+            return pvs_fv_encode(g, pca, dd, doff, n, rows, power, norm_order, eps, dout, nullptr, ws, wsb, st);
+        },
+        desc_host);
 }
 
 extern "C" int pvs_cosine_matrix_host(const float* x, int64_t n, const float* y, int64_t m, int64_t d, float* s_host)

@@ -35,6 +35,8 @@ int launch_fv_finalize(const float* S, int ld, const float* s0part, int parts, c
 
 // ---- similarity / top-k --------------------------------------------------------------------
 int launch_l2_normalize(const float* x, int64_t n, int64_t d, void* out, int out_dtype, cudaStream_t st);
+// uint8 -> float32 (the uint8 transport of the host entry points); n = number of elements, both pointers 16-byte aligned
+int launch_u8_to_f32(const uint8_t* in, float* out, size_t n, cudaStream_t st);
 int launch_bf16_to_f32(const void* x, int64_t n, float* out, cudaStream_t st);
 int launch_f32_to_split(const float* x, int64_t n, void* out, cudaStream_t st);
 // s[n, m] = cosine of raw rows, for small n * m (one CTA per pair, no workspace)

@@ -1126,4 +1126,32 @@ int launch_label_metrics(const int64_t* idx, const int32_t* db_labels, const int
     return PVS_OK;
 }
 
+// =====================================================================================
+// uint8 -> float32 widening (uint8 transport of the host entry points): 16 bytes in, 64 bytes out per thread step
+// =====================================================================================
+namespace {
+__global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint4* __restrict__ in, float4* __restrict__ out, size_t n16,
+                                                          const uint8_t* __restrict__ tail_in, float* __restrict__ tail_out, int n_tail)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = __ldg(in + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            out[4 * i + q] = make_float4((float)(w[q] & 0xffu), (float)((w[q] >> 8) & 0xffu), (float)((w[q] >> 16) & 0xffu), (float)(w[q] >> 24));
+    }
+    if (blockIdx.x == 0 && (int)threadIdx.x < n_tail) tail_out[threadIdx.x] = (float)tail_in[threadIdx.x];
+}
+}  // namespace
+
+int launch_u8_to_f32(const uint8_t* in, float* out, size_t n, cudaStream_t st)
+{
+    if (n == 0) return PVS_OK;
+    const size_t n16 = n / 16;
+    const int n_tail = (int)(n - n16 * 16);
+    const unsigned grid = (unsigned)std::min<size_t>(std::max<size_t>((n16 + 255) / 256, 1), 148 * 16);
+    PVS_LAUNCH(u8_to_f32_kernel, grid, 256, 0, st, (const uint4*)in, (float4*)out, n16, in + n16 * 16, out + n16 * 16, n_tail);
+    return PVS_OK;
+}
+
 }  // namespace pvs

@@ -83,6 +83,8 @@ EXPORTS = {
     "pvs_allgather_topk": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "pvs_vlad_encode_host": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _vp, _vp, _i64]),
     "pvs_fv_encode_host": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _vp, _i64]),
+    "pvs_vlad_encode_host_u8": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _vp, _vp, _i64]),
+    "pvs_fv_encode_host_u8": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _vp, _i64]),
     "pvs_cosine_matrix_host": (_i32, [_vp, _i64, _vp, _i64, _i64, _vp]),
     "pvs_cosine_topk_host": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _i32, _vp, _vp]),
     "pvs_debug_tc_gemm": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),

@@ -34,7 +34,9 @@ def normalise_inputs(descriptors, offsets, d_in: int):
     if isinstance(descriptors, np.ndarray) and descriptors.ndim == 2:
         if descriptors.shape[1] != d_in:
             raise ValueError(f"descriptors must be (rows, {d_in}), got {descriptors.shape}")
-        x = np.ascontiguousarray(descriptors, dtype=np.float32)
+        # uint8 rows (integer-valued descriptors such as OpenCV SIFT's, as they are usually stored) keep their dtype: the
+        # host entry points move them over PCIe as bytes and widen them on the device (bit-identical results)
+        x = np.ascontiguousarray(descriptors) if descriptors.dtype == np.uint8 else np.ascontiguousarray(descriptors, dtype=np.float32)
         offs = np.array([0, x.shape[0]], np.int64) if offsets is None else np.ascontiguousarray(offsets, dtype=np.int64)
         return x, offs, False
     descs = [np.asarray(d) for d in descriptors]

@@ -106,6 +106,7 @@ class FisherVectorEncoder(ImageEncoderBase):
             out = np.empty((n, dim), dtype=np.float32)
         elif out.dtype != np.float32 or out.shape != (n, dim) or not out.flags.c_contiguous:
             raise ValueError(f"out must be C-contiguous float32 of shape {(n, dim)}")
-        N.check(N.lib().pvs_fv_encode_host(cluster.handle, pca.handle if pca else None, x.ctypes.data,
-                                           offs.ctypes.data, n, *params, out.ctypes.data, int(chunk_rows)))
+        host_fn = N.lib().pvs_fv_encode_host_u8 if x.dtype == np.uint8 else N.lib().pvs_fv_encode_host
+        N.check(host_fn(cluster.handle, pca.handle if pca else None, x.ctypes.data,
+                        offs.ctypes.data, n, *params, out.ctypes.data, int(chunk_rows)))
         return out

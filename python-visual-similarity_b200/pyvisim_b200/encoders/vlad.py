@@ -99,7 +99,8 @@ class VLADEncoder(ImageEncoderBase):
         elif out.dtype != np.float32 or out.shape != (n, dim) or not out.flags.c_contiguous:
             raise ValueError(f"out must be C-contiguous float32 of shape {(n, dim)}")
         labels = np.empty(x.shape[0], dtype=np.int32) if return_labels else None
-        N.check(N.lib().pvs_vlad_encode_host(cluster.handle, pca.handle if pca else None, x.ctypes.data,
-                                             offs.ctypes.data, n, *params, out.ctypes.data,
-                                             labels.ctypes.data if return_labels else None, int(chunk_rows)))
+        host_fn = N.lib().pvs_vlad_encode_host_u8 if x.dtype == np.uint8 else N.lib().pvs_vlad_encode_host
+        N.check(host_fn(cluster.handle, pca.handle if pca else None, x.ctypes.data,
+                        offs.ctypes.data, n, *params, out.ctypes.data,
+                        labels.ctypes.data if return_labels else None, int(chunk_rows)))
         return (out, labels) if return_labels else out

@@ -274,3 +274,24 @@ def test_vlad_near_ties_resolved_exactly(api):
     g1, g2 = exact_labels(d1, cen)[0], exact_labels(d2, cen)[0]
     ref = float(np.asarray(O.similarity_score(vlad_from_labels(d1, g1)[None], vlad_from_labels(d2, g2)[None])).ravel()[0])
     assert abs(score - ref) <= 1e-5 * abs(ref), (score, ref)
+
+
+def test_uint8_transport_is_bit_identical(api):
+    """Declared option of the host entry points (pvs_*_encode_host_u8): integer-valued descriptors (OpenCV SIFT) passed as
+    uint8 rows cross PCIe as bytes, are widened on the device and give bit-identical encodings and labels."""
+    from pyvisim_b200.encoders._base_encoder import kmeans_from_centers
+    rng = np.random.default_rng(5)
+    ts = [300, 1, 77, 513, 0, 40]
+    offs = np.concatenate([[0], np.cumsum(ts)]).astype(np.int64)
+    xf = np.floor(np.clip(np.abs(rng.normal(0, 40, (int(offs[-1]), 128))), 0, 255)).astype(np.float32)
+    xu = xf.astype(np.uint8)
+    fv = api.enc.FisherVectorEncoder(feature_extractor=api.feat.Descriptors(128), weights=api.enc.GMMWeights.OXFORD102_K256_SIFT_PCA)
+    a, b = fv.encode_descriptors(xf, offs), fv.encode_descriptors(xu, offs)
+    assert a.dtype == np.float32 and np.array_equal(a, b, equal_nan=True)
+    cen = xf[rng.choice(xf.shape[0], 256, replace=False)] + 0.25
+    vl = api.enc.VLADEncoder(feature_extractor=api.feat.Descriptors(128), kmeans_model=kmeans_from_centers(cen))
+    (va, la), (vb, lb) = vl.encode_descriptors(xf, offs, return_labels=True), vl.encode_descriptors(xu, offs, return_labels=True)
+    assert np.array_equal(va, vb) and np.array_equal(la, lb)
+    # small chunks: several H2D / widen / encode / D2H rounds on the two slots
+    c = fv.encode_descriptors(xu, offs, chunk_rows=350)
+    assert np.array_equal(a, c, equal_nan=True)
