@@ -183,12 +183,68 @@ struct StatsParams {
     float* S;                                 // [n_images, 256, 128]: [k][ s1 (64) | s2 (64) ], already / T
     float* s0part;                            // [n_images, 16, 256]: raw column sums of Q per producer warp
     int64_t n_images;
+    const int* smax;                          // segments per image slot: max over the images of ceil(k-blocks / segk), >= 1 (device)
+    int segk;                                 // k-blocks (ST_KT descriptors each) per statistics segment
 };
+
+// A tile of the statistics kernels is one SEGMENT of an image: `segk` k-blocks accumulated from zero in one of the two TMEM
+// accumulators and folded into the image's S rows (global memory, L2-resident, fp32 round-to-nearest adds) while the next
+// segment is being multiplied into the other accumulator.  tcgen05.mma adds every K-slice to the accumulator with truncation;
+// accumulated over a whole 2 000-descriptor image that bias, amplified by the cancellation in d_sigma, put 46 (fp16x2) to
+// 98 (3xTF32) of the 8 189 images of the C2 batch 1e-4 .. 3.2e-4 off the fp64 result.  Every image gets *smax consecutive
+// tiles on ONE CTA (the folds of an image are ordered: same threads, same addresses); tiles past the image's last segment
+// are empty and skipped.
+struct SegTile { int nkb; int t; int64_t img, r0; int kb0; bool first, last, skip; };
+__device__ __forceinline__ int seg_tile_at(const StatsParams& p, int it)
+{
+    const int smax = *p.smax;
+    const long long img = (long long)blockIdx.x + (long long)(it / smax) * gridDim.x;
+    return img < p.n_images ? (int)(img * smax + it % smax) : -1;
+}
+__device__ __forceinline__ SegTile seg_tile(const StatsParams& p, int i, int kt)
+{
+    const int smax = *p.smax;
+    const int64_t img = i / smax;
+    const int seg = i - (int)img * smax;
+    const int64_t r0 = p.offsets[img];
+    const int t = (int)(p.offsets[img + 1] - r0);
+    const int total = (t + kt - 1) / kt, kb0 = seg * p.segk;
+    const int left = total - kb0;
+    SegTile tl;
+    tl.nkb = left <= 0 ? 0 : (left < p.segk ? left : p.segk);
+    tl.t = t; tl.img = img; tl.r0 = r0; tl.kb0 = kb0;
+    tl.first = seg == 0;
+    tl.last = left <= p.segk;                              // also true for an empty image (its only tile writes NaN)
+    tl.skip = seg > 0 && left <= 0;
+    return tl;
+}
+// fold of a finished segment by one warp (its TMEM lane quarter): 32 running sums per trip to L2
+__device__ __forceinline__ void seg_fold(const SegTile& t, float* Srow, uint32_t tmem, float scale)
+{
+    const bool empty = t.t == 0;
+    const float nanv = __int_as_float(0x7fc00000);
+#pragma unroll 1
+    for (int c = 0; c < FV_K; c += 32) {
+        float v[32], r[32];
+        if (!t.first) {
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) r[jj] = __ldcg(Srow + (int64_t)(c + jj) * FV_2D);
+        }
+        __syncwarp();
+        tmem_ld32(tmem + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+            const float x = t.first ? v[jj] : v[jj] + r[jj];
+            __stcg(Srow + (int64_t)(c + jj) * FV_2D, empty ? nanv : x * scale);
+        }
+    }
+}
 
 struct StatsPolicy {
     using Params = StatsParams;
     using EpiState = NoEpiState;
-    struct Tile { int nkb; int t; int64_t img, r0; };
+    using Tile = SegTile;
     static constexpr bool BF16 = false, A_MN = true, B_MN = true, EPI_READS_STAGES = false, MANUAL = true;
     static constexpr int KT = ST_KT;
     static constexpr int PASSES = 3, BLOCK_N = FV_K, STAGES = 4, KSTEPS = KT / 8, PGROUPS = 4;
@@ -196,14 +252,9 @@ struct StatsPolicy {
     static constexpr int A_BYTES = (FV_2D / 32) * A_LBO, B_BYTES = (FV_K / 32) * B_LBO, SCRATCH_BYTES = 0;
     static constexpr int TMA_BYTES = 0;
     __device__ static void prefetch(const Params&) {}
-    __device__ static int num_tiles(const Params& p) { return (int)p.n_images; }
-    __device__ static int tile_at(const Params&, int it, int n) { return strided_tile(it, n); }
-    __device__ static Tile tile(const Params& p, int i)
-    {
-        const int64_t r0 = p.offsets[i];
-        const int t = (int)(p.offsets[i + 1] - r0);
-        return {(t + KT - 1) / KT, t, (int64_t)i, r0};
-    }
+    __device__ static int num_tiles(const Params& p) { return (int)p.n_images * *p.smax; }
+    __device__ static int tile_at(const Params& p, int it, int) { return seg_tile_at(p, it); }
+    __device__ static Tile tile(const Params& p, int i) { return seg_tile(p, i, KT); }
     __device__ static void load(const Params&, const Tile&, int, uint8_t*, uint8_t*, uint8_t*, uint8_t*, uint64_t*) {}
     // producer warp pw owns descriptor rows [RPW pw, RPW pw + RPW) of the stage; rows past the
     // end of the image are written as zeros (that is what makes ragged T exact)
@@ -215,7 +266,7 @@ struct StatsPolicy {
         // Q: 64 float4 per row -> two per lane
 #pragma unroll
         for (int rr = 0; rr < RPW; ++rr) {
-            const int tt = kb * KT + pw * RPW + rr;
+            const int tt = (t.kb0 + kb) * KT + pw * RPW + rr;
             const float* qrow = p.q + (t.r0 + tt) * FV_K;
 #pragma unroll
             for (int h2 = 0; h2 < 2; ++h2) g.q[rr * 2 + h2] = tt < t.t ? ldg4(qrow + (lane + 32 * h2) * 4) : z;
@@ -223,7 +274,7 @@ struct StatsPolicy {
         // Y: 16 float4 per row -> half a warp per row, two rows per pass
 #pragma unroll
         for (int pr = 0; pr < RPW / 2; ++pr) {
-            const int tt = kb * KT + pw * RPW + pr * 2 + (lane >> 4);
+            const int tt = (t.kb0 + kb) * KT + pw * RPW + pr * 2 + (lane >> 4);
             g.y[pr] = tt < t.t ? ldg4(p.y + (t.r0 + tt) * FV_D + (lane & 15) * 4) : z;
         }
     }
@@ -267,11 +318,12 @@ struct StatsPolicy {
             *reinterpret_cast<float4*>(a_hi + 2 * A_LBO + off) = h;
             *reinterpret_cast<float4*>(a_lo + 2 * A_LBO + off) = l;
         }
-        if (kb + PGROUPS >= t.nkb) {                       // this group's last k-block of the image
+        const int kba = t.kb0 + kb;                        // k-block index inside the image (tiles are segments of an image)
+        if (kba + PGROUPS >= (t.t + KT - 1) / KT) {        // this group's last k-block of the image
             // slot by the k-block's position in the image, not by the group: which rows meet in a
             // partial sum then does not depend on the tiles this CTA handled before (same bits for
             // any chunking of the batch)
-            float4* dst = reinterpret_cast<float4*>(p.s0part + ((t.img * (PGROUPS * 4) + (kb % PGROUPS) * 4 + pw) * FV_K));
+            float4* dst = reinterpret_cast<float4*>(p.s0part + ((t.img * (PGROUPS * 4) + (kba % PGROUPS) * 4 + pw) * FV_K));
             dst[lane] = ps.s0[0];
             dst[lane + 32] = ps.s0[1];
             ps.s0[0] = ps.s0[1] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -282,21 +334,12 @@ struct StatsPolicy {
     __device__ static void epilogue(const Params& p, const Tile& t, uint32_t tmem, int quarter, int lane, uint8_t*,
                                     EpiState&)
     {
+        if (t.skip) return;                                // past the image's last segment
         const int e = quarter * 32 + lane;                 // operand row: [0,64) = y*y, [64,128) = y
         const int n = e < FV_D ? FV_D + e : e - FV_D;      // column in the [ s1 | s2 ] layout
-        float* Simg = p.S + t.img * (int64_t)FV_K * FV_2D;
-        const float inv_t = 1.f / (float)t.t;              // T == 0 -> NaN, like the reference
-        const bool empty = t.nkb == 0;
-        const float nanv = __int_as_float(0x7fc00000);
-#pragma unroll 1
-        for (int c = 0; c < FV_K; c += 32) {
-            float v[32];
-            __syncwarp();
-            tmem_ld32(tmem + c, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int jj = 0; jj < 32; ++jj) Simg[(int64_t)(c + jj) * FV_2D + n] = empty ? nanv : v[jj] * inv_t;
-        }
+        // the epilogue warps have nothing else to do here (the producers take the zeroth-order sums), so they fold;
+        // the last segment applies 1 / T (T == 0 -> NaN, like the reference)
+        seg_fold(t, p.S + t.img * (int64_t)FV_K * FV_2D + n, tmem, t.last ? 1.f / (float)t.t : 1.f);
     }
 };
 
@@ -317,8 +360,6 @@ struct Stats16Params {
     StatsParams b;
     const float* rinv;                        // [rows + 16, 4]: per-descriptor softmax normaliser (slot 0 of 16 bytes)
     const int* flag;                          // != 0: operands out of fp16 range -> this kernel does nothing
-    const int* smax;                          // segments per image slot: max over the images of ceil(k-blocks / segk), >= 1 (device)
-    int segk;                                 // k-blocks (16 descriptors each) per statistics segment
     float sc_y, un1, un2;                     // 2^-e, 2^(e-14), 2^(2e-14)
 };
 
@@ -334,14 +375,7 @@ struct Stats16Params {
 struct Stats16Policy {
     using Params = Stats16Params;
     struct EpiState { float2 s0; };
-    // A tile of the skeleton is one SEGMENT of an image: `segk` k-blocks accumulated from zero in one of the two TMEM
-    // accumulators and folded into the image's S rows (global memory, L2-resident, fp32 round-to-nearest adds) by the
-    // epilogue warps while the next segment is being multiplied into the other accumulator.  tcgen05.mma adds every K = 16
-    // slice to the accumulator with truncation; accumulated over a whole 2 000-descriptor image that bias, amplified by the
-    // cancellation in d_sigma, put 46 of the 8 189 images of the C2 batch 1e-4 .. 2.6e-4 off the fp64 result.
-    // Every image gets *p.smax consecutive tiles on ONE CTA (the folds of an image are ordered: same threads, same
-    // addresses); tiles past the image's last segment are empty and skipped.
-    struct Tile { int nkb; int t; int64_t img, r0; int kb0; bool first, last, skip; };
+    using Tile = SegTile;                      // one segment of an image (see StatsParams)
     static constexpr bool BF16 = false, F16 = true, A_MN = true, B_MN = true, EPI_READS_STAGES = true, MANUAL = true;
     // The fold of a finished segment belongs to four warps of its own: the epilogue warps have to release every operand stage
     // after reading it for the zeroth-order sums, and with the fold on them the ring stalled (4.6 -> 5.9 ms for the kernel).
@@ -360,30 +394,9 @@ struct Stats16Policy {
     __device__ static bool enabled(const Params& p) { return *p.flag == 0; }
     __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.qh_map); tma_prefetch_desc(&p.ql_map); tma_prefetch_desc(&p.y_map); }
     __device__ static void init_stage(uint8_t* extra) { mbar_init(reinterpret_cast<uint64_t*>(extra + BAR_OFF), 1); }
-    __device__ static int num_tiles(const Params& p) { return (int)p.b.n_images * *p.smax; }
-    __device__ static int tile_at(const Params& p, int it, int)
-    {
-        const int smax = *p.smax;
-        const long long img = (long long)blockIdx.x + (long long)(it / smax) * gridDim.x;
-        return img < p.b.n_images ? (int)(img * smax + it % smax) : -1;
-    }
-    __device__ static Tile tile(const Params& p, int i)
-    {
-        const int smax = *p.smax;
-        const int64_t img = i / smax;
-        const int seg = i - (int)img * smax;
-        const int64_t r0 = p.b.offsets[img];
-        const int t = (int)(p.b.offsets[img + 1] - r0);
-        const int total = (t + KT - 1) / KT, kb0 = seg * p.segk;
-        const int left = total - kb0;
-        Tile tl;
-        tl.nkb = left <= 0 ? 0 : (left < p.segk ? left : p.segk);
-        tl.t = t; tl.img = img; tl.r0 = r0; tl.kb0 = kb0;
-        tl.first = seg == 0;
-        tl.last = left <= p.segk;                          // also true for an empty image (its only tile writes NaN)
-        tl.skip = seg > 0 && left <= 0;
-        return tl;
-    }
+    __device__ static int num_tiles(const Params& p) { return (int)p.b.n_images * *p.b.smax; }
+    __device__ static int tile_at(const Params& p, int it, int) { return seg_tile_at(p.b, it); }
+    __device__ static Tile tile(const Params& p, int i) { return seg_tile(p.b, i, KT); }
     __device__ static void load(const Params& p, const Tile& t, int kb, uint8_t*, uint8_t*, uint8_t* b_hi, uint8_t* b_lo, uint64_t*)
     {
         uint8_t* extra = b_lo + B_BYTES;
@@ -515,7 +528,7 @@ struct StatsGatedPolicy : StatsPolicy {
     using Params = Stats16Params;
     __device__ static bool enabled(const Params& p) { return *p.flag != 0; }
     __device__ static int num_tiles(const Params& p) { return StatsPolicy::num_tiles(p.b); }
-    __device__ static int tile_at(const Params&, int it, int n) { return strided_tile(it, n); }
+    __device__ static int tile_at(const Params& p, int it, int n) { return StatsPolicy::tile_at(p.b, it, n); }
     __device__ static Tile tile(const Params& p, int i) { return StatsPolicy::tile(p.b, i); }
     __device__ static void prefetch(const Params&) {}
     __device__ static void load(const Params&, const Tile&, int, uint8_t*, uint8_t*, uint8_t*, uint8_t*, uint64_t*) {}
@@ -1258,6 +1271,12 @@ int tc_fv_stats(const TcFvPlan& pl, const pvs_model* g, const float* y, const in
     if (n_images <= 0) return PVS_OK;
     StatsParams p{};
     p.y = y; p.q = pl.q; p.offsets = offsets; p.S = pl.S; p.s0part = pl.s0part; p.n_images = n_images;
+    int seg = 2;                                               // 128-descriptor tiles per segment (table in DESIGN.md)
+    if (const char* e = getenv("PVS_FV_SEG")) { const int v = atoi(e); if (v >= 1) seg = v; }
+    p.segk = seg * (128 / ST_KT);
+    p.smax = pl.flag + 1;                                      // the int behind the range flag (cleared by tc_fv_begin)
+    fv_smax_kernel<<<1, 1024, 0, st>>>(offsets, n_images, p.segk, pl.flag + 1);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     if (!pl.fp16x2) return launch_tc<StatsPolicy>(p, (int)n_images, st);
     // fp16x2 kernel, and behind it the 3xTF32 kernel that only runs when the range flag was raised
     Stats16Params h{};
@@ -1268,15 +1287,7 @@ int tc_fv_stats(const TcFvPlan& pl, const pvs_model* g, const float* y, const in
     if ((rc = make_tmap_2d(&h.qh_map, pl.q, true, rows, FV_K, FV_K, 64, Stats16Policy::KT))) return rc;
     if ((rc = make_tmap_2d(&h.ql_map, (const __half*)pl.q + (size_t)rows * FV_K, true, rows, FV_K, FV_K, 64, Stats16Policy::KT))) return rc;
     if ((rc = make_tmap_2d(&h.y_map, y, false, rows, FV_D, FV_D, 32, Stats16Policy::KT))) return rc;
-    if (!fallback_only) {
-        int seg = 2;                                           // 128-descriptor tiles per segment, as in the fused kernel
-        if (const char* e = getenv("PVS_FV_SEG")) { const int v = atoi(e); if (v >= 1) seg = v; }
-        h.segk = seg * 8;
-        h.smax = pl.flag + 1;                                  // the int behind the range flag (cleared by tc_fv_begin)
-        fv_smax_kernel<<<1, 1024, 0, st>>>(offsets, n_images, h.segk, pl.flag + 1);
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-        if ((rc = launch_tc<Stats16Policy>(h, (int)n_images, st))) return rc;
-    }
+    if (!fallback_only && (rc = launch_tc<Stats16Policy>(h, (int)n_images, st))) return rc;
     return launch_tc<StatsGatedPolicy>(h, (int)n_images, st);
 }
 
