@@ -426,7 +426,7 @@ extern "C" int pvs_vlad_encode(const pvs_model* km, const pvs_model* pca, const 
 }
 
 // ---- Fisher vector ---------------------------------------------------------------------
-struct FvWs { size_t y, q, s, s0, total; };
+struct FvWs { size_t y, q, s, s0, smax, total; };
 static FvWs fv_ws(const pvs_model* g, const pvs_model* pca, int64_t rows, int64_t n_images)
 {
     FvWs w{};
@@ -435,6 +435,7 @@ static FvWs fv_ws(const pvs_model* g, const pvs_model* pca, int64_t rows, int64_
     w.q = off; off += align_up((size_t)rows * g->k * 4, 256);
     w.s = off; off += align_up((size_t)n_images * g->k * (2 * g->d + 1) * 4, 256);
     w.s0 = off; off += align_up((size_t)n_images * TC_FV_S0_PARTS * g->k * 4, 256);
+    w.smax = off; off += 256;                              // one int: statistics segments per image slot
     w.total = off + 256;
     return w;
 }
@@ -520,7 +521,7 @@ extern "C" int pvs_fv_encode(const pvs_model* g, const pvs_model* pca, const flo
     if (int rc = PVS_STAGE(ST_GMM_SOFTMAX, st, launch_row_softmax(q, total_rows, g->k, argmax_out, st))) return rc;
     if (g_path.load() != PVS_PATH_SIMT && tc_fv_stats_generic_supported(g, n_images)) {
         float* s0part = (float*)(ws + w.s0);
-        if (int rc = PVS_STAGE(ST_TC_FV_STATS, st, tc_fv_stats_generic(q, y, g->d, offsets, n_images, S, s0part, st))) return rc;
+        if (int rc = PVS_STAGE(ST_TC_FV_STATS, st, tc_fv_stats_generic(q, y, g->d, offsets, n_images, S, s0part, (int*)(ws + w.smax), st))) return rc;
         return PVS_STAGE(ST_FV_FINALIZE, st, launch_fv_finalize(S, 2 * g->d, s0part, TC_FV_S0_PARTS, offsets, g, n_images, power,
                                                                  norm_order, eps, out, st));
     }

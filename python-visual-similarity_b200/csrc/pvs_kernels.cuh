@@ -103,7 +103,7 @@ int tc_gemm_nt(const float* a, int64_t lda, int a_cols, bool square_cat, const f
 
 bool tc_fv_stats_generic_supported(const pvs_model* g, int64_t n_images);
 int tc_fv_stats_generic(const float* q, const float* y, int d, const int64_t* offsets, int64_t n_images, float* S,
-                        float* s0part, cudaStream_t st);
+                        float* s0part, int* smax_dev, cudaStream_t st);   // smax_dev: one int of scratch (segments per image slot)
 
 // similarity + fused top-k on bf16 tensor cores (pvs_tc_sim.cu)
 bool tc_sim_supported(int dtype, int64_t n_q, int64_t n_db, int64_t d, int k);

@@ -219,24 +219,26 @@ __device__ __forceinline__ SegTile seg_tile(const StatsParams& p, int i, int kt)
     return tl;
 }
 // fold of a finished segment by one warp (its TMEM lane quarter): 32 running sums per trip to L2
-__device__ __forceinline__ void seg_fold(const SegTile& t, float* Srow, uint32_t tmem, float scale)
+__device__ __forceinline__ void seg_fold(const SegTile& t, float* Srow, uint32_t tmem, float scale, int64_t ld = FV_2D, bool live = true)
 {
     const bool empty = t.t == 0;
     const float nanv = __int_as_float(0x7fc00000);
 #pragma unroll 1
     for (int c = 0; c < FV_K; c += 32) {
         float v[32], r[32];
-        if (!t.first) {
+        if (!t.first && live) {
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) r[jj] = __ldcg(Srow + (int64_t)(c + jj) * FV_2D);
+            for (int jj = 0; jj < 32; ++jj) r[jj] = __ldcg(Srow + (int64_t)(c + jj) * ld);
         }
         __syncwarp();
         tmem_ld32(tmem + c, v);
         tmem_ld_wait();
+        if (live) {
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {
-            const float x = t.first ? v[jj] : v[jj] + r[jj];
-            __stcg(Srow + (int64_t)(c + jj) * FV_2D, empty ? nanv : x * scale);
+            for (int jj = 0; jj < 32; ++jj) {
+                const float x = t.first ? v[jj] : v[jj] + r[jj];
+                __stcg(Srow + (int64_t)(c + jj) * ld, empty ? nanv : x * scale);
+            }
         }
     }
 }
@@ -562,12 +564,14 @@ struct StatsGenParams {
     float* s0part;                            // [n_images, 16, 256]
     int64_t n_images;
     int d, n_mt;
+    const int* smax;                          // segments per (image, M tile) slot, see StatsParams
+    int segk;
 };
 
 struct StatsGenPolicy {
     using Params = StatsGenParams;
     using EpiState = NoEpiState;
-    struct Tile { int nkb; int t; int mt; int64_t img, r0; };
+    struct Tile : SegTile { int mt; };         // one segment of (image, M tile of 128 augmented columns)
     static constexpr bool BF16 = false, A_MN = true, B_MN = true, EPI_READS_STAGES = false, MANUAL = true;
     static constexpr int KT = ST_KT;
     static constexpr int PASSES = 3, BLOCK_N = FV_K, STAGES = 4, KSTEPS = KT / 8, PGROUPS = 4;
@@ -576,14 +580,28 @@ struct StatsGenPolicy {
     static constexpr int RPW = KT / 4;
     static_assert(PGROUPS * 4 == TC_FV_S0_PARTS, "one partial per producer warp");
     __device__ static void prefetch(const Params&) {}
-    __device__ static int num_tiles(const Params& p) { return (int)(p.n_images * p.n_mt); }
-    __device__ static int tile_at(const Params&, int it, int n) { return strided_tile(it, n); }
+    __device__ static int num_tiles(const Params& p) { return (int)(p.n_images * p.n_mt) * *p.smax; }
+    __device__ static int tile_at(const Params& p, int it, int)
+    {
+        const int smax = *p.smax;
+        const long long u = (long long)blockIdx.x + (long long)(it / smax) * gridDim.x;    // (image, M tile) unit
+        return u < p.n_images * p.n_mt ? (int)(u * smax + it % smax) : -1;
+    }
     __device__ static Tile tile(const Params& p, int i)
     {
-        const int64_t img = i / p.n_mt;
+        const int smax = *p.smax;
+        const int u = i / smax, seg = i - u * smax;
+        const int64_t img = u / p.n_mt;
         const int64_t r0 = p.offsets[img];
         const int t = (int)(p.offsets[img + 1] - r0);
-        return {(t + KT - 1) / KT, t, i - (int)img * p.n_mt, img, r0};
+        const int total = (t + KT - 1) / KT, kb0 = seg * p.segk;
+        const int left = total - kb0;
+        Tile tl;
+        tl.nkb = left <= 0 ? 0 : (left < p.segk ? left : p.segk);
+        tl.t = t; tl.img = img; tl.r0 = r0; tl.kb0 = kb0;
+        tl.first = seg == 0; tl.last = left <= p.segk; tl.skip = seg > 0 && left <= 0;
+        tl.mt = u - (int)img * p.n_mt;
+        return tl;
     }
     __device__ static void load(const Params&, const Tile&, int, uint8_t*, uint8_t*, uint8_t*, uint8_t*, uint64_t*) {}
     struct Regs { float4 q[RPW * 2]; float4 y[RPW]; };
@@ -600,7 +618,7 @@ struct StatsGenPolicy {
         const int a0 = t.mt * 128 + lane * 4;                  // this lane's four augmented columns
 #pragma unroll
         for (int rr = 0; rr < RPW; ++rr) {
-            const int tt = kb * KT + pw * RPW + rr;
+            const int tt = (t.kb0 + kb) * KT + pw * RPW + rr;
             const bool valid = tt < t.t;
             const float* qrow = p.q + (t.r0 + tt) * FV_K;
 #pragma unroll
@@ -635,9 +653,10 @@ struct StatsGenPolicy {
             *reinterpret_cast<float4*>(a_hi + off) = h;
             *reinterpret_cast<float4*>(a_lo + off) = l;
         }
-        if (kb + PGROUPS >= t.nkb) {                       // this group's last k-block of the tile
+        const int kba = t.kb0 + kb;                        // k-block index inside the image (tiles are segments)
+        if (kba + PGROUPS >= (t.t + KT - 1) / KT) {        // this group's last k-block of the (image, M tile)
             if (t.mt == 0) {
-                float4* dst = reinterpret_cast<float4*>(p.s0part + ((t.img * (PGROUPS * 4) + (kb % PGROUPS) * 4 + pw) * FV_K));
+                float4* dst = reinterpret_cast<float4*>(p.s0part + ((t.img * (PGROUPS * 4) + (kba % PGROUPS) * 4 + pw) * FV_K));
                 dst[lane] = ps.s0[0];
                 dst[lane + 32] = ps.s0[1];
             }
@@ -650,25 +669,12 @@ struct StatsGenPolicy {
     __device__ static void epilogue(const Params& p, const Tile& t, uint32_t tmem, int quarter, int lane, uint8_t*,
                                     EpiState&)
     {
+        if (t.skip) return;                                // past the last segment
         const int a = t.mt * 128 + quarter * 32 + lane;    // augmented column owned by this thread
         const int ld = 2 * p.d;
         const int col = a < p.d ? p.d + a : a - p.d;       // [ s1 | s2 ] layout
-        const bool live = a < ld;
-        float* Simg = p.S + t.img * (int64_t)FV_K * ld;
-        const float inv_t = 1.f / (float)t.t;              // T == 0 -> NaN, like the reference
-        const bool empty = t.nkb == 0;
-        const float nanv = __int_as_float(0x7fc00000);
-#pragma unroll 1
-        for (int c = 0; c < FV_K; c += 32) {
-            float v[32];
-            __syncwarp();
-            tmem_ld32(tmem + c, v);
-            tmem_ld_wait();
-            if (live) {
-#pragma unroll
-                for (int jj = 0; jj < 32; ++jj) Simg[(int64_t)(c + jj) * ld + col] = empty ? nanv : v[jj] * inv_t;
-            }
-        }
+        // fold of the segment (the epilogue warps are otherwise idle); the last one applies 1 / T (T == 0 -> NaN)
+        seg_fold(t, p.S + t.img * (int64_t)FV_K * ld + col, tmem, t.last ? 1.f / (float)t.t : 1.f, ld, a < ld);
     }
 };
 
@@ -1273,11 +1279,17 @@ int tc_fv_stats(const TcFvPlan& pl, const pvs_model* g, const float* y, const in
     p.y = y; p.q = pl.q; p.offsets = offsets; p.S = pl.S; p.s0part = pl.s0part; p.n_images = n_images;
     int seg = 2;                                               // 128-descriptor tiles per segment (table in DESIGN.md)
     if (const char* e = getenv("PVS_FV_SEG")) { const int v = atoi(e); if (v >= 1) seg = v; }
+    // fp16x2: K = 16 per MMA, `seg` tiles of 128 descriptors per segment; 3xTF32: K = 8 per MMA, i.e. twice the accumulation
+    // steps per descriptor, so half the descriptors per segment.  Two ints behind the range flag hold the segment counts.
     p.segk = seg * (128 / ST_KT);
-    p.smax = pl.flag + 1;                                      // the int behind the range flag (cleared by tc_fv_begin)
+    p.smax = pl.flag + 1;
+    StatsParams pt = p;
+    pt.segk = p.segk > 1 ? p.segk / 2 : 1;
+    pt.smax = pl.flag + 2;
     fv_smax_kernel<<<1, 1024, 0, st>>>(offsets, n_images, p.segk, pl.flag + 1);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    if (!pl.fp16x2) return launch_tc<StatsPolicy>(p, (int)n_images, st);
+    fv_smax_kernel<<<1, 1024, 0, st>>>(offsets, n_images, pt.segk, pl.flag + 2);
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+    if (!pl.fp16x2) return launch_tc<StatsPolicy>(pt, (int)n_images, st);
     // fp16x2 kernel, and behind it the 3xTF32 kernel that only runs when the range flag was raised
     Stats16Params h{};
     h.b = p; h.flag = pl.flag; h.rinv = pl.rinv;
@@ -1288,6 +1300,7 @@ int tc_fv_stats(const TcFvPlan& pl, const pvs_model* g, const float* y, const in
     if ((rc = make_tmap_2d(&h.ql_map, (const __half*)pl.q + (size_t)rows * FV_K, true, rows, FV_K, FV_K, 64, Stats16Policy::KT))) return rc;
     if ((rc = make_tmap_2d(&h.y_map, y, false, rows, FV_D, FV_D, 32, Stats16Policy::KT))) return rc;
     if (!fallback_only && (rc = launch_tc<Stats16Policy>(h, (int)n_images, st))) return rc;
+    h.b = pt;                                                  // the gated 3xTF32 kernel walks its own (shorter) segments
     return launch_tc<StatsGatedPolicy>(h, (int)n_images, st);
 }
 
@@ -1298,14 +1311,20 @@ bool tc_fv_stats_generic_supported(const pvs_model* g, int64_t n_images)
 }
 
 int tc_fv_stats_generic(const float* q, const float* y, int d, const int64_t* offsets, int64_t n_images, float* S,
-                        float* s0part, cudaStream_t st)
+                        float* s0part, int* smax_dev, cudaStream_t st)
 {
     if (n_images <= 0) return PVS_OK;
     PVS_CHECK((((uintptr_t)q) & 15) == 0, PVS_ERR_BAD_ARG, "posterior buffer must be 16-byte aligned");
     StatsGenParams p{};
     p.y = y; p.q = q; p.offsets = offsets; p.S = S; p.s0part = s0part; p.n_images = n_images;
     p.d = d; p.n_mt = (2 * d + 127) / 128;
+    int seg = 2;                                               // 128-descriptor tiles per statistics segment
+    if (const char* e = getenv("PVS_FV_SEG")) { const int v = atoi(e); if (v >= 1) seg = v; }
+    p.segk = seg * (128 / ST_KT) > 1 ? seg * (128 / ST_KT) / 2 : 1;   // 3xTF32: K = 8 per MMA, half the descriptors per segment
+    p.smax = smax_dev;
     PVS_CUDA(cudaMemsetAsync(s0part, 0, (size_t)n_images * TC_FV_S0_PARTS * FV_K * 4, st));
+    fv_smax_kernel<<<1, 1024, 0, st>>>(offsets, n_images, p.segk, smax_dev);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     return launch_tc<StatsGenPolicy>(p, (int)(n_images * p.n_mt), st);
 }
 

@@ -24,6 +24,7 @@ struct GemmNtParams {
     int64_t lda, ldc, m;
     float alpha;
     int n, a_cols, nkb, m_blocks, n_blocks;
+    int segk, nseg;                    // k-blocks per accumulation segment, segments per output tile
 };
 struct GemmNtState {};
 struct GRegs { float4 v[8]; };
@@ -33,23 +34,33 @@ struct GemmNtPolicy {
     using Params = GemmNtParams;
     using EpiState = GemmNtState;
     using Regs = GRegs;
-    struct Tile { int nkb, mb, nb; };
+    // A tile of the skeleton is one K-SEGMENT of an output tile: the tensor core accumulates `segk` k-blocks from zero, the
+    // epilogue adds the segment to C (the first one writes alpha * acc + bias, the others C += alpha * acc; the tile was
+    // written by the same threads a moment ago and is still in L2).  tcgen05.mma truncates when it adds a K-slice to the
+    // accumulator; over the 514-long contraction of the VGG16-PCA logits (195 accumulation steps) that put 9 of 4 096 images
+    // 1e-4 .. 1.8e-4 off the fp64 result.  The segments of an output tile run back to back on one CTA pair.
+    struct Tile { int nkb, mb, nb, kb0; bool first; };
     static constexpr bool BF16 = false, MANUAL = true, B_RESIDENT = false, ACC_INIT = false, TILE_SYNC = false;
     static constexpr int PASSES = 3, BLOCK_N = 256, KSTEPS = 4, NKB_RES = 0, STAGES = 3, PGROUPS = 3;
     static constexpr int A_BYTES = 128 * 128, B_BYTES = 128 * 128, SCRATCH_BYTES = 0, TMA_BYTES = 2 * B_BYTES;
     __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.b_hi); tma_prefetch_desc(&p.b_lo); }
-    __device__ static int num_tiles(const Params& p) { return p.m_blocks * p.n_blocks; }
-    __device__ static int tile_at(const Params&, int it, int pair, int n_pairs, int n)
+    __device__ static int num_tiles(const Params& p) { return p.m_blocks * p.n_blocks * p.nseg; }
+    __device__ static int tile_at(const Params& p, int it, int pair, int n_pairs, int)
     {
-        const long long t = (long long)pair + (long long)it * n_pairs;
-        return t < n ? (int)t : -1;
+        const long long u = (long long)pair + (long long)(it / p.nseg) * n_pairs;
+        return u < (long long)p.m_blocks * p.n_blocks ? (int)(u * p.nseg + it % p.nseg) : -1;
     }
-    __device__ static Tile tile(const Params& p, int i) { return {p.nkb, i / p.n_blocks, i % p.n_blocks}; }
+    __device__ static Tile tile(const Params& p, int i)
+    {
+        const int u = i / p.nseg, seg = i - u * p.nseg, kb0 = seg * p.segk;
+        const int left = p.nkb - kb0;
+        return {left < p.segk ? left : p.segk, u / p.n_blocks, u % p.n_blocks, kb0, seg == 0};
+    }
     __device__ static void load(const Params& p, const Tile& t, int kb, int rank, uint8_t*, uint8_t*, uint8_t* b_hi,
                                 uint8_t* b_lo, uint64_t* bar)
     {
-        tma_load_2d_pair(b_hi, &p.b_hi, bar, kb * 32, t.nb * BLOCK_N + rank * 128);
-        tma_load_2d_pair(b_lo, &p.b_lo, bar, kb * 32, t.nb * BLOCK_N + rank * 128);
+        tma_load_2d_pair(b_hi, &p.b_hi, bar, (t.kb0 + kb) * 32, t.nb * BLOCK_N + rank * 128);
+        tma_load_2d_pair(b_lo, &p.b_lo, bar, (t.kb0 + kb) * 32, t.nb * BLOCK_N + rank * 128);
     }
     // element `col` of the (virtual) operand row A'
     __device__ static float a_elem(const Params& p, const float* row, int col)
@@ -69,7 +80,7 @@ struct GemmNtPolicy {
     }
     __device__ static void fetch(const Params& p, const Tile& t, int kb, int rank, int pw, int lane, Regs& g)
     {
-        const int col = kb * 32 + (lane & 7) * 4;
+        const int col = (t.kb0 + kb) * 32 + (lane & 7) * 4;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int64_t gr = (int64_t)t.mb * 256 + rank * 128 + pw * 32 + i * 4 + (lane >> 3);
@@ -116,10 +127,23 @@ struct GemmNtPolicy {
             tmem_ld_wait();
             const int col0 = t.nb * BLOCK_N + c0;
             if (row >= p.m || col0 >= p.n) continue;
+            if (t.first) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int col = col0 + j;
-                v[j] = p.alpha * v[j] + ((p.bias && col < p.n) ? p.bias[col] : 0.f);
+                for (int j = 0; j < 32; ++j) {
+                    const int col = col0 + j;
+                    v[j] = p.alpha * v[j] + ((p.bias && col < p.n) ? p.bias[col] : 0.f);
+                }
+            } else if (vec && col0 + 32 <= p.n) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 o = __ldcg(reinterpret_cast<const float4*>(crow + col0 + j));
+                    v[j] = fmaf(p.alpha, v[j], o.x); v[j + 1] = fmaf(p.alpha, v[j + 1], o.y);
+                    v[j + 2] = fmaf(p.alpha, v[j + 2], o.z); v[j + 3] = fmaf(p.alpha, v[j + 3], o.w);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (col0 + j < p.n) v[j] = fmaf(p.alpha, v[j], __ldcg(crow + col0 + j));
             }
             if (vec && col0 + 32 <= p.n) {
 #pragma unroll
@@ -202,6 +226,9 @@ int tc_gemm_nt(const float* a, int64_t lda, int a_cols, bool square_cat, const f
     if ((rc = make_tmap_2d(&p.b_lo, b_lo, false, n, b_ld, b_ld, 32, 128))) return rc;
     p.a = a; p.lda = lda; p.a_cols = a_cols; p.bias = bias; p.c = c; p.ldc = ldc; p.m = m; p.n = n; p.alpha = alpha;
     p.nkb = b_ld / 32;
+    p.segk = 4;                                                // 128 K-elements = 48 accumulation steps per segment
+    if (const char* e = getenv("PVS_GEMM_SEGK")) { const int v = atoi(e); if (v >= 1) p.segk = v; }
+    p.nseg = (p.nkb + p.segk - 1) / p.segk;
     p.m_blocks = (int)ceil_div(m, 256);
     p.n_blocks = (int)ceil_div(n, 256);
     const int tiles = p.m_blocks * p.n_blocks;
