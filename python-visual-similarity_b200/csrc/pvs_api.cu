@@ -435,7 +435,7 @@ static FvWs fv_ws(const pvs_model* g, const pvs_model* pca, int64_t rows, int64_
     w.q = off; off += align_up((size_t)rows * g->k * 4, 256);
     w.s = off; off += align_up((size_t)n_images * g->k * (2 * g->d + 1) * 4, 256);
     w.s0 = off; off += align_up((size_t)n_images * TC_FV_S0_PARTS * g->k * 4, 256);
-    w.smax = off; off += 256;                              // one int: statistics segments per image slot
+    w.smax = off; off += 256;                              // two ints: statistics segments per image slot
     w.total = off + 256;
     return w;
 }

@@ -1251,23 +1251,28 @@ int tc_fv_posterior(const TcFvPlan& pl, const pvs_model* g, const float* y, int6
     return tc2::launch_tc2<tc2::PostPairPolicy>(p, p.m_blocks, st);
 }
 
-// segments per image slot of the fp16x2 statistics kernel: max over the images of ceil(k-blocks / segk), at least 1
-__global__ void fv_smax_kernel(const int64_t* __restrict__ offsets, int64_t n_images, int segk, int* __restrict__ smax)
+// segments per image slot of the statistics kernels: max over the images of ceil(k-blocks / segk), at least 1, for two
+// segment lengths at once (smax[0] for segk_a, smax[1] for segk_b)
+__global__ void fv_smax_kernel(const int64_t* __restrict__ offsets, int64_t n_images, int segk_a, int segk_b, int* __restrict__ smax)
 {
-    int m = 1;
+    int ma = 1, mb = 1;
     for (int64_t i = threadIdx.x; i < n_images; i += blockDim.x) {
         const int t = (int)(offsets[i + 1] - offsets[i]);
-        const int nkb = (t + Stats16Policy::KT - 1) / Stats16Policy::KT;
-        m = max(m, (nkb + segk - 1) / segk);
+        const int nkb = (t + ST_KT - 1) / ST_KT;
+        ma = max(ma, (nkb + segk_a - 1) / segk_a);
+        mb = max(mb, (nkb + segk_b - 1) / segk_b);
     }
-    m = __reduce_max_sync(0xffffffffu, m);
-    __shared__ int part[32];
-    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = m;
+    ma = __reduce_max_sync(0xffffffffu, ma);
+    mb = __reduce_max_sync(0xffffffffu, mb);
+    __shared__ int part[2][32];
+    if ((threadIdx.x & 31) == 0) { part[0][threadIdx.x >> 5] = ma; part[1][threadIdx.x >> 5] = mb; }
     __syncthreads();
     if (threadIdx.x < 32) {
-        m = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 1;
-        m = __reduce_max_sync(0xffffffffu, m);
-        if (threadIdx.x == 0) *smax = m;
+        ma = threadIdx.x < (blockDim.x >> 5) ? part[0][threadIdx.x] : 1;
+        mb = threadIdx.x < (blockDim.x >> 5) ? part[1][threadIdx.x] : 1;
+        ma = __reduce_max_sync(0xffffffffu, ma);
+        mb = __reduce_max_sync(0xffffffffu, mb);
+        if (threadIdx.x == 0) { smax[0] = ma; smax[1] = mb; }
     }
 }
 
@@ -1286,9 +1291,8 @@ int tc_fv_stats(const TcFvPlan& pl, const pvs_model* g, const float* y, const in
     StatsParams pt = p;
     pt.segk = p.segk > 1 ? p.segk / 2 : 1;
     pt.smax = pl.flag + 2;
-    fv_smax_kernel<<<1, 1024, 0, st>>>(offsets, n_images, p.segk, pl.flag + 1);
-    fv_smax_kernel<<<1, 1024, 0, st>>>(offsets, n_images, pt.segk, pl.flag + 2);
-    g_launches.fetch_add(2, std::memory_order_relaxed);
+    fv_smax_kernel<<<1, 1024, 0, st>>>(offsets, n_images, p.segk, pt.segk, pl.flag + 1);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     if (!pl.fp16x2) return launch_tc<StatsPolicy>(pt, (int)n_images, st);
     // fp16x2 kernel, and behind it the 3xTF32 kernel that only runs when the range flag was raised
     Stats16Params h{};
@@ -1323,7 +1327,7 @@ int tc_fv_stats_generic(const float* q, const float* y, int d, const int64_t* of
     p.segk = seg * (128 / ST_KT) > 1 ? seg * (128 / ST_KT) / 2 : 1;   // 3xTF32: K = 8 per MMA, half the descriptors per segment
     p.smax = smax_dev;
     PVS_CUDA(cudaMemsetAsync(s0part, 0, (size_t)n_images * TC_FV_S0_PARTS * FV_K * 4, st));
-    fv_smax_kernel<<<1, 1024, 0, st>>>(offsets, n_images, p.segk, smax_dev);
+    fv_smax_kernel<<<1, 1024, 0, st>>>(offsets, n_images, p.segk, p.segk, smax_dev);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return launch_tc<StatsGenPolicy>(p, (int)(n_images * p.n_mt), st);
 }
