@@ -35,7 +35,10 @@ def run(tag):
     print(json.dumps({"variant": tag, "ms": round(e0.elapsed_time(e1) / 3, 3), "images_per_s": round(n / (e0.elapsed_time(e1) / 3) * 1e3),
                       "err_max": float(per.max()), "err_median": float(per.median()), "n_gt_1e-4": int((per > 1e-4).sum()),
                       "n_gt_5e-5": int((per > 5e-5).sum()), "worst": per.topk(3).indices.tolist()}), flush=True)
-for mode, segs in (("0", ("1", "2", "4", "16")), ("2", ("2", "4")), ("1", ("",))):
+plan = (("0", ("1", "2", "4", "16")), ("2", ("2", "4")), ("1", ("",)))
+if os.environ.get("VARIANTS"):                                  # e.g. VARIANTS=2:1,2:2,0:2
+    plan = tuple((v.split(":")[0], (v.split(":")[1],)) for v in os.environ["VARIANTS"].split(","))
+for mode, segs in plan:
     for seg in segs:
         os.environ["PVS_FV_FUSED"] = mode
         if seg: os.environ["PVS_FV_SEG"] = seg
