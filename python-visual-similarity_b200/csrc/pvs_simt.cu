@@ -25,76 +25,196 @@ constexpr unsigned FULL = 0xffffffffu;
 // generic NT contraction
 // =====================================================================================
 namespace {
-constexpr int G_BM = 128, G_BN = 64, G_BK = 16;
+constexpr int G_BM = 128, G_BK = 16;
 
-__global__ void __launch_bounds__(256)
+// C = alpha * A' B^T + bias, fp32 FMA on CUDA cores (the round-to-nearest path: long contractions, shapes the tensor kernels
+// do not take, PVS_PATH_SIMT).  CTA tile 128 x (16 TN), 256 threads, thread tile 8 x TN as 4-wide groups 64 apart (the float4
+// reads of a k-row are then conflict-free and the row reads broadcast), k-slabs of 16 double-buffered in shared memory with
+// the global loads of the next slab in flight during the FMAs.  Every output element is ONE accumulator that takes its
+// products in increasing k -- the same sequence whatever the tile width, so the wide and the narrow variant (and the earlier
+// single-buffered kernel) give bit-identical results.
+template <int TN, bool SQ>
+__global__ void __launch_bounds__(256, TN == 8 ? 2 : 3)
 gemm_nt_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb,
-               float* __restrict__ C, int64_t ldc, int64_t M, int N, int a_cols, int sq, float alpha,
+               float* __restrict__ C, int64_t ldc, int64_t M, int N, int n_base, int a_cols, float alpha,
                const float* __restrict__ bias)
 {
-    __shared__ __align__(16) float As[G_BK][G_BM + 4];
-    __shared__ __align__(16) float Bs[G_BK][G_BN + 4];
+    constexpr int BN = 16 * TN, NB = BN / 16, CG = TN >= 4 ? TN / 4 : 1, CW = TN >= 4 ? 4 : TN;
+    __shared__ __align__(16) float As[2][G_BK][G_BM + 4];
+    __shared__ __align__(16) float Bs[2][G_BK][BN + 4];
     const int tid = threadIdx.x;
     const int64_t m0 = (int64_t)blockIdx.x * G_BM;
-    const int n0 = blockIdx.y * G_BN;
-    const int kdim = sq ? 2 * a_cols : a_cols;
+    const int n0 = n_base + blockIdx.y * BN;
+    const int kdim = SQ ? 2 * a_cols : a_cols;
     const int ty = tid >> 4, tx = tid & 15;
     const int lc = tid & 15, lr = tid >> 4;
 
-    float acc[8][4];
+    float acc[8][TN];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-    for (int k0 = 0; k0 < kdim; k0 += G_BK) {
+    // this thread's rows of the two operands: one base pointer each, a constant step between them, validity as bit masks
+    // (the loads below are predicated, not branched over)
+    const float* arow = A + (m0 + lr) * lda;
+    const float* brow = B + (int64_t)(n0 + lr) * ldb;
+    const int64_t astep = 16 * lda, bstep = 16 * ldb;
+    unsigned amask = 0, bmask = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) amask |= (m0 + lr + 16 * i < M ? 1u : 0u) << i;
+#pragma unroll
+    for (int i = 0; i < NB; ++i) bmask |= (n0 + lr + 16 * i < N ? 1u : 0u) << i;
+    float pa[8], pb[NB];
+    auto gload = [&](int k0) {
         const int kk = k0 + lc;
+        const bool kin = kk < kdim;
+        const bool sqr = SQ && kk < a_cols;                  // A' = [a^2 | a]: the first a_cols columns are squares
+        const int kc = (SQ && kk >= a_cols) ? kk - a_cols : kk;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int r = lr + 16 * i;
-            const int64_t m = m0 + r;
             float v = 0.f;
-            if (m < M && kk < kdim) {
-                if (sq) {
-                    if (kk < a_cols) { const float a = A[m * lda + kk]; v = a * a; }
-                    else v = A[m * lda + (kk - a_cols)];
-                } else {
-                    v = A[m * lda + kk];
-                }
-            }
-            As[lc][r] = v;
+            if (kin && ((amask >> i) & 1u)) v = __ldg(arow + i * astep + kc);
+            pa[i] = sqr ? v * v : v;
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int r = lr + 16 * i;
-            const int n = n0 + r;
-            Bs[lc][r] = (n < N && kk < kdim) ? B[(int64_t)n * ldb + kk] : 0.f;
+        for (int i = 0; i < NB; ++i) {
+            float v = 0.f;
+            if (kin && ((bmask >> i) & 1u)) v = __ldg(brow + i * bstep + kk);
+            pb[i] = v;
         }
-        __syncthreads();
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) As[buf][lc][lr + 16 * i] = pa[i];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) Bs[buf][lc][lr + 16 * i] = pb[i];
+    };
+    const int n_slab = (kdim + G_BK - 1) / G_BK;
+    gload(0);
+    sstore(0);
+    __syncthreads();
+#pragma unroll 1
+    for (int s = 0; s < n_slab; ++s) {
+        const int buf = s & 1;
+        if (s + 1 < n_slab) gload((s + 1) * G_BK);
 #pragma unroll
         for (int k = 0; k < G_BK; ++k) {
-            const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
-            const float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
-            const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
             const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            const float bb[4] = {b.x, b.y, b.z, b.w};
+            float bb[TN];
+            if constexpr (TN >= 4) {
+#pragma unroll
+                for (int g = 0; g < CG; ++g) {
+                    const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][g * 64 + tx * 4]);
+                    bb[4 * g] = b.x; bb[4 * g + 1] = b.y; bb[4 * g + 2] = b.z; bb[4 * g + 3] = b.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < TN; ++j) bb[j] = Bs[buf][k][tx * TN + j];
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
         }
+        if (s + 1 < n_slab) sstore(buf ^ 1);                   // nobody reads that buffer between the two barriers
         __syncthreads();
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const int64_t m = m0 + ty * 8 + i;
+        const int64_t m = m0 + (i >> 2) * 64 + ty * 4 + (i & 3);
         if (m >= M) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int n = n0 + tx * 4 + j;
+        for (int j = 0; j < TN; ++j) {
+            const int n = n0 + (TN >= 4 ? (j / CW) * 64 + tx * 4 + (j % CW) : tx * TN + j);
             if (n < N) C[m * ldc + n] = alpha * acc[i][j] + (bias ? bias[n] : 0.f);
         }
     }
+}
+
+// The last R <= 4 columns of an N that is a few columns past a multiple of 128 (the VGG16 PCA has N = 257): a 32-wide tile
+// for one column costs as much as for 32.  Here a thread owns a row and its R accumulators, the k-slabs of A go through
+// shared memory so that the global loads stay coalesced, and the products are added in increasing k like everywhere else.
+template <int R, bool SQ>
+__global__ void __launch_bounds__(256)
+gemm_nt_skinny_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb,
+                      float* __restrict__ C, int64_t ldc, int64_t M, int N, int n_base, int a_cols, float alpha,
+                      const float* __restrict__ bias)
+{
+    __shared__ float As[G_BK][256 + 1];
+    __shared__ float Bs[G_BK][R];
+    const int tid = threadIdx.x, lc = tid & 15, lr = tid >> 4;
+    const int64_t m0 = (int64_t)blockIdx.x * 256;
+    const int kdim = SQ ? 2 * a_cols : a_cols;
+    const float* arow = A + (m0 + lr) * lda;
+    const int64_t astep = 16 * lda;
+    unsigned amask = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) amask |= (m0 + lr + 16 * i < M ? 1u : 0u) << i;
+    float acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = 0.f;
+    for (int k0 = 0; k0 < kdim; k0 += G_BK) {
+        const int kk = k0 + lc;
+        const bool kin = kk < kdim;
+        const bool sqr = SQ && kk < a_cols;
+        const int kc = (SQ && kk >= a_cols) ? kk - a_cols : kk;
+        float pa[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            float v = 0.f;
+            if (kin && ((amask >> i) & 1u)) v = __ldg(arow + i * astep + kc);
+            pa[i] = sqr ? v * v : v;
+        }
+        __syncthreads();                                       // the previous slab has been consumed
+#pragma unroll
+        for (int i = 0; i < 16; ++i) As[lc][lr + 16 * i] = pa[i];
+        if (tid < G_BK * R) {
+            const int k = tid / R, r = tid - k * R, n = n_base + r;
+            Bs[k][r] = (n < N && k0 + k < kdim) ? __ldg(B + (int64_t)n * ldb + k0 + k) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < G_BK; ++k) {
+            const float a = As[k][tid];
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc[r] = fmaf(a, Bs[k][r], acc[r]);
+        }
+    }
+    const int64_t m = m0 + tid;
+    if (m < M) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int n = n_base + r;
+            if (n < N) C[m * ldc + n] = alpha * acc[r] + (bias ? bias[n] : 0.f);
+        }
+    }
+}
+
+template <bool SQ>
+int launch_gemm_nt_t(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                     int64_t M, int N, int a_cols, float alpha, const float* bias, cudaStream_t st)
+{
+    // full 128-column tiles on the wide variant, the remaining columns on a 64- or 32-wide tile or, if there are at most
+    // four of them, on the row-per-thread kernel (N = 257: 2 wide tiles + 1 column)
+    const int n_wide = N / 128, rem = N - 128 * n_wide, nb = 128 * n_wide;
+    const unsigned gm = (unsigned)ceil_div(M, G_BM);
+    if (n_wide > 0)
+        PVS_LAUNCH((gemm_nt_kernel<8, SQ>), dim3(gm, (unsigned)n_wide), 256, 0, st, A, lda, B, ldb, C, ldc, M, N, 0, a_cols, alpha, bias);
+    if (rem > 32)
+        PVS_LAUNCH((gemm_nt_kernel<4, SQ>), dim3(gm, (unsigned)ceil_div(rem, 64)), 256, 0, st, A, lda, B, ldb, C, ldc, M, N, nb, a_cols,
+                   alpha, bias);
+    else if (rem > 4)
+        PVS_LAUNCH((gemm_nt_kernel<2, SQ>), dim3(gm, 1), 256, 0, st, A, lda, B, ldb, C, ldc, M, N, nb, a_cols, alpha, bias);
+    else if (rem > 1)
+        PVS_LAUNCH((gemm_nt_skinny_kernel<4, SQ>), dim3((unsigned)ceil_div(M, 256)), 256, 0, st, A, lda, B, ldb, C, ldc, M, N, nb, a_cols,
+                   alpha, bias);
+    else if (rem == 1)
+        PVS_LAUNCH((gemm_nt_skinny_kernel<1, SQ>), dim3((unsigned)ceil_div(M, 256)), 256, 0, st, A, lda, B, ldb, C, ldc, M, N, nb, a_cols,
+                   alpha, bias);
+    return PVS_OK;
 }
 }  // namespace
 
@@ -103,9 +223,8 @@ int launch_gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, flo
                    cudaStream_t st)
 {
     if (M <= 0 || N <= 0) return PVS_OK;
-    dim3 grid((unsigned)ceil_div(M, G_BM), (unsigned)ceil_div(N, G_BN));
-    PVS_LAUNCH(gemm_nt_kernel, grid, 256, 0, st, A, lda, B, ldb, C, ldc, M, N, a_cols, square_cat, alpha, bias);
-    return PVS_OK;
+    return square_cat ? launch_gemm_nt_t<true>(A, lda, B, ldb, C, ldc, M, N, a_cols, alpha, bias, st)
+                      : launch_gemm_nt_t<false>(A, lda, B, ldb, C, ldc, M, N, a_cols, alpha, bias, st);
 }
 
 // =====================================================================================
