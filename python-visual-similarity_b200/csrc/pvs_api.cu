@@ -489,12 +489,14 @@ extern "C" int pvs_fv_encode(const pvs_model* g, const pvs_model* pca, const flo
             if (int rc = PVS_STAGE(ST_TC_FV_POSTERIOR, st, tc_fv_posterior(pl, g, y, total_rows, argmax_out, st, true))) return rc;
             if (int rc = PVS_STAGE(ST_TC_FV_STATS, st, tc_fv_stats(pl, g, y, offsets, n_images, st, true))) return rc;
         } else {
+            // the fp16x2 statistics kernel folds raw segment sums into S as well
+            if (pl.fp16x2) { raw1 = ldexpf(1.f, g->h_exp - 14); raw2 = ldexpf(1.f, 2 * g->h_exp - 14); }
             if (int rc = PVS_STAGE(ST_TC_FV_POSTERIOR, st, tc_fv_posterior(pl, g, y, total_rows, argmax_out, st))) return rc;
             if (int rc = PVS_STAGE(ST_TC_FV_STATS, st, tc_fv_stats(pl, g, y, offsets, n_images, st))) return rc;
         }
-        // the cluster kernel (the default) leaves raw segment-folded sums in S; every other kernel writes S / T
-        // (the gated 3xTF32 fallback overwrites S with S / T, so the raw scaling applies only while the range flag is down:
-        // fv_finalize reads the flag)
+        // the fp16x2 statistics kernel and the cluster kernel leave raw segment-folded sums in S; every other kernel writes
+        // S / T (the gated 3xTF32 fallback overwrites S with S / T, so the raw scaling applies only while the range flag is
+        // down: fv_finalize reads the flag)
         return PVS_STAGE(ST_FV_FINALIZE, st, launch_fv_finalize(pl.S, 2 * g->d, pl.s0part, TC_FV_S0_PARTS, offsets, g, n_images, power,
                                                                  norm_order, eps, out, st, raw1, raw2, pl.flag));
     }

@@ -363,6 +363,7 @@ struct Stats16Params {
     const float* rinv;                        // [rows + 16, 4]: per-descriptor softmax normaliser (slot 0 of 16 bytes)
     const int* flag;                          // != 0: operands out of fp16 range -> this kernel does nothing
     float sc_y, un1, un2;                     // 2^-e, 2^(e-14), 2^(2e-14)
+    int red;                                  // later segments are added to S with RED.ADD instead of load + add + store
 };
 
 // The posterior kernel leaves e' = 2^14 exp(l - max) split into two fp16 planes plus the per-descriptor
@@ -492,34 +493,47 @@ struct Stats16Policy {
         reinterpret_cast<float2*>(p.b.s0part + t.img * (int64_t)(TC_FV_S0_PARTS * FV_K))[e] =
             make_float2(st.s0.x * (1.f / 16384.f), st.s0.y * (1.f / 16384.f));
     }
-    // fold warps: add the finished segment to the image's S rows.  64 columns per round trip to L2 (the running sums of the
-    // earlier segments come back while the accumulator is read); the last segment applies the operand scales and 1 / T.
+    // fold warps: add the finished segment to the image's S rows.  S stays in raw operand units (fv_finalize applies the
+    // operand scales and 1 / T, like for the cluster kernel).  The first segment of an image stores; the later ones either
+    // go as fire-and-forget fp32 reductions (RED.ADD at L2: round to nearest, one owner thread per address and program
+    // order per address, so the sum is the same ((s0 + s1) + s2) ... as with the loads) or, PVS_FV_RED=0, as 64 loads per
+    // round trip to L2 that come back while the accumulator is read.
     __device__ static void fold(const Params& p, const Tile& t, uint32_t tmem, int quarter, int lane, FoldState&)
     {
         if (t.skip) return;                                // past the image's last segment
         const int e = quarter * 32 + lane;                 // operand row: [0,64) = y'^2, [64,128) = y'
         const int n = e < FV_D ? FV_D + e : e - FV_D;      // column in the [ s1 | s2 ] layout
         float* Simg = p.b.S + t.img * (int64_t)FV_K * FV_2D + n;
-        const float scale = t.last ? (e < FV_D ? p.un2 : p.un1) / (float)t.t : 1.f;   // undo the operand scales; T == 0 -> NaN below
-        const bool empty = t.t == 0;
+        const bool empty = t.t == 0;                       // T == 0: NaN, like the reference's division by zero
         const float nanv = __int_as_float(0x7fc00000);
+        if (t.first || p.red) {
+#pragma unroll 1
+            for (int c = 0; c < FV_K; c += 32) {
+                float v[32];
+                tmem_ld32(tmem + c, v);
+                tmem_ld_wait();
+                if (t.first) {
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) __stcg(Simg + (int64_t)(c + jj) * FV_2D, empty ? nanv : v[jj]);
+                } else {
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) atomicAdd(Simg + (int64_t)(c + jj) * FV_2D, v[jj]);
+                }
+            }
+            return;
+        }
 #pragma unroll 1
         for (int c = 0; c < FV_K; c += 64) {               // 64 running sums in flight per trip to L2, the accumulator in two halves
             float v[32], r[64];
-            if (!t.first) {
 #pragma unroll
-                for (int jj = 0; jj < 64; ++jj) r[jj] = __ldcg(Simg + (int64_t)(c + jj) * FV_2D);
-            }
+            for (int jj = 0; jj < 64; ++jj) r[jj] = __ldcg(Simg + (int64_t)(c + jj) * FV_2D);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 __syncwarp();
                 tmem_ld32(tmem + c + 32 * h, v);
                 tmem_ld_wait();
 #pragma unroll
-                for (int jj = 0; jj < 32; ++jj) {
-                    const float x = t.first ? v[jj] : v[jj] + r[32 * h + jj];
-                    __stcg(Simg + (int64_t)(c + 32 * h + jj) * FV_2D, empty ? nanv : x * scale);
-                }
+                for (int jj = 0; jj < 32; ++jj) __stcg(Simg + (int64_t)(c + 32 * h + jj) * FV_2D, v[jj] + r[32 * h + jj]);
             }
         }
     }
@@ -1298,6 +1312,8 @@ int tc_fv_stats(const TcFvPlan& pl, const pvs_model* g, const float* y, const in
     Stats16Params h{};
     h.b = p; h.flag = pl.flag; h.rinv = pl.rinv;
     h.sc_y = ldexpf(1.f, -g->h_exp); h.un1 = ldexpf(1.f, g->h_exp - 14); h.un2 = ldexpf(1.f, 2 * g->h_exp - 14);
+    h.red = 1;
+    if (const char* e = getenv("PVS_FV_RED")) h.red = atoi(e) != 0;
     const int64_t rows = pl.rows;
     int rc;
     if ((rc = make_tmap_2d(&h.qh_map, pl.q, true, rows, FV_K, FV_K, 64, Stats16Policy::KT))) return rc;

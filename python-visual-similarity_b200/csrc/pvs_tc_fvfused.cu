@@ -491,16 +491,17 @@ __global__ void __launch_bounds__(THREADS, 1) kernel(const __grid_constant__ Par
 
 using namespace tc;
 
-// PVS_FV_FUSED selects how posterior + statistics run.  Default 0: the posterior kernel and the statistics kernel
-// (pvs_tc_fv.cu), the statistics folded in segments of 256 descriptors -- on the full C2 batch the fastest variant that
-// keeps EVERY image inside the 1e-4 bar (658 k images/s, worst image 8.9e-5; table in DESIGN.md).  2: the 2-CTA cluster
-// kernel of pvs_tc_fvfused2.cu (Q never leaves the SM; same segment fold, but the fold sits on its softmax chain: 560-620 k
-// images/s, worst image 9.9e-5).  1: this file's single-CTA kernel (statistics of a whole image accumulated in the tensor
-// core: 712 k images/s but 58 of the 8 189 images 1e-4 .. 2.8e-4 off; kept as a reference for the tests only).
+// PVS_FV_FUSED selects how posterior + statistics run.  Default 2: the 2-CTA cluster kernel of pvs_tc_fvfused2.cu -- the
+// posteriors never leave the SM (2.3 MB of DRAM traffic per image instead of 7.1), the statistics are folded in segments of
+// 256 descriptors with fire-and-forget RED.ADDs: 746 k images/s on the full C2 batch, worst image 9.9e-5 from the CUDA-core
+// path (8.4e-5 from fp64).  0: the posterior kernel and the statistics kernel of pvs_tc_fv.cu with the same segments (693 k
+// images/s on the same box, worst image 8.9e-5); it also serves the calls that want the arg-max of the posteriors.
+// 1: this file's single-CTA kernel (statistics of a whole image accumulated in the tensor core: 712 k images/s but 58 of
+// the 8 189 images 1e-4 .. 2.8e-4 off; kept as a reference for the tests only).  Table in DESIGN.md.
 int tc_fv_fused_mode()
 {
     const char* e = getenv("PVS_FV_FUSED");
-    return !e ? 0 : (e[0] == '1' ? 1 : e[0] == '2' ? 2 : 0);
+    return !e ? 2 : (e[0] == '1' ? 1 : e[0] == '0' ? 0 : 2);
 }
 
 int tc_fv_poststats_fused(const TcFvPlan& pl, const pvs_model* g, const float* y, const int64_t* offsets, int64_t n_images,

@@ -53,6 +53,12 @@ __device__ unsigned long long g_ft[16];
 #endif
 
 constexpr int K = 256, CK = 128, D = 64, AUG = 128, TT = 128, QC = 64;
+#ifndef PVS_FOLD_HALVES
+#define PVS_FOLD_HALVES 1
+#endif
+// 1: the first warp of every lane quarter folds (it is ahead of its partner); 2: both fold 64 of the 128 columns each --
+// measured slower (0.949 against 0.929 of the two-kernel path's time): the second warp is the late one of the pair
+constexpr int FOLD_HALVES = PVS_FOLD_HALVES;
 constexpr int A1_BYTES = 65536, W_BYTES = 65536, Q_BYTES = 32768;
 constexpr int OFF_A1 = 0, OFF_W = 2 * A1_BYTES, OFF_Q = OFF_W + W_BYTES, OFF_BAR = OFF_Q + Q_BYTES;
 constexpr int OFF_XI = OFF_BAR + 256;          // intra-CTA exchange: [4 quarters][32 rows], one slot per warp pair
@@ -141,8 +147,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) kernel(c
         }
         mbar_init(s_full, 1);
         mbar_init(s_full2, 1);
-        mbar_init(&s_free[0], 4);                              // the four folding warps (one per lane quarter)
-        mbar_init(&s_free[1], 4);
+        mbar_init(&s_free[0], FOLD_HALVES * 4);                // the folding warps (FOLD_HALVES per lane quarter)
+        mbar_init(&s_free[1], FOLD_HALVES * 4);
         for (int i = 0; i < 4; ++i) {
             mbar_init(&q_full[i], 4);
             mbar_init(&q_empty[i], 1 + 4);
@@ -316,6 +322,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) kernel(c
         // would otherwise wait for its partner (which publishes the second chunk of a tile and runs about 2 k cycles behind).
         struct Rec { int64_t img; int tile, nt; uint32_t sg; bool valid; };
         Rec h1{0, 0, 0, 0, false}, h2{0, 0, 0, 0, false};     // tiles g - 1 and g - 2
+        const int fold_c0 = FOLD_HALVES == 2 ? 64 * half : 0, fold_c1 = FOLD_HALVES == 2 ? fold_c0 + 64 : CK;
         auto fold = [&](const Rec& t) {
             if (!t.valid || !(t.tile % SEG == SEG - 1 || t.tile == t.nt - 1)) return;
             const uint32_t sb = t.sg & 1;
@@ -325,20 +332,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) kernel(c
             float* Sp = p.S + t.img * (int64_t)(K * AUG) + (int64_t)(rank * CK) * AUG + col;
             const uint32_t ts = tmem_S + sb * CK + lane_off;
 #pragma unroll 1
-            for (int c = 0; c < CK; c += 32) {
-                float v[32], r[32];
-                if (!first) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) r[j] = __ldcg(Sp + (c + j) * AUG);
-                }
+            for (int c = fold_c0; c < fold_c1; c += 32) {
+                float v[32];
                 tmem_ld32(ts + c, v);
                 tmem_ld_wait();
-                if (!first) {
+                if (first) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] += r[j];
+                    for (int j = 0; j < 32; ++j) __stcg(Sp + (c + j) * AUG, v[j]);
+                } else {                                       // fire-and-forget RED.ADD at L2: nothing to wait for
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) atomicAdd(Sp + (c + j) * AUG, v[j]);
                 }
-#pragma unroll
-                for (int j = 0; j < 32; ++j) __stcg(Sp + (c + j) * AUG, v[j]);
             }
             tcgen05_fence_before();
             __syncwarp();
@@ -362,7 +366,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) kernel(c
                 // the segment that ended with tile g - 2 is complete (l_full(g) was committed after the statistics MMAs of tile
                 // g - 2): fold it while no logits are held in registers
                 FT0(t11f);
-                if (half == 0) fold(h2);
+                if (half < FOLD_HALVES) fold(h2);
                 FTA(11, t11f);
 
                 FT0(t5);
@@ -463,7 +467,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) kernel(c
             }
             FTA(11, t11);
         }
-        if (half == 0) { fold(h2); fold(h1); }
+        if (half < FOLD_HALVES) { fold(h2); fold(h1); }
 #ifdef PVS_TIMING
         FTA(12, t_all);
         if (warp == 2 && lane == 0 && rank == 0) for (int i = 4; i < 13; ++i) atomicAdd(&g_ft[i], (unsigned long long)ft[i]);

@@ -198,7 +198,7 @@ def test_fv_full_c2_batch_every_image_inside_the_bar(api):
     finally:
         api.nat.set_path(api.nat.PATH_AUTO)
     w, p = load_weights("gmm_k256_sift_pca"), load_weights("pca_k256_sift_f2")
-    for mode in (None, "2"):
+    for mode in (None, "0"):                                # the cluster kernel (default) and the two-kernel path
         if mode:
             os.environ["PVS_FV_FUSED"] = mode
         try:
