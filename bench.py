@@ -669,7 +669,7 @@ def run_ours(args):
             "stages_ms": {k: round(v[0] / max(prof_steps, 1), 4) for k, v in stages.items()},
             # algorithmic bytes of each stage / its single-stream time, as a fraction of the measured HBM peak
             "stages_hbm_frac": {k: round(bytes_per_image[k] * n_img / (v[0] / max(prof_steps, 1) / 1e3) / 1e9 / pk["hbm_gbs"], 4)
-                                for k, v in stages.items() if k in bytes_per_image and v[0] > 0},
+                                for k, v in stages.items() if k in bytes_per_image and v[0] > 0.02 * sum(w[0] for w in stages.values())},
             "cpu_baseline": cpu,
             "extra": extra,
             "clocks": clocks.summary(),
