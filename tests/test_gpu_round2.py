@@ -369,3 +369,35 @@ def test_fv_rootsift_pca_model_typical_descriptors(api):
           f"{per.median().item():.2e}; worst {worst} vs fp64 oracle: tensor {max(e_t):.2e}, CUDA cores {max(e_u):.2e}")
     assert torch.isfinite(a).all() and not torch.equal(a, u)
     assert per.max().item() <= 1e-4 and max(e_t) <= 1e-4 and max(e_u) <= 1e-4, (per.max().item(), e_t, e_u)
+
+
+def test_fv_empty_images_inside_a_batch(api):
+    """Descriptor-level entry with images of zero descriptors in the middle and at the end of a batch: the reference divides
+    by T = 0 (`fisher_vector.py:93,103`), i.e. an all-NaN row; every other row must be what it is without the empty
+    neighbours.  Cluster kernel (default) and the two-kernel path, two chunkings each."""
+    import os
+    rng = np.random.default_rng(5)
+    ts = [300, 0, 129, 0, 2000, 1, 0]
+    offs = np.concatenate([[0], np.cumsum(ts)]).astype(np.int64)
+    x = np.floor(np.clip(np.abs(rng.normal(0, 40, (int(offs[-1]), 128))), 0, 255)).astype(np.float32)
+    enc = api.enc.FisherVectorEncoder(feature_extractor=api.feat.Descriptors(128), weights=api.enc.GMMWeights.OXFORD102_K256_SIFT_PCA)
+    w, p = load_weights("gmm_k256_sift_pca"), load_weights("pca_k256_sift_f2")
+    live = [i for i, t in enumerate(ts) if t > 0]
+    ref = O.fv_encode([x[offs[i]:offs[i + 1]] for i in live], w["weights"], w["means"], w["covariances"], w["precisions_cholesky"],
+                      pca=(p["components"], p["mean"]))
+    xd, od = torch.from_numpy(x).cuda(), torch.from_numpy(offs)
+    assert "PVS_FV_FUSED" not in os.environ
+    for mode in (None, "0"):
+        if mode:
+            os.environ["PVS_FV_FUSED"] = mode
+        try:
+            a = enc.encode_descriptors(xd, od).cpu().numpy()
+            b = enc.encode_descriptors(xd, od, images_per_call=2).cpu().numpy()
+        finally:
+            os.environ.pop("PVS_FV_FUSED", None)
+        assert np.array_equal(a, b, equal_nan=True), mode
+        for i, t in enumerate(ts):
+            if t == 0:
+                assert np.isnan(a[i]).all(), (mode, i)
+        assert np.isfinite(a[live]).all()
+        assert max(rel_l2(a[i], ref[j]) for j, i in enumerate(live)) <= 1e-4, mode
