@@ -401,3 +401,31 @@ def test_fv_empty_images_inside_a_batch(api):
                 assert np.isnan(a[i]).all(), (mode, i)
         assert np.isfinite(a[live]).all()
         assert max(rel_l2(a[i], ref[j]) for j, i in enumerate(live)) <= 1e-4, mode
+
+
+def test_fv_long_images(api):
+    """Images far longer than the benchmark's 2 000 descriptors (40 001 and 12 345: hundreds of statistics segments per
+    image, odd and even counts, partial last tiles) next to short ones: cluster kernel (default) against the two-kernel
+    path and the fp64 oracle."""
+    import os
+    rng = np.random.default_rng(77)
+    ts = [40001, 5, 12345, 256]
+    offs = np.concatenate([[0], np.cumsum(ts)]).astype(np.int64)
+    x = np.floor(np.clip(np.abs(rng.normal(0, 40, (int(offs[-1]), 128))), 0, 255)).astype(np.float32)
+    enc = api.enc.FisherVectorEncoder(feature_extractor=api.feat.Descriptors(128), weights=api.enc.GMMWeights.OXFORD102_K256_SIFT_PCA)
+    w, p = load_weights("gmm_k256_sift_pca"), load_weights("pca_k256_sift_f2")
+    ref = O.fv_encode([x[offs[i]:offs[i + 1]] for i in range(len(ts))], w["weights"], w["means"], w["covariances"],
+                      w["precisions_cholesky"], pca=(p["components"], p["mean"]))
+    xd, od = torch.from_numpy(x).cuda(), torch.from_numpy(offs)
+    assert "PVS_FV_FUSED" not in os.environ
+    a = enc.encode_descriptors(xd, od).cpu().numpy()
+    os.environ["PVS_FV_FUSED"] = "0"
+    try:
+        b = enc.encode_descriptors(xd, od).cpu().numpy()
+    finally:
+        os.environ.pop("PVS_FV_FUSED", None)
+    e_a = [rel_l2(a[i], ref[i]) for i in range(len(ts))]
+    e_b = [rel_l2(b[i], ref[i]) for i in range(len(ts))]
+    print(f"\n[fv long images {ts}] vs fp64 oracle: cluster kernel {['%.1e' % e for e in e_a]}, two kernels {['%.1e' % e for e in e_b]}")
+    assert np.isfinite(a).all() and np.isfinite(b).all()
+    assert max(e_a) <= 1e-4 and max(e_b) <= 1e-4, (e_a, e_b)
