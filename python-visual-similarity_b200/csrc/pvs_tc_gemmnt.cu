@@ -134,16 +134,18 @@ struct GemmNtPolicy {
                     v[j] = p.alpha * v[j] + ((p.bias && col < p.n) ? p.bias[col] : 0.f);
                 }
             } else if (vec && col0 + 32 <= p.n) {
+                // later K-segments: fire-and-forget RED.ADD at L2 (round to nearest; this thread owns the row and its
+                // operations on one address keep program order, so the sum is the same as with load + add + store)
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 o = __ldcg(reinterpret_cast<const float4*>(crow + col0 + j));
-                    v[j] = fmaf(p.alpha, v[j], o.x); v[j + 1] = fmaf(p.alpha, v[j + 1], o.y);
-                    v[j + 2] = fmaf(p.alpha, v[j + 2], o.z); v[j + 3] = fmaf(p.alpha, v[j + 3], o.w);
-                }
+                for (int j = 0; j < 32; j += 4)
+                    atomicAdd(reinterpret_cast<float4*>(crow + col0 + j),
+                              make_float4(p.alpha * v[j], p.alpha * v[j + 1], p.alpha * v[j + 2], p.alpha * v[j + 3]));
+                continue;
             } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                    if (col0 + j < p.n) v[j] = fmaf(p.alpha, v[j], __ldcg(crow + col0 + j));
+                    if (col0 + j < p.n) atomicAdd(crow + col0 + j, p.alpha * v[j]);
+                continue;
             }
             if (vec && col0 + 32 <= p.n) {
 #pragma unroll
