@@ -491,14 +491,15 @@ extern "C" int pvs_fv_encode(const pvs_model* g, const pvs_model* pca, const flo
         } else {
             // the fp16x2 statistics kernel folds raw segment sums into S as well
             if (pl.fp16x2) { raw1 = ldexpf(1.f, g->h_exp - 14); raw2 = ldexpf(1.f, 2 * g->h_exp - 14); }
+            else raw1 = raw2 = 1.f;                          // 3xTF32 kernels only: raw sums in plain units
             if (int rc = PVS_STAGE(ST_TC_FV_POSTERIOR, st, tc_fv_posterior(pl, g, y, total_rows, argmax_out, st))) return rc;
             if (int rc = PVS_STAGE(ST_TC_FV_STATS, st, tc_fv_stats(pl, g, y, offsets, n_images, st))) return rc;
         }
-        // the fp16x2 statistics kernel and the cluster kernel leave raw segment-folded sums in S; every other kernel writes
-        // S / T (the gated 3xTF32 fallback overwrites S with S / T, so the raw scaling applies only while the range flag is
-        // down: fv_finalize reads the flag)
+        // every tensor statistics kernel leaves raw segment-folded sums in S, the fp16x2 ones in operand units (raw1, raw2),
+        // the 3xTF32 fallback behind the range flag in plain units (rawg = 1): fv_finalize reads the flag and applies the
+        // matching scale / T.  Only the single-CTA fused kernel (PVS_FV_FUSED=1) writes S / T (raw1 = 0).
         return PVS_STAGE(ST_FV_FINALIZE, st, launch_fv_finalize(pl.S, 2 * g->d, pl.s0part, TC_FV_S0_PARTS, offsets, g, n_images, power,
-                                                                 norm_order, eps, out, st, raw1, raw2, pl.flag));
+                                                                 norm_order, eps, out, st, raw1, raw2, pl.flag, 1.f));
     }
     PVS_CHECK(g_path.load() != PVS_PATH_TENSOR, PVS_ERR_UNSUPPORTED,
               "pvs_fv_encode: the tensor-core path handles K=256, D=64 (d_in %% 32 == 0) only");
@@ -525,7 +526,7 @@ extern "C" int pvs_fv_encode(const pvs_model* g, const pvs_model* pca, const flo
         float* s0part = (float*)(ws + w.s0);
         if (int rc = PVS_STAGE(ST_TC_FV_STATS, st, tc_fv_stats_generic(q, y, g->d, offsets, n_images, S, s0part, (int*)(ws + w.smax), st))) return rc;
         return PVS_STAGE(ST_FV_FINALIZE, st, launch_fv_finalize(S, 2 * g->d, s0part, TC_FV_S0_PARTS, offsets, g, n_images, power,
-                                                                 norm_order, eps, out, st));
+                                                                 norm_order, eps, out, st, 1.f, 1.f));   // raw sums, plain units
     }
     if (int rc = PVS_STAGE(ST_FV_STATS, st, launch_fv_stats(q, y, g->d, g->k, offsets, n_images, S, st))) return rc;
     return PVS_STAGE(ST_FV_FINALIZE, st, launch_fv_finalize(S, 2 * g->d + 1, nullptr, 0, offsets, g, n_images, power,

@@ -30,7 +30,8 @@ int launch_fv_stats(const float* q, const float* y, int d, int k, const int64_t*
 // raw partial sums per image in s0part [n_images, parts, k] that still need / T)
 int launch_fv_finalize(const float* S, int ld, const float* s0part, int parts, const int64_t* offsets,
                        const pvs_model* gmm, int64_t n_images, float power, float norm_order, float eps,
-                       float* out, cudaStream_t st, float raw1 = 0.f, float raw2 = 0.f, const int* raw_gate = nullptr);
+                       float* out, cudaStream_t st, float raw1 = 0.f, float raw2 = 0.f, const int* raw_gate = nullptr, float rawg = 0.f);
+// with *raw_gate != 0 the scales are (rawg, rawg) instead of (raw1, raw2); a scale of 0 means S is S / T already.
 // raw1 != 0 (and *raw_gate == 0 when a gate is given): S holds raw sums that still need raw1 / T (first-order columns), raw2 / T
 
 // ---- similarity / top-k --------------------------------------------------------------------

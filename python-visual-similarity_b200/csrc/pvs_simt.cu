@@ -710,7 +710,7 @@ fv_finalize_kernel(const float* __restrict__ S, int ld, const float* __restrict_
                    const float* __restrict__ var, const float* __restrict__ pi,
                    const float* __restrict__ g_pi, const float* __restrict__ g_mu,
                    const float* __restrict__ g_sig, float power, float ord, float eps,
-                   float* __restrict__ out, float raw1, float raw2, const int* __restrict__ raw_gate)
+                   float* __restrict__ out, float raw1, float raw2, const int* __restrict__ raw_gate, float rawg)
 {
     extern __shared__ float s0s[];                          // [k]
     __shared__ float red[32];
@@ -722,9 +722,12 @@ fv_finalize_kernel(const float* __restrict__ S, int ld, const float* __restrict_
     float* o = out + img * (int64_t)(2 * kd + k);
     // raw1 != 0: S holds raw sums in operand units (segment-folded by the fused kernel): first-order columns still need
     // raw1 / T, second-order columns raw2 / T -- unless the range flag went up and the 3xTF32 kernels wrote S / T instead
-    const bool raw = raw1 != 0.f && (!raw_gate || *raw_gate == 0);
-    const float f1 = raw ? raw1 / (float)(offsets[img + 1] - offsets[img]) : 1.f;
-    const float f2 = raw ? raw2 / (float)(offsets[img + 1] - offsets[img]) : 1.f;
+    // With the range flag up the 3xTF32 kernels wrote S instead: raw as well, in units of rawg (0 = already S / T).
+    const bool gated = raw_gate && *raw_gate != 0;
+    const float r1 = gated ? rawg : raw1, r2 = gated ? rawg : raw2;
+    const bool raw = r1 != 0.f;
+    const float f1 = raw ? r1 / (float)(offsets[img + 1] - offsets[img]) : 1.f;
+    const float f2 = raw ? r2 / (float)(offsets[img + 1] - offsets[img]) : 1.f;
     if (s0part) {
         const float inv_t = 1.f / (float)(offsets[img + 1] - offsets[img]);   // T == 0 -> inf -> NaN, as the reference
         for (int j = tid; j < k; j += nt) {
@@ -823,7 +826,7 @@ fv_finalize_k256_d64_kernel(const float* __restrict__ S, const float* __restrict
                             const float* __restrict__ var, const float* __restrict__ pi,
                             const float* __restrict__ g_pi, const float* __restrict__ g_mu,
                             const float* __restrict__ g_sig, float eps, float* __restrict__ out, float raw1, float raw2,
-                            const int* __restrict__ raw_gate)
+                            const int* __restrict__ raw_gate, float rawg)
 {
     constexpr int K = 256, D = 64, KD = K * D, NJ = 16;
     __shared__ float s0s[K];
@@ -845,9 +848,11 @@ fv_finalize_k256_d64_kernel(const float* __restrict__ S, const float* __restrict
         s1[it] = Simg[j * (2 * D) + dd];
         s2[it] = Simg[j * (2 * D) + D + dd];
     }
-    if (raw1 != 0.f && (!raw_gate || *raw_gate == 0)) {  // raw sums in operand units (see fv_finalize_kernel)
+    const bool gated = raw_gate && *raw_gate != 0;
+    const float r1 = gated ? rawg : raw1, r2 = gated ? rawg : raw2;
+    if (r1 != 0.f) {                                     // raw sums in operand units (see fv_finalize_kernel)
         const float inv_t = 1.f / (float)(offsets[img + 1] - offsets[img]);
-        const float f1 = raw1 * inv_t, f2 = raw2 * inv_t;
+        const float f1 = r1 * inv_t, f2 = r2 * inv_t;
 #pragma unroll
         for (int it = 0; it < NJ; ++it) { s1[it] *= f1; s2[it] *= f2; }
     }
@@ -908,19 +913,19 @@ int launch_fv_stats(const float* q, const float* y, int d, int k, const int64_t*
 
 int launch_fv_finalize(const float* S, int ld, const float* s0part, int parts, const int64_t* offsets,
                        const pvs_model* g, int64_t n_images, float power, float norm_order, float eps, float* out,
-                       cudaStream_t st, float raw1, float raw2, const int* raw_gate)
+                       cudaStream_t st, float raw1, float raw2, const int* raw_gate, float rawg)
 {
     if (n_images <= 0) return PVS_OK;
     PVS_CHECK(g->k <= 12000, PVS_ERR_UNSUPPORTED, "fv_finalize supports k <= 12000 (got %d)", g->k);
     if (power == 0.5f && norm_order == 2.f && g->k == 256 && g->d == 64 && ld == 128 && s0part)
         PVS_LAUNCH(fv_finalize_k256_d64_kernel, (unsigned)n_images, 1024, 0, st, S, s0part, parts, offsets, g->mu, g->var, g->pi,
-                   g->g_pi, g->g_mu, g->g_sig, eps, out, raw1, raw2, raw_gate);
+                   g->g_pi, g->g_mu, g->g_sig, eps, out, raw1, raw2, raw_gate, rawg);
     else if (power == 0.5f && norm_order == 2.f)
         PVS_LAUNCH(fv_finalize_kernel<true>, (unsigned)n_images, 1024, (size_t)g->k * sizeof(float), st, S, ld, s0part, parts, offsets, g->k, g->d,
-                   g->mu, g->var, g->pi, g->g_pi, g->g_mu, g->g_sig, power, norm_order, eps, out, raw1, raw2, raw_gate);
+                   g->mu, g->var, g->pi, g->g_pi, g->g_mu, g->g_sig, power, norm_order, eps, out, raw1, raw2, raw_gate, rawg);
     else
         PVS_LAUNCH(fv_finalize_kernel<false>, (unsigned)n_images, 1024, (size_t)g->k * sizeof(float), st, S, ld, s0part, parts, offsets, g->k, g->d,
-                   g->mu, g->var, g->pi, g->g_pi, g->g_mu, g->g_sig, power, norm_order, eps, out, raw1, raw2, raw_gate);
+                   g->mu, g->var, g->pi, g->g_pi, g->g_mu, g->g_sig, power, norm_order, eps, out, raw1, raw2, raw_gate, rawg);
     return PVS_OK;
 }
 

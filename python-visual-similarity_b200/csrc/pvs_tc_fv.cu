@@ -218,27 +218,26 @@ __device__ __forceinline__ SegTile seg_tile(const StatsParams& p, int i, int kt)
     tl.skip = seg > 0 && left <= 0;
     return tl;
 }
-// fold of a finished segment by one warp (its TMEM lane quarter): 32 running sums per trip to L2
-__device__ __forceinline__ void seg_fold(const SegTile& t, float* Srow, uint32_t tmem, float scale, int64_t ld = FV_2D, bool live = true)
+// fold of a finished segment by one warp (its TMEM lane quarter).  S keeps RAW sums (fv_finalize applies 1 / T, exactly the
+// multiply the last segment used to apply here); the first segment is stored (NaN for T == 0, like the reference), the later
+// ones are added with fire-and-forget RED.ADDs at L2 (round to nearest; one owner thread per address, program order per
+// address: a fixed summation order)
+__device__ __forceinline__ void seg_fold(const SegTile& t, float* Srow, uint32_t tmem, int64_t ld = FV_2D, bool live = true)
 {
     const bool empty = t.t == 0;
     const float nanv = __int_as_float(0x7fc00000);
 #pragma unroll 1
     for (int c = 0; c < FV_K; c += 32) {
-        float v[32], r[32];
-        if (!t.first && live) {
-#pragma unroll
-            for (int jj = 0; jj < 32; ++jj) r[jj] = __ldcg(Srow + (int64_t)(c + jj) * ld);
-        }
-        __syncwarp();
+        float v[32];
         tmem_ld32(tmem + c, v);
         tmem_ld_wait();
-        if (live) {
+        if (!live) continue;
+        if (t.first) {
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) {
-                const float x = t.first ? v[jj] : v[jj] + r[jj];
-                __stcg(Srow + (int64_t)(c + jj) * ld, empty ? nanv : x * scale);
-            }
+            for (int jj = 0; jj < 32; ++jj) __stcg(Srow + (int64_t)(c + jj) * ld, empty ? nanv : v[jj]);
+        } else {
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) atomicAdd(Srow + (int64_t)(c + jj) * ld, v[jj]);
         }
     }
 }
@@ -340,8 +339,8 @@ struct StatsPolicy {
         const int e = quarter * 32 + lane;                 // operand row: [0,64) = y*y, [64,128) = y
         const int n = e < FV_D ? FV_D + e : e - FV_D;      // column in the [ s1 | s2 ] layout
         // the epilogue warps have nothing else to do here (the producers take the zeroth-order sums), so they fold;
-        // the last segment applies 1 / T (T == 0 -> NaN, like the reference)
-        seg_fold(t, p.S + t.img * (int64_t)FV_K * FV_2D + n, tmem, t.last ? 1.f / (float)t.t : 1.f);
+        // S stays raw: fv_finalize applies 1 / T
+        seg_fold(t, p.S + t.img * (int64_t)FV_K * FV_2D + n, tmem);
     }
 };
 
@@ -687,8 +686,8 @@ struct StatsGenPolicy {
         const int a = t.mt * 128 + quarter * 32 + lane;    // augmented column owned by this thread
         const int ld = 2 * p.d;
         const int col = a < p.d ? p.d + a : a - p.d;       // [ s1 | s2 ] layout
-        // fold of the segment (the epilogue warps are otherwise idle); the last one applies 1 / T (T == 0 -> NaN)
-        seg_fold(t, p.S + t.img * (int64_t)FV_K * ld + col, tmem, t.last ? 1.f / (float)t.t : 1.f, ld, a < ld);
+        // fold of the segment (the epilogue warps are otherwise idle); S stays raw, fv_finalize applies 1 / T
+        seg_fold(t, p.S + t.img * (int64_t)FV_K * ld + col, tmem, ld, a < ld);
     }
 };
 
